@@ -1,0 +1,126 @@
+/*
+ * dsoft.h - C ABI of the B200-native DINO-Soft loss path (libdsoft.so).
+ *
+ * The reference (nickxir12/Refining-CLIP-via-Dinov2-representations) is pure Python; the interface this
+ * library sits under is the loss module `ClipLossWithDINOEnhancements`
+ * (reference src/open_clip/loss.py:190-607) together with `gather_features` (loss.py:23-81) and
+ * `compute_student_tau` (loss.py:166-175).  The Python mirror of that module
+ * (refining-clip-via-dinov2-representations_b200/loss.py) binds these symbols through ctypes; see
+ * INTEGRATION.md for the stub.
+ *
+ * Conventions
+ *   - every pointer named *_dev is a CUDA device pointer on the current device;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered and host-sync free;
+ *   - functions return 0 on success, a cudaError_t value (>0) or a DSOFT_E* code (<0) on failure;
+ *     dsoft_last_error() gives the message for the calling thread;
+ *   - there is no CPU path: calls fail with DSOFT_ENODEV when the device is not sm_100.
+ */
+#ifndef DSOFT_H_
+#define DSOFT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSOFT_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define DSOFT_EINVAL (-1)  /* bad argument / unsupported shape            */
+#define DSOFT_ENODEV (-2)  /* no sm_100 device / driver entry point missing */
+#define DSOFT_ETMA (-3)    /* cuTensorMapEncodeTiled failed               */
+
+/* dsoft_shape_t.flags */
+#define DSOFT_F_SOFT 1u        /* image-image KL-teacher term enabled (loss.py:356-384)            */
+#define DSOFT_F_TEXT 2u        /* text-text KL term enabled (loss.py:387-397)                      */
+#define DSOFT_F_SOFT_LOCAL 4u  /* soft terms over the local b x b block only (reference at W>1)    */
+#define DSOFT_F_ROW_ONLY 8u    /* gather_with_grad=False: gathered columns carry no gradient       */
+
+/* element types accepted by dsoft_pack */
+#define DSOFT_DT_F32 0
+#define DSOFT_DT_BF16 1
+#define DSOFT_DT_F16 2
+
+/* Problem description. b = local batch, B = world*b = global batch.
+ * Replaces the shape information the reference reads off its tensors in
+ * ClipLossWithDINOEnhancements.forward (loss.py:301-302, 324-325). */
+typedef struct dsoft_shape {
+  int32_t b;      /* local rows per rank                                            */
+  int32_t world;  /* world size W                                                   */
+  int32_t rank;   /* this rank                                                      */
+  int32_t D;      /* CLIP embedding dim (image and text), multiple of 8             */
+  int32_t Dp;     /* student dim after the projection head; 0 = no projection       */
+  int32_t Dd;     /* DINO feature dim; 0 = no DINO features                         */
+  uint32_t flags; /* DSOFT_F_*                                                      */
+  float teacher_temp; /* tau_t  (loss.py:368)                                       */
+  float text_temp;    /* tau_txt (loss.py:391)                                      */
+} dsoft_shape_t;
+
+typedef struct dsoft_plan dsoft_plan_t; /* opaque: packed layout, tile/split schedule, workspace map */
+
+int dsoft_version(void);
+const char* dsoft_last_error(void);
+
+/* Plan life cycle (host only; no device work). */
+int dsoft_plan_create(const dsoft_shape_t* shape, dsoft_plan_t** out);
+void dsoft_plan_destroy(dsoft_plan_t* plan);
+
+/* Sizes the caller must allocate (device memory):
+ *   gathered : [B, row_elems] bf16 - packed image|text|student|dino embeddings of all ranks; the local
+ *              block (rows rank*b ..) is written by dsoft_pack, the rest by the caller's all-gather
+ *              (this is the buffer `gather_features` loss.py:23-81 would have produced, in bf16);
+ *   state    : small per-call state that must survive from forward to backward;
+ *   scratch  : partial statistics / partial gradients, free to reuse after each call. */
+size_t dsoft_plan_gathered_row_elems(const dsoft_plan_t* plan);
+size_t dsoft_plan_gathered_bytes(const dsoft_plan_t* plan);
+size_t dsoft_plan_state_bytes(const dsoft_plan_t* plan);
+size_t dsoft_plan_scratch_bytes(const dsoft_plan_t* plan);
+/* Algorithmic FLOPs of one fwd+bwd evaluation for this rank (SURVEY.md 8(d) formula / world). */
+double dsoft_plan_algorithmic_flops(const dsoft_plan_t* plan);
+/* Number of CUDA kernels dsoft_forward / dsoft_backward launch (for bench.py's gpu_launches). */
+int dsoft_plan_launches_forward(const dsoft_plan_t* plan);
+int dsoft_plan_launches_backward(const dsoft_plan_t* plan);
+
+/* Round the local embeddings to bf16 and write them into rows [rank*b, rank*b+b) of `gathered`.
+ * student_dev may be NULL when Dp == 0; dino_dev may be NULL when Dd == 0.  ld* are row strides in
+ * elements.  Replaces the operand preparation of loss.py:313, 330-347, 358-359, 392. */
+int dsoft_pack(const dsoft_plan_t* plan, const void* image_dev, int image_dtype, int64_t ld_image,
+               const void* text_dev, int text_dtype, int64_t ld_text, const void* student_dev,
+               int student_dtype, int64_t ld_student, const void* dino_dev, int dino_dtype,
+               int64_t ld_dino, void* gathered_dev, void* stream);
+
+/* Forward statistics pass.  logit_scale_dev: one fp32 (already exp'd, reference model.py:571).
+ * Outputs: lse_local_dev [5][b] fp32 (log2-domain row log-sum-exps: clip i->t, clip t->i, teacher,
+ * student, text) and losses_dev[3] = {classic_loss, soft_imgimg, soft_texttext} (loss.py:317-319,
+ * 383, 396), each already divided by b. */
+int dsoft_forward(const dsoft_plan_t* plan, const void* gathered_dev, const float* logit_scale_dev,
+                  void* state_dev, void* scratch_dev, float* lse_local_dev, float* losses_dev,
+                  void* stream);
+
+/* Backward pass.  lse_all_dev [world][5][b] = all ranks' lse_local (all-gathered by the caller when
+ * world > 1).  gout_dev[3] = upstream gradients of the three forward outputs.  Outputs (fp32):
+ * d_image [b][D], d_text [b][D], d_student [b][Dp] (ignored when Dp == 0), d_logit_scale [1].
+ * Gradients follow the reference's per-rank convention (sum over ranks' losses == W x gradient of the
+ * global mean loss; SURVEY.md "Gradient scaling"). */
+int dsoft_backward(const dsoft_plan_t* plan, const void* gathered_dev, const void* state_dev,
+                   void* scratch_dev, const float* lse_all_dev, const float* gout_dev,
+                   float* d_image_dev, float* d_text_dev, float* d_student_dev,
+                   float* d_logit_scale_dev, void* stream);
+
+/* Test / bring-up helper: C[M][N] (fp32) = A[M][K] . B[N][K]^T with bf16 operands through the same
+ * TMA + tcgen05 tile path the loss kernels use (128 x 128 tiles). */
+int dsoft_selftest_gemm(const void* a_bf16_dev, const void* b_bf16_dev, float* c_dev, int M, int N,
+                        int K, void* stream);
+
+/* Test / bring-up helper: out[M][F] (fp32) = bf16(A . B^T) . V with A [M][K], B [N][K], V [N][F] bf16:
+ * the backward data path (tile -> bf16 G tile in swizzled shared memory -> second tcgen05 GEMM with an
+ * MN-major operand) without any soft-max arithmetic. */
+int dsoft_selftest_chain(const void* a_bf16_dev, const void* b_bf16_dev, const void* v_bf16_dev,
+                         float* out_dev, int M, int N, int K, int F, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSOFT_H_ */

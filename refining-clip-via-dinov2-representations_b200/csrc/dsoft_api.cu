@@ -1,0 +1,951 @@
+// C ABI of libdsoft.so (see include/dsoft.h): plan/schedule, TMA descriptor construction, the small
+// memory-bound helper kernels (pack, norms, scalars, finalize) and the launches of the tcgen05 tile
+// kernels in dsoft_kernels.cuh.
+#include "../../include/dsoft.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "dsoft_kernels.cuh"
+
+using namespace dsoft;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess)                                                                \
+      return fail(static_cast<int>(e__), "%s failed: %s (%s:%d)", #expr,                   \
+                  cudaGetErrorString(e__), __FILE__, __LINE__);                            \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+struct SplitPlan {
+  int nsplit = 1;
+  int tps = 1;  // tiles per split
+};
+
+struct dsoft_plan {
+  dsoft_shape_t sh;
+  int B;           // global batch
+  int Bcol;        // padded length of per-column fp32 vectors
+  int have_soft, have_text, have_proj, soft_local, row_only;
+  int Dz;          // student width (Dp or D)
+  // packed row layout (elements)
+  int offI, offT, offZ, offD, row_elems;
+  int num_sms;
+  // column scopes
+  int ntiles_g;               // clip / global scope
+  int s_col0, s_ncols, ntiles_s;  // soft scope
+  SplitPlan f_clip, f_soft, b_clip, b_stu, b_txt;
+  int nch_clip, nch_stu, nch_txt;
+  // state layout (float offsets)
+  size_t st_scal, st_rinv_t, st_rinv_z, st_rinv_d, st_diag, st_lsecols, st_total;
+  // scratch layout (float offsets)
+  size_t sc_pc_it, sc_pc_ti, sc_ps, sc_rowloss, sc_acc1, sc_acc2, sc_acc3, sc_acc4, sc_ds1, sc_ds2,
+      sc_dsrow, sc_total;
+};
+
+static int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Choose the column split so that (row blocks x splits x chunks) CTAs fill the SMs in whole waves.
+// cost ~ waves x (tiles per CTA + fixed prologue/drain overhead expressed in tiles).
+static SplitPlan choose_split(int row_blocks, int nchunk, int ntiles, int num_sms) {
+  SplitPlan best;
+  double best_cost = 1e300;
+  const int max_split = std::min(ntiles, 64);
+  for (int ns = 1; ns <= max_split; ++ns) {
+    const int tps = ceil_div(ntiles, ns);
+    const int ns_eff = ceil_div(ntiles, tps);
+    const long ctas = static_cast<long>(row_blocks) * nchunk * ns_eff;
+    const long waves = (ctas + num_sms - 1) / num_sms;
+    const double cost = static_cast<double>(waves) * (tps + 1.5);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best.nsplit = ns_eff;
+      best.tps = tps;
+    }
+  }
+  return best;
+}
+
+extern "C" int dsoft_version(void) { return DSOFT_VERSION; }
+extern "C" const char* dsoft_last_error(void) { return g_err; }
+
+static int query_num_sms(int* out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(DSOFT_ENODEV, "cudaGetDevice: %s", cudaGetErrorString(e));
+  int major = 0, sms = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (major != 10)
+    return fail(DSOFT_ENODEV, "libdsoft needs an sm_100 (B200) device, found compute capability %d.x",
+                major);
+  *out = sms;
+  return 0;
+}
+
+extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
+  if (!sh || !out) return fail(DSOFT_EINVAL, "null argument");
+  if (sh->b <= 0 || sh->world <= 0 || sh->rank < 0 || sh->rank >= sh->world)
+    return fail(DSOFT_EINVAL, "bad b/world/rank (%d/%d/%d)", sh->b, sh->world, sh->rank);
+  if (sh->D <= 0 || sh->D % 8 || sh->Dp < 0 || sh->Dp % 8 || sh->Dd < 0 || sh->Dd % 8)
+    return fail(DSOFT_EINVAL, "feature dims must be positive multiples of 8 (D=%d Dp=%d Dd=%d)", sh->D,
+                sh->Dp, sh->Dd);
+  if (sh->world > 1 && sh->b % 8)
+    return fail(DSOFT_EINVAL, "local batch must be a multiple of 8 when world > 1 (b=%d)", sh->b);
+  const bool soft = (sh->flags & DSOFT_F_SOFT) != 0;
+  if (soft && sh->Dd == 0) return fail(DSOFT_EINVAL, "DSOFT_F_SOFT needs Dd > 0");
+  if ((sh->flags & DSOFT_F_TEXT) && !soft) return fail(DSOFT_EINVAL, "DSOFT_F_TEXT needs DSOFT_F_SOFT");
+  if (soft && !(sh->teacher_temp > 0.f)) return fail(DSOFT_EINVAL, "teacher_temp must be > 0");
+  if ((sh->flags & DSOFT_F_TEXT) && !(sh->text_temp > 0.f))
+    return fail(DSOFT_EINVAL, "text_temp must be > 0");
+  if (static_cast<long>(sh->b) * sh->world > (1L << 30)) return fail(DSOFT_EINVAL, "batch too large");
+
+  int sms = 0;
+  int rc = query_num_sms(&sms);
+  if (rc) return rc;
+
+  dsoft_plan* p = new (std::nothrow) dsoft_plan();
+  if (!p) return fail(DSOFT_EINVAL, "out of host memory");
+  p->sh = *sh;
+  p->num_sms = sms;
+  p->B = sh->b * sh->world;
+  p->Bcol = ceil_div(p->B, BN) * BN + BN;
+  p->have_soft = soft;
+  p->have_text = (sh->flags & DSOFT_F_TEXT) != 0;
+  p->have_proj = soft && sh->Dp > 0;
+  p->soft_local = (sh->flags & DSOFT_F_SOFT_LOCAL) != 0 && sh->world > 1;
+  p->row_only = (sh->flags & DSOFT_F_ROW_ONLY) != 0 && sh->world > 1;
+  p->Dz = p->have_proj ? sh->Dp : sh->D;
+
+  p->offI = 0;
+  p->offT = sh->D;
+  p->offZ = p->have_proj ? 2 * sh->D : 0;
+  p->offD = 2 * sh->D + (p->have_proj ? sh->Dp : 0);
+  p->row_elems = p->offD + (soft ? sh->Dd : 0);
+
+  const int rbs = ceil_div(sh->b, BM);
+  p->ntiles_g = ceil_div(p->B, BN);
+  p->s_col0 = p->soft_local ? sh->rank * sh->b : 0;
+  p->s_ncols = p->soft_local ? sh->b : p->B;
+  p->ntiles_s = ceil_div(p->s_ncols, BN);
+  p->nch_clip = ceil_div(sh->D, CHUNK_F);
+  p->nch_stu = ceil_div(p->Dz, CHUNK_F);
+  p->nch_txt = ceil_div(sh->D, CHUNK_F);
+  p->f_clip = choose_split(rbs, 1, p->ntiles_g, sms);
+  p->f_soft = choose_split(rbs, 1, p->ntiles_s, sms);
+  p->b_clip = choose_split(rbs, p->nch_clip, p->ntiles_g, sms);
+  p->b_stu = choose_split(rbs, p->nch_stu, p->ntiles_s, sms);
+  p->b_txt = choose_split(rbs, p->nch_txt, p->ntiles_s, sms);
+
+  // ---- state (floats)
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o = align_up(o + n, 64); return r; };
+  p->st_scal = take(SC_COUNT);
+  p->st_rinv_t = take(p->Bcol);
+  p->st_rinv_z = take(p->Bcol);
+  p->st_rinv_d = take(p->Bcol);
+  p->st_diag = take(sh->b);
+  p->st_lsecols = take(static_cast<size_t>(5) * p->Bcol);
+  p->st_total = o;
+
+  // ---- scratch (floats)
+  o = 0;
+  const size_t b = sh->b;
+  p->sc_pc_it = take(2 * 2 * p->f_clip.nsplit * b);
+  p->sc_pc_ti = take(2 * 2 * p->f_clip.nsplit * b);
+  p->sc_ps = take(soft ? 7 * 2 * p->f_soft.nsplit * b : 0);
+  p->sc_rowloss = take(3 * b);
+  p->sc_acc1 = take(static_cast<size_t>(p->b_clip.nsplit) * b * sh->D);
+  p->sc_acc2 = take(static_cast<size_t>(p->b_clip.nsplit) * b * sh->D);
+  p->sc_acc3 = take(soft ? static_cast<size_t>(p->b_stu.nsplit) * b * p->Dz : 0);
+  p->sc_acc4 = take(p->have_text ? static_cast<size_t>(p->b_txt.nsplit) * b * sh->D : 0);
+  p->sc_ds1 = take(2 * p->b_clip.nsplit * b);
+  p->sc_ds2 = take(2 * p->b_clip.nsplit * b);
+  p->sc_dsrow = take(b);
+  p->sc_total = o;
+
+  *out = p;
+  return 0;
+}
+
+extern "C" void dsoft_plan_destroy(dsoft_plan_t* plan) { delete plan; }
+
+extern "C" size_t dsoft_plan_gathered_row_elems(const dsoft_plan_t* p) { return p ? p->row_elems : 0; }
+extern "C" size_t dsoft_plan_gathered_bytes(const dsoft_plan_t* p) {
+  return p ? static_cast<size_t>(p->B) * p->row_elems * 2 : 0;
+}
+extern "C" size_t dsoft_plan_state_bytes(const dsoft_plan_t* p) { return p ? p->st_total * 4 : 0; }
+extern "C" size_t dsoft_plan_scratch_bytes(const dsoft_plan_t* p) { return p ? p->sc_total * 4 : 0; }
+
+extern "C" double dsoft_plan_algorithmic_flops(const dsoft_plan_t* p) {
+  if (!p) return 0.0;
+  // F_alg = 2 B^2 (3D + 2Dp + Dd [+ 2D]) for the whole job; this rank's share is 1/W.
+  const double b = p->sh.b, cols_c = p->B, cols_s = p->s_ncols;
+  double f = 2.0 * b * cols_c * (3.0 * p->sh.D);
+  if (p->have_soft) f += 2.0 * b * cols_s * (2.0 * p->Dz + p->sh.Dd);
+  if (p->have_text) f += 2.0 * b * cols_s * (2.0 * p->sh.D);
+  return f;
+}
+extern "C" int dsoft_plan_launches_forward(const dsoft_plan_t* p) {
+  if (!p) return 0;
+  return 1 /*scalars*/ + (p->have_soft ? 3 : 1) /*norms*/ + 2 /*clip x2*/ + (p->have_soft ? 1 : 0) +
+         2 /*finalize, reduce*/;
+}
+extern "C" int dsoft_plan_launches_backward(const dsoft_plan_t* p) {
+  if (!p) return 0;
+  return 1 /*relayout*/ + 2 /*clip x2*/ + (p->have_soft ? 1 : 0) + (p->have_text ? 1 : 0) +
+         2 /*finalize, ds reduce*/;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA descriptors
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// bf16 matrix [rows][cols] with row pitch `pitch_elems`; box = 64 columns x 128 rows, 128B swizzle.
+static int make_map(CUtensorMap* map, const void* base, int rows, int cols, size_t pitch_elems) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(DSOFT_ENODEV, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(pitch_elems) * 2};
+  cuuint32_t box[2] = {BK, BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(DSOFT_ETMA, "cuTensorMapEncodeTiled failed (%d) base=%p rows=%d cols=%d pitch=%zu",
+                static_cast<int>(r), base, rows, cols, pitch_elems);
+  return 0;
+}
+
+static int make_maps(const dsoft_plan* p, const void* gathered, TileMaps* tm) {
+  const __nv_bfloat16* g = static_cast<const __nv_bfloat16*>(gathered);
+  if (reinterpret_cast<uintptr_t>(g) % 16) return fail(DSOFT_EINVAL, "gathered buffer must be 16-byte aligned");
+  int rc;
+  if ((rc = make_map(&tm->m[0], g + p->offI, p->B, p->sh.D, p->row_elems))) return rc;
+  if ((rc = make_map(&tm->m[1], g + p->offT, p->B, p->sh.D, p->row_elems))) return rc;
+  if ((rc = make_map(&tm->m[2], g + p->offZ, p->B, p->Dz, p->row_elems))) return rc;
+  if (p->have_soft) {
+    if ((rc = make_map(&tm->m[3], g + p->offD, p->B, p->sh.Dd, p->row_elems))) return rc;
+  } else {
+    tm->m[3] = tm->m[0];
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// helper kernels (memory bound, tiny next to the tile kernels)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float to_f32(T x);
+template <>
+__device__ __forceinline__ float to_f32<float>(float x) { return x; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 x) { return __bfloat162float(x); }
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half x) { return __half2float(x); }
+
+// src [rows][cols] (any float type, row stride ld) -> bf16 dst rows (row stride dst_ld)
+template <typename T>
+__global__ void pack_rows_kernel(const T* __restrict__ src, int64_t ld, __nv_bfloat16* __restrict__ dst,
+                                 int64_t dst_ld, int rows, int cols) {
+  const int64_t total = static_cast<int64_t>(rows) * (cols / 2);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / (cols / 2));
+    const int c = static_cast<int>(i % (cols / 2)) * 2;
+    const float x0 = to_f32<T>(src[r * ld + c]);
+    const float x1 = to_f32<T>(src[r * ld + c + 1]);
+    *reinterpret_cast<__nv_bfloat162*>(dst + r * dst_ld + c) = __floats2bfloat162_rn(x0, x1);
+  }
+}
+
+// one warp per row: out[r] = 1 / max(||row||, 1e-12)  (F.normalize eps, loss.py:345-359, 392)
+__global__ void rinv_kernel(const __nv_bfloat16* __restrict__ mat, int64_t ld, int rows, int cols,
+                            float* __restrict__ out, int out_len) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= out_len) return;
+  if (r >= rows) {
+    if (lane == 0) out[r] = 0.f;
+    return;
+  }
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(mat + r * ld);
+  float acc = 0.f;
+  for (int c = lane; c < cols / 2; c += 32) {
+    const float2 f = __bfloat1622float2(p[c]);
+    acc = fmaf(f.x, f.x, acc);
+    acc = fmaf(f.y, f.y, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[r] = 1.f / fmaxf(sqrtf(acc), 1e-12f);
+}
+
+// compute_student_tau (loss.py:166-175) + temperature reciprocals, all on device
+__global__ void prep_scalars_kernel(const float* __restrict__ logit_scale, float teacher_temp,
+                                    float text_temp, float* __restrict__ scal) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float L2E = 1.4426950408889634f;
+  const float s = *logit_scale;
+  float mult = (s > 10.f) ? s : expf(s);
+  mult = fminf(mult, 100.f);
+  float tau_s = 1.f / mult;
+  tau_s = fminf(fmaxf(tau_s, 0.008f), 0.02f);
+  scal[SC_SCALE] = s;
+  scal[SC_SCALE_L2] = s * L2E;
+  scal[SC_ITS] = 1.f / tau_s;
+  scal[SC_ITS_L2] = L2E / tau_s;
+  scal[SC_ITT] = teacher_temp > 0.f ? 1.f / teacher_temp : 0.f;
+  scal[SC_ITT_L2] = teacher_temp > 0.f ? L2E / teacher_temp : 0.f;
+  scal[SC_ITX] = text_temp > 0.f ? 1.f / text_temp : 0.f;
+  scal[SC_ITX_L2] = text_temp > 0.f ? L2E / text_temp : 0.f;
+}
+
+struct FinFwdArgs {
+  int b, np_c, np_s, have_soft, have_text;
+  const float* pc_it;  // [2][np_c][b]
+  const float* pc_ti;
+  const float* ps;     // [7][np_s][b]
+  const float* diag;
+  const float* scal;
+  float* lse;      // [5][b]
+  float* rowloss;  // [3][b]
+};
+
+__device__ __forceinline__ float combine_lse2(const float* part, int np, int b, int i) {
+  float m = M_FLOOR;
+  for (int k = 0; k < np; ++k) m = fmaxf(m, part[k * b + i]);
+  float s = 0.f;
+  for (int k = 0; k < np; ++k) s += part[(np + k) * b + i] * exp2f(part[k * b + i] - m);
+  return m + log2f(s);
+}
+
+// per-row combination of the column-split partial statistics -> LSEs (log2 domain) and row losses
+__global__ void finalize_fwd_kernel(FinFwdArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.b) return;
+  const float LN2 = 0.6931471805599453f;
+  const float l_it = combine_lse2(a.pc_it, a.np_c, a.b, i);
+  const float l_ti = combine_lse2(a.pc_ti, a.np_c, a.b, i);
+  a.lse[0 * a.b + i] = l_it;
+  a.lse[1 * a.b + i] = l_ti;
+  // classic CE row term (loss.py:317-319): lse_it - L_ii + lse_ti - L_ii
+  a.rowloss[0 * a.b + i] = LN2 * (l_it + l_ti) - 2.f * a.scal[SC_SCALE] * a.diag[i];
+  float l_t = 0.f, l_s = 0.f, l_x = 0.f, kl_s = 0.f, kl_x = 0.f;
+  if (a.have_soft) {
+    const int st = a.np_s * a.b;
+    float m = M_FLOOR;
+    for (int k = 0; k < a.np_s; ++k) m = fmaxf(m, a.ps[0 * st + k * a.b + i]);
+    float zt = 0.f, aq = 0.f, ap = 0.f, ar = 0.f, zs = 0.f, zx = 0.f;
+    for (int k = 0; k < a.np_s; ++k) {
+      const int o = k * a.b + i;
+      const float sc = exp2f(a.ps[0 * st + o] - m);
+      zt += a.ps[1 * st + o] * sc;
+      aq += a.ps[2 * st + o] * sc;
+      ap += a.ps[3 * st + o] * sc;
+      ar += a.ps[4 * st + o] * sc;
+      zs += a.ps[5 * st + o];
+      zx += a.ps[6 * st + o];
+    }
+    l_t = m + log2f(zt);
+    l_s = a.scal[SC_ITS_L2] + log2f(zs);
+    // KL(q || p) = E_q[q2 - p2] - lse_t + lse_s   (log2 units -> nats), loss.py:380-383
+    kl_s = LN2 * ((aq - ap) / zt - l_t + l_s);
+    if (a.have_text) {
+      l_x = a.scal[SC_ITX_L2] + log2f(zx);
+      kl_x = LN2 * ((aq - ar) / zt - l_t + l_x);
+    }
+  }
+  a.lse[2 * a.b + i] = l_t;
+  a.lse[3 * a.b + i] = l_s;
+  a.lse[4 * a.b + i] = l_x;
+  a.rowloss[1 * a.b + i] = kl_s;
+  a.rowloss[2 * a.b + i] = kl_x;
+}
+
+// deterministic single-block reduction: out[k] = scale[k] * sum_i in[k][i]
+__global__ void reduce_rows_kernel(const float* __restrict__ in, int b, int nk, float s0, float s1,
+                                   float s2, float* __restrict__ out) {
+  __shared__ double sh[32];
+  for (int k = 0; k < nk; ++k) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < b; i += blockDim.x) acc += static_cast<double>(in[k * b + i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      double v = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (threadIdx.x == 0) out[k] = static_cast<float>(v * (k == 0 ? s0 : (k == 1 ? s1 : s2)));
+    }
+    __syncthreads();
+  }
+}
+
+// [W][5][b] (rank-major, as all-gathered) -> [5][Bcol] indexed by global column, zero padded
+__global__ void lse_relayout_kernel(const float* __restrict__ lse_all, int W, int b, int Bcol,
+                                    float* __restrict__ out) {
+  const int total = 5 * Bcol;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i / Bcol, j = i % Bcol;
+    float v = 0.f;
+    if (j < W * b) v = lse_all[(static_cast<size_t>(j / b) * 5 + k) * b + (j % b)];
+    out[i] = v;
+  }
+}
+
+struct FinBwdArgs {
+  int b, D, Dz, row0, row_elems, offI, offT, offZ;
+  int have_soft, have_text, have_proj, row_only;
+  int ns_c, ns_s, ns_x;
+  const __nv_bfloat16* gathered;
+  const float* acc1;  // [ns_c][b][D]   sum_j G_clip . T_j   (image rows)
+  const float* acc2;  // [ns_c][b][D]   sum_j G_clip' . I_j  (text rows)
+  const float* acc3;  // [ns_s][b][Dz]  sum_j G_stu . Z_j / ||Z_j||
+  const float* acc4;  // [ns_x][b][D]   sum_j G_txt . T_j / ||T_j||
+  const float* ds1;   // [2 ns_c][b]
+  const float* ds2;
+  const float* diag;
+  const float* scal;
+  const float* rinv_z;
+  const float* rinv_t;
+  const float* gout;  // [3]
+  float* d_image;
+  float* d_text;
+  float* d_student;
+  float* dsrow;  // [b]
+};
+
+__device__ __forceinline__ float block_sum_128(float v, float* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return sh[0] + sh[1] + sh[2] + sh[3];
+}
+
+// One 128-thread block per local row: sum the column-split partial gradients, apply the fp32 one-hot
+// part of the CE gradient, the temperature / batch factors and the chain rule through F.normalize.
+__global__ void __launch_bounds__(128) finalize_bwd_kernel(FinBwdArgs a) {
+  __shared__ float sh[4];
+  const int i = blockIdx.x;
+  const size_t gi = static_cast<size_t>(a.row0) + i;
+  const __nv_bfloat16* rowp = a.gathered + gi * a.row_elems;
+  const float inv_b = 1.f / static_cast<float>(a.b);
+  const float gc = a.gout[0], gs = a.gout[1], gx = a.gout[2];
+  const float coefc = gc * a.scal[SC_SCALE] * 0.5f * inv_b;
+  const float onehot = a.row_only ? 1.f : 2.f;
+
+  // ---- CLIP part (loss.py:317-319 backward)
+  for (int f = threadIdx.x; f < a.D; f += blockDim.x) {
+    float u1 = 0.f, u2 = 0.f;
+    for (int s = 0; s < a.ns_c; ++s) {
+      u1 += a.acc1[(static_cast<size_t>(s) * a.b + i) * a.D + f];
+      u2 += a.acc2[(static_cast<size_t>(s) * a.b + i) * a.D + f];
+    }
+    const float tf = __bfloat162float(rowp[a.offT + f]);
+    const float imf = __bfloat162float(rowp[a.offI + f]);
+    a.d_image[static_cast<size_t>(i) * a.D + f] = coefc * (u1 - onehot * tf);
+    a.d_text[static_cast<size_t>(i) * a.D + f] = coefc * (u2 - onehot * imf);
+  }
+  if (threadIdx.x == 0) {
+    float d = 0.f;
+    for (int s = 0; s < 2 * a.ns_c; ++s) d += a.ds1[s * a.b + i] + a.ds2[s * a.b + i];
+    a.dsrow[i] = d - 2.f * a.diag[i];
+  }
+  __syncthreads();
+
+  // ---- student KL (loss.py:358-383 backward): d z~ = (g / (b tau_s)) * acc3 ; chain through normalize
+  if (a.have_soft) {
+    const float rz = a.rinv_z[gi];
+    const float coefs = gs * a.scal[SC_ITS] * inv_b;
+    float dot = 0.f;
+    for (int f = threadIdx.x; f < a.Dz; f += blockDim.x) {
+      float u = 0.f;
+      for (int s = 0; s < a.ns_s; ++s) u += a.acc3[(static_cast<size_t>(s) * a.b + i) * a.Dz + f];
+      const float zt = __bfloat162float(rowp[a.offZ + f]) * rz;
+      dot = fmaf(zt, coefs * u, dot);
+    }
+    dot = block_sum_128(dot, sh);
+    float* dst = a.have_proj ? a.d_student : a.d_image;
+    for (int f = threadIdx.x; f < a.Dz; f += blockDim.x) {
+      float u = 0.f;
+      for (int s = 0; s < a.ns_s; ++s) u += a.acc3[(static_cast<size_t>(s) * a.b + i) * a.Dz + f];
+      const float zt = __bfloat162float(rowp[a.offZ + f]) * rz;
+      const float gval = rz * (coefs * u - zt * dot);
+      if (a.have_proj)
+        dst[static_cast<size_t>(i) * a.Dz + f] = gval;
+      else
+        dst[static_cast<size_t>(i) * a.Dz + f] += gval;
+    }
+  }
+  // ---- text-text KL (loss.py:387-397 backward)
+  if (a.have_text) {
+    __syncthreads();
+    const float rt = a.rinv_t[gi];
+    const float coefx = gx * a.scal[SC_ITX] * inv_b;
+    float dot = 0.f;
+    for (int f = threadIdx.x; f < a.D; f += blockDim.x) {
+      float u = 0.f;
+      for (int s = 0; s < a.ns_x; ++s) u += a.acc4[(static_cast<size_t>(s) * a.b + i) * a.D + f];
+      const float tt = __bfloat162float(rowp[a.offT + f]) * rt;
+      dot = fmaf(tt, coefx * u, dot);
+    }
+    dot = block_sum_128(dot, sh);
+    for (int f = threadIdx.x; f < a.D; f += blockDim.x) {
+      float u = 0.f;
+      for (int s = 0; s < a.ns_x; ++s) u += a.acc4[(static_cast<size_t>(s) * a.b + i) * a.D + f];
+      const float tt = __bfloat162float(rowp[a.offT + f]) * rt;
+      a.d_text[static_cast<size_t>(i) * a.D + f] += rt * (coefx * u - tt * dot);
+    }
+  }
+}
+
+// d logit_scale = g_classic / (2b) * sum_i dsrow[i]
+__global__ void reduce_ds_kernel(const float* __restrict__ dsrow, int b, const float* __restrict__ gout,
+                                 float* __restrict__ out) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < b; i += blockDim.x) acc += static_cast<double>(dsrow[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) out[0] = static_cast<float>(v * static_cast<double>(gout[0]) * 0.5 / b);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+template <typename K>
+static int set_smem(K kernel, int bytes) {
+  CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return 0;
+}
+
+static int pack_one(const void* src, int dtype, int64_t ld, __nv_bfloat16* dst, int64_t dst_ld, int rows,
+                    int cols, cudaStream_t st) {
+  const int64_t total = static_cast<int64_t>(rows) * (cols / 2);
+  const int threads = 256;
+  const int blocks = static_cast<int>(std::min<int64_t>((total + threads - 1) / threads, 148 * 16));
+  switch (dtype) {
+    case DSOFT_DT_F32:
+      pack_rows_kernel<float><<<blocks, threads, 0, st>>>(static_cast<const float*>(src), ld, dst, dst_ld,
+                                                          rows, cols);
+      break;
+    case DSOFT_DT_BF16:
+      pack_rows_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(src),
+                                                                  ld, dst, dst_ld, rows, cols);
+      break;
+    case DSOFT_DT_F16:
+      pack_rows_kernel<__half><<<blocks, threads, 0, st>>>(static_cast<const __half*>(src), ld, dst,
+                                                           dst_ld, rows, cols);
+      break;
+    default:
+      return fail(DSOFT_EINVAL, "unknown dtype %d", dtype);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dsoft_pack(const dsoft_plan_t* p, const void* image, int image_dt, int64_t ld_image,
+                          const void* text, int text_dt, int64_t ld_text, const void* student,
+                          int student_dt, int64_t ld_student, const void* dino, int dino_dt,
+                          int64_t ld_dino, void* gathered, void* stream) {
+  if (!p || !image || !text || !gathered) return fail(DSOFT_EINVAL, "null argument");
+  if (p->have_proj && !student) return fail(DSOFT_EINVAL, "plan has Dp > 0 but student pointer is null");
+  if (p->have_soft && !dino) return fail(DSOFT_EINVAL, "plan has soft term but dino pointer is null");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* base =
+      static_cast<__nv_bfloat16*>(gathered) + static_cast<size_t>(p->sh.rank) * p->sh.b * p->row_elems;
+  int rc;
+  if ((rc = pack_one(image, image_dt, ld_image, base + p->offI, p->row_elems, p->sh.b, p->sh.D, st))) return rc;
+  if ((rc = pack_one(text, text_dt, ld_text, base + p->offT, p->row_elems, p->sh.b, p->sh.D, st))) return rc;
+  if (p->have_proj)
+    if ((rc = pack_one(student, student_dt, ld_student, base + p->offZ, p->row_elems, p->sh.b, p->sh.Dp, st)))
+      return rc;
+  if (p->have_soft)
+    if ((rc = pack_one(dino, dino_dt, ld_dino, base + p->offD, p->row_elems, p->sh.b, p->sh.Dd, st)))
+      return rc;
+  return 0;
+}
+
+static void fill_clip_fwd(const dsoft_plan* p, FwdParams& P, int amap, int bmap, float* scal, float* part,
+                          float* diag) {
+  memset(&P, 0, sizeof(P));
+  P.nprod = 1;
+  P.a_map[0] = amap;
+  P.b_map[0] = bmap;
+  P.kchunks[0] = ceil_div(p->sh.D, BK);
+  P.row0 = p->sh.rank * p->sh.b;
+  P.b = p->sh.b;
+  P.col0 = 0;
+  P.ncols = p->B;
+  P.ntiles = p->ntiles_g;
+  P.tiles_per_split = p->f_clip.tps;
+  P.npart = 2 * p->f_clip.nsplit;
+  P.scal = scal;
+  P.part = part;
+  P.diag = diag;
+}
+
+extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const float* logit_scale,
+                             void* state, void* scratch, float* lse_local, float* losses, void* stream) {
+  if (!p || !gathered || !logit_scale || !state || !scratch || !lse_local || !losses)
+    return fail(DSOFT_EINVAL, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* S = static_cast<float*>(state);
+  float* X = static_cast<float*>(scratch);
+  const __nv_bfloat16* g = static_cast<const __nv_bfloat16*>(gathered);
+  const int b = p->sh.b;
+  const int rbs = ceil_div(b, BM);
+  TileMaps tm;
+  int rc = make_maps(p, gathered, &tm);
+  if (rc) return rc;
+
+  prep_scalars_kernel<<<1, 32, 0, st>>>(logit_scale, p->have_soft ? p->sh.teacher_temp : 0.f,
+                                        p->have_text ? p->sh.text_temp : 0.f, S + p->st_scal);
+  CUDA_TRY(cudaGetLastError());
+
+  {  // inverse norms of text / student / dino rows of all ranks (grid.y selects the matrix)
+    const int wpb = 8;
+    const int blocks = ceil_div(p->Bcol, wpb);
+    rinv_kernel<<<blocks, wpb * 32, 0, st>>>(g + p->offT, p->row_elems, p->B, p->sh.D, S + p->st_rinv_t,
+                                             p->Bcol);
+    if (p->have_soft) {
+      rinv_kernel<<<blocks, wpb * 32, 0, st>>>(g + p->offZ, p->row_elems, p->B, p->Dz, S + p->st_rinv_z,
+                                               p->Bcol);
+      rinv_kernel<<<blocks, wpb * 32, 0, st>>>(g + p->offD, p->row_elems, p->B, p->sh.Dd,
+                                               S + p->st_rinv_d, p->Bcol);
+    }
+    CUDA_TRY(cudaGetLastError());
+  }
+
+  if ((rc = set_smem(dsoft_fwd_kernel<MODE_CLIP>, FWD_SMEM_BYTES))) return rc;
+  if ((rc = set_smem(dsoft_fwd_kernel<MODE_SOFT>, FWD_SMEM_BYTES))) return rc;
+
+  FwdParams P;
+  // image -> text (loss.py:266/272) and text -> image (loss.py:267/273)
+  fill_clip_fwd(p, P, 0, 1, S + p->st_scal, X + p->sc_pc_it, S + p->st_diag);
+  dsoft_fwd_kernel<MODE_CLIP><<<dim3(rbs, p->f_clip.nsplit), NUM_THREADS, FWD_SMEM_BYTES, st>>>(tm, P);
+  CUDA_TRY(cudaGetLastError());
+  fill_clip_fwd(p, P, 1, 0, S + p->st_scal, X + p->sc_pc_ti, S + p->st_diag);
+  dsoft_fwd_kernel<MODE_CLIP><<<dim3(rbs, p->f_clip.nsplit), NUM_THREADS, FWD_SMEM_BYTES, st>>>(tm, P);
+  CUDA_TRY(cudaGetLastError());
+
+  if (p->have_soft) {
+    memset(&P, 0, sizeof(P));
+    P.nprod = p->have_text ? 3 : 2;
+    P.a_map[0] = P.b_map[0] = 3;  // teacher: dino . dino^T       (loss.py:373)
+    P.a_map[1] = P.b_map[1] = 2;  // student: Zs . Zs^T           (loss.py:372)
+    P.a_map[2] = P.b_map[2] = 1;  // text:    Tn . Tn^T           (loss.py:394)
+    P.kchunks[0] = ceil_div(p->sh.Dd, BK);
+    P.kchunks[1] = ceil_div(p->Dz, BK);
+    P.kchunks[2] = ceil_div(p->sh.D, BK);
+    P.row0 = p->sh.rank * b;
+    P.b = b;
+    P.col0 = p->s_col0;
+    P.ncols = p->s_ncols;
+    P.ntiles = p->ntiles_s;
+    P.tiles_per_split = p->f_soft.tps;
+    P.npart = 2 * p->f_soft.nsplit;
+    P.scal = S + p->st_scal;
+    P.rinv[0] = S + p->st_rinv_d;
+    P.rinv[1] = S + p->st_rinv_z;
+    P.rinv[2] = S + p->st_rinv_t;
+    P.part = X + p->sc_ps;
+    dsoft_fwd_kernel<MODE_SOFT><<<dim3(rbs, p->f_soft.nsplit), NUM_THREADS, FWD_SMEM_BYTES, st>>>(tm, P);
+    CUDA_TRY(cudaGetLastError());
+  }
+
+  FinFwdArgs fa;
+  fa.b = b;
+  fa.np_c = 2 * p->f_clip.nsplit;
+  fa.np_s = 2 * p->f_soft.nsplit;
+  fa.have_soft = p->have_soft;
+  fa.have_text = p->have_text;
+  fa.pc_it = X + p->sc_pc_it;
+  fa.pc_ti = X + p->sc_pc_ti;
+  fa.ps = X + p->sc_ps;
+  fa.diag = S + p->st_diag;
+  fa.scal = S + p->st_scal;
+  fa.lse = lse_local;
+  fa.rowloss = X + p->sc_rowloss;
+  finalize_fwd_kernel<<<ceil_div(b, 128), 128, 0, st>>>(fa);
+  CUDA_TRY(cudaGetLastError());
+  const float inv_b = 1.f / static_cast<float>(b);
+  reduce_rows_kernel<<<1, 1024, 0, st>>>(X + p->sc_rowloss, b, 3, 0.5f * inv_b, inv_b, inv_b, losses);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const void* state, void* scratch,
+                              const float* lse_all, const float* gout, float* d_image, float* d_text,
+                              float* d_student, float* d_scale, void* stream) {
+  if (!p || !gathered || !state || !scratch || !lse_all || !gout || !d_image || !d_text || !d_scale)
+    return fail(DSOFT_EINVAL, "null argument");
+  if (p->have_proj && !d_student) return fail(DSOFT_EINVAL, "d_student is null but the plan has Dp > 0");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // state is logically const for the caller; the relayouted LSE columns live in it
+  float* S = const_cast<float*>(static_cast<const float*>(state));
+  float* X = static_cast<float*>(scratch);
+  const int b = p->sh.b;
+  const int rbs = ceil_div(b, BM);
+  TileMaps tm;
+  int rc = make_maps(p, gathered, &tm);
+  if (rc) return rc;
+
+  float* lsec = S + p->st_lsecols;
+  lse_relayout_kernel<<<ceil_div(5 * p->Bcol, 256), 256, 0, st>>>(lse_all, p->sh.world, b, p->Bcol, lsec);
+  CUDA_TRY(cudaGetLastError());
+  const float* lse_loc = lse_all + static_cast<size_t>(p->sh.rank) * 5 * b;
+
+  if ((rc = set_smem(dsoft_bwd_kernel<MODE_CLIP>, BWD_SMEM_BYTES))) return rc;
+  if ((rc = set_smem(dsoft_bwd_kernel<MODE_SOFT>, BWD_SMEM_BYTES))) return rc;
+
+  BwdParams P;
+  auto base = [&](const SplitPlan& sp, int col0, int ncols, int ntiles) {
+    memset(&P, 0, sizeof(P));
+    P.row0 = p->sh.rank * b;
+    P.b = b;
+    P.col0 = col0;
+    P.ncols = ncols;
+    P.ntiles = ntiles;
+    P.tiles_per_split = sp.tps;
+    P.nsplit = sp.nsplit;
+    P.row_only = p->row_only;
+    P.scal = S + p->st_scal;
+  };
+  // ---- CLIP, image rows: d image = s/(2b) sum_j (p_it[a,j] + p_ti[j,a]) T_j - ...
+  base(p->b_clip, 0, p->B, p->ntiles_g);
+  P.nprod = 1;
+  P.a_map[0] = 0;
+  P.b_map[0] = 1;
+  P.kchunks[0] = ceil_div(p->sh.D, BK);
+  P.v_map = 1;
+  P.dout = p->sh.D;
+  P.want_ds = 1;
+  P.lse_row = lse_loc + 0 * b;
+  P.lse_col = lsec + 1 * p->Bcol;
+  P.acc_part = X + p->sc_acc1;
+  P.ds_part = X + p->sc_ds1;
+  dsoft_bwd_kernel<MODE_CLIP>
+      <<<dim3(rbs, p->b_clip.nsplit, p->nch_clip), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, P);
+  CUDA_TRY(cudaGetLastError());
+  // ---- CLIP, text rows
+  P.a_map[0] = 1;
+  P.b_map[0] = 0;
+  P.v_map = 0;
+  P.lse_row = lse_loc + 1 * b;
+  P.lse_col = lsec + 0 * p->Bcol;
+  P.acc_part = X + p->sc_acc2;
+  P.ds_part = X + p->sc_ds2;
+  dsoft_bwd_kernel<MODE_CLIP>
+      <<<dim3(rbs, p->b_clip.nsplit, p->nch_clip), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, P);
+  CUDA_TRY(cudaGetLastError());
+
+  if (p->have_soft) {
+    base(p->b_stu, p->s_col0, p->s_ncols, p->ntiles_s);
+    P.nprod = 2;
+    P.a_map[0] = P.b_map[0] = 3;
+    P.kchunks[0] = ceil_div(p->sh.Dd, BK);
+    P.a_map[1] = P.b_map[1] = 2;
+    P.kchunks[1] = ceil_div(p->Dz, BK);
+    P.v_map = 2;
+    P.dout = p->Dz;
+    P.tau_idx = SC_ITS_L2;
+    P.lse_t_row = lse_loc + 2 * b;
+    P.lse_t_col = lsec + 2 * p->Bcol;
+    P.lse_y_row = lse_loc + 3 * b;
+    P.lse_y_col = lsec + 3 * p->Bcol;
+    P.rinv_d = S + p->st_rinv_d;
+    P.rinv_y = S + p->st_rinv_z;
+    P.acc_part = X + p->sc_acc3;
+    dsoft_bwd_kernel<MODE_SOFT>
+        <<<dim3(rbs, p->b_stu.nsplit, p->nch_stu), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, P);
+    CUDA_TRY(cudaGetLastError());
+    if (p->have_text) {
+      base(p->b_txt, p->s_col0, p->s_ncols, p->ntiles_s);
+      P.nprod = 2;
+      P.a_map[0] = P.b_map[0] = 3;
+      P.kchunks[0] = ceil_div(p->sh.Dd, BK);
+      P.a_map[1] = P.b_map[1] = 1;
+      P.kchunks[1] = ceil_div(p->sh.D, BK);
+      P.v_map = 1;
+      P.dout = p->sh.D;
+      P.tau_idx = SC_ITX_L2;
+      P.lse_t_row = lse_loc + 2 * b;
+      P.lse_t_col = lsec + 2 * p->Bcol;
+      P.lse_y_row = lse_loc + 4 * b;
+      P.lse_y_col = lsec + 4 * p->Bcol;
+      P.rinv_d = S + p->st_rinv_d;
+      P.rinv_y = S + p->st_rinv_t;
+      P.acc_part = X + p->sc_acc4;
+      dsoft_bwd_kernel<MODE_SOFT>
+          <<<dim3(rbs, p->b_txt.nsplit, p->nch_txt), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, P);
+      CUDA_TRY(cudaGetLastError());
+    }
+  }
+
+  FinBwdArgs fa;
+  memset(&fa, 0, sizeof(fa));
+  fa.b = b;
+  fa.D = p->sh.D;
+  fa.Dz = p->Dz;
+  fa.row0 = p->sh.rank * b;
+  fa.row_elems = p->row_elems;
+  fa.offI = p->offI;
+  fa.offT = p->offT;
+  fa.offZ = p->offZ;
+  fa.have_soft = p->have_soft;
+  fa.have_text = p->have_text;
+  fa.have_proj = p->have_proj;
+  fa.row_only = p->row_only;
+  fa.ns_c = p->b_clip.nsplit;
+  fa.ns_s = p->b_stu.nsplit;
+  fa.ns_x = p->b_txt.nsplit;
+  fa.gathered = static_cast<const __nv_bfloat16*>(gathered);
+  fa.acc1 = X + p->sc_acc1;
+  fa.acc2 = X + p->sc_acc2;
+  fa.acc3 = X + p->sc_acc3;
+  fa.acc4 = X + p->sc_acc4;
+  fa.ds1 = X + p->sc_ds1;
+  fa.ds2 = X + p->sc_ds2;
+  fa.diag = S + p->st_diag;
+  fa.scal = S + p->st_scal;
+  fa.rinv_z = S + p->st_rinv_z;
+  fa.rinv_t = S + p->st_rinv_t;
+  fa.gout = gout;
+  fa.d_image = d_image;
+  fa.d_text = d_text;
+  fa.d_student = d_student;
+  fa.dsrow = X + p->sc_dsrow;
+  finalize_bwd_kernel<<<b, 128, 0, st>>>(fa);
+  CUDA_TRY(cudaGetLastError());
+  reduce_ds_kernel<<<1, 1024, 0, st>>>(X + p->sc_dsrow, b, gout, d_scale);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bring-up self tests (exercise exactly the TMA / tcgen05 / TMEM plumbing of the loss kernels)
+// ------------------------------------------------------------------------------------------------
+extern "C" int dsoft_selftest_gemm(const void* a, const void* bmat, float* c, int M, int N, int K,
+                                   void* stream) {
+  if (!a || !bmat || !c || M <= 0 || N <= 0 || K <= 0 || K % 8)
+    return fail(DSOFT_EINVAL, "bad selftest arguments");
+  int sms = 0;
+  int rc = query_num_sms(&sms);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TileMaps tm;
+  if ((rc = make_map(&tm.m[0], a, M, K, K))) return rc;
+  if ((rc = make_map(&tm.m[1], bmat, N, K, K))) return rc;
+  tm.m[2] = tm.m[0];
+  tm.m[3] = tm.m[1];
+  if ((rc = set_smem(dsoft_fwd_kernel<MODE_RAW>, FWD_SMEM_BYTES))) return rc;
+  FwdParams P;
+  memset(&P, 0, sizeof(P));
+  P.nprod = 1;
+  P.a_map[0] = 0;
+  P.b_map[0] = 1;
+  P.kchunks[0] = ceil_div(K, BK);
+  P.row0 = 0;
+  P.b = M;
+  P.col0 = 0;
+  P.ncols = N;
+  P.ntiles = ceil_div(N, BN);
+  const int nsplit = std::min(P.ntiles, 3);
+  P.tiles_per_split = ceil_div(P.ntiles, nsplit);
+  P.npart = 0;
+  P.part = c;
+  dsoft_fwd_kernel<MODE_RAW>
+      <<<dim3(ceil_div(M, BM), ceil_div(P.ntiles, P.tiles_per_split)), NUM_THREADS, FWD_SMEM_BYTES, st>>>(tm, P);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// out[M][F] (fp32) = bf16(A . B^T) . V   with A [M][K], B [N][K], V [N][F] (bf16): the backward data path
+// (tile -> bf16 G in swizzled smem -> second tcgen05 GEMM with an MN-major operand) without any soft-max.
+extern "C" int dsoft_selftest_chain(const void* a, const void* bmat, const void* vmat, float* out, int M,
+                                    int N, int K, int F, void* stream) {
+  if (!a || !bmat || !vmat || !out || M <= 0 || N <= 0 || K <= 0 || K % 8 || F <= 0 || F % 8)
+    return fail(DSOFT_EINVAL, "bad selftest arguments");
+  int sms = 0;
+  int rc = query_num_sms(&sms);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TileMaps tm;
+  if ((rc = make_map(&tm.m[0], a, M, K, K))) return rc;
+  if ((rc = make_map(&tm.m[1], bmat, N, K, K))) return rc;
+  if ((rc = make_map(&tm.m[2], vmat, N, F, F))) return rc;
+  tm.m[3] = tm.m[0];
+  if ((rc = set_smem(dsoft_bwd_kernel<MODE_RAW>, BWD_SMEM_BYTES))) return rc;
+  BwdParams P;
+  memset(&P, 0, sizeof(P));
+  P.nprod = 1;
+  P.a_map[0] = 0;
+  P.b_map[0] = 1;
+  P.kchunks[0] = ceil_div(K, BK);
+  P.v_map = 2;
+  P.dout = F;
+  P.row0 = 0;
+  P.b = M;
+  P.col0 = 0;
+  P.ncols = N;
+  P.ntiles = ceil_div(N, BN);
+  P.tiles_per_split = P.ntiles;  // single split: `out` is the only partial
+  P.nsplit = 1;
+  P.acc_part = out;
+  dsoft_bwd_kernel<MODE_RAW>
+      <<<dim3(ceil_div(M, BM), 1, ceil_div(F, CHUNK_F)), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, P);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}

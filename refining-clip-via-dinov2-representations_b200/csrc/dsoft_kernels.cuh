@@ -1,0 +1,715 @@
+// DINO-Soft streaming row-block kernels for sm_100a (tcgen05 + TMEM + TMA).
+//
+// One CTA owns a block of 128 rows (TMEM lanes) of the B x B similarity matrices and streams
+// 128-column tiles of them.  Nothing of size B x B is ever written to HBM:
+//   * forward ("stats") kernels reduce every tile to per-row soft-max statistics;
+//   * backward kernels recompute the tile, turn it into the logit-gradient tile G (bf16, in shared
+//     memory) and feed G straight back into the tensor core as the A operand of dX += G . Y.
+//
+// Reference semantics being reproduced (file:line in /root/reference/src/open_clip/loss.py):
+//   CLIP logits / CE ............ get_logits 254-274, forward 313-319
+//   teacher / student / text KL .. forward 356-397
+// Warp roles (12 warps): 0 = TMA producer, 1 = tcgen05.mma issuer, 2 = TMEM allocator,
+// 3 = idle, 4..11 = epilogue (warp w owns TMEM lanes 32*(w%4).., column half (w-4)/4).
+#pragma once
+
+#include "dsoft_ptx.cuh"
+
+namespace dsoft {
+
+constexpr int BM = 128;                  // rows per CTA == TMEM lanes
+constexpr int BN = 128;                  // columns per similarity tile
+constexpr int BK = 64;                   // bf16 per 128-byte swizzled smem row
+constexpr int TILE_BYTES = BM * BK * 2;  // one TMA box: 128 rows x 128 B = 16 KiB
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_WARP0 = 4;
+constexpr int NUM_EPI_THREADS = 256;
+constexpr int TMEM_COLS = 512;
+constexpr int F_STAGES = 6;      // forward operand ring (A+B boxes per stage)
+constexpr int F_SLOTS = 4;       // forward S-tile slots in TMEM (4 x 128 columns)
+constexpr int B_STAGES = 4;      // backward operand ring
+constexpr int B_SLOTS = 2;       // backward S-tile slots (2 x 128 columns) + 256 accumulator columns
+constexpr int CHUNK_F = 256;     // gradient features accumulated in TMEM per pass
+constexpr int ACC_COL = 256;     // TMEM column where the gradient accumulator starts
+constexpr float NEG_BIG = -1.0e30f;  // masked logit (finite: 0 * NEG_BIG stays 0)
+constexpr float M_FLOOR = -1.0e4f;   // initial running max (log2 units); real logits are far above
+
+constexpr int MODE_CLIP = 0;
+constexpr int MODE_SOFT = 1;
+constexpr int MODE_RAW = 2;  // bring-up: forward stores the raw tile, backward uses G = raw dot products
+
+// scalar block computed on device by prep_scalars_kernel (no host sync on logit_scale)
+enum {
+  SC_SCALE = 0,     // logit scale s
+  SC_SCALE_L2 = 1,  // s * log2(e)
+  SC_ITS = 2,       // 1/tau_s            (compute_student_tau, loss.py:166-175)
+  SC_ITS_L2 = 3,    // log2(e)/tau_s
+  SC_ITT = 4,       // 1/tau_t            (teacher_temp, loss.py:368-369)
+  SC_ITT_L2 = 5,
+  SC_ITX = 6,       // 1/tau_txt          (text_student_temp, loss.py:391-393)
+  SC_ITX_L2 = 7,
+  SC_COUNT = 8
+};
+
+struct TileMaps {
+  CUtensorMap m[4];  // 0 = image, 1 = text, 2 = student, 3 = dino; box = 64 features x 128 rows, SW128
+};
+
+struct FwdParams {
+  int nprod;        // products per tile: clip 1; soft 2 (teacher, student) or 3 (+ text)
+  int a_map[3];     // tensor map of the row-side operand of product p
+  int b_map[3];     // tensor map of the column-side operand of product p
+  int kchunks[3];   // ceil(K_p / 64)
+  int row0;         // global index of local row 0 (rank * b)
+  int b;            // local rows
+  int col0;         // first global column in scope
+  int ncols;        // number of columns in scope
+  int ntiles;       // ceil(ncols / 128)
+  int tiles_per_split;
+  int npart;        // nsplit * 2 (two column halves per split)
+  const float* scal;
+  const float* rinv[3];  // per product: inverse L2 norms by global index (soft only)
+  float* part;           // partial statistics [nstat][npart][b]
+  float* diag;           // clip: raw dot product on the diagonal [b]
+};
+
+struct BwdParams {
+  int nprod;       // clip 1; soft 2 (teacher, then student-or-text)
+  int a_map[2];
+  int b_map[2];
+  int kchunks[2];
+  int v_map;       // operand of the gradient GEMM (== column-side operand of the last product)
+  int dout;        // feature width of the gradient
+  int row0, b, col0, ncols, ntiles, tiles_per_split, nsplit;
+  int row_only;    // gather_with_grad == False: gathered columns are constants
+  int want_ds;     // clip: also accumulate the d(logit_scale) row term
+  const float* scal;
+  int tau_idx;             // soft: SC_ITS_L2 or SC_ITX_L2
+  const float* lse_row;    // clip: this direction's row LSE (log2), local rows
+  const float* lse_col;    // clip: other direction's LSE by global column (padded)
+  const float* lse_t_row;  // soft: teacher LSE, local rows
+  const float* lse_t_col;  // soft: teacher LSE by global column
+  const float* lse_y_row;  // soft: student/text LSE, local rows
+  const float* lse_y_col;
+  const float* rinv_d;     // by global index
+  const float* rinv_y;
+  float* acc_part;         // [nsplit][b][dout] fp32
+  float* ds_part;          // [nsplit*2][b]
+};
+
+__device__ __forceinline__ uint8_t* align_1024(uint8_t* p) {
+  uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  return reinterpret_cast<uint8_t*>((a + 1023) & ~static_cast<uintptr_t>(1023));
+}
+
+// S tile (128 x 128, K = 64 slice): 4 tcgen05.mma of K=16, both operands K-major SW128.
+__device__ __forceinline__ void issue_s_stage(uint32_t tmem_d, uint32_t a_smem, uint32_t b_smem,
+                                              bool first_stage) {
+  constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+  const uint64_t ad = make_smem_desc(a_smem, 16, 1024);
+  const uint64_t bd = make_smem_desc(b_smem, 16, 1024);
+#pragma unroll
+  for (int kk = 0; kk < BK / 16; ++kk) {
+    // advancing 16 elements (32 B) inside the 128 B swizzle row: +2 in the (addr >> 4) field
+    umma_bf16(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, (first_stage && kk == 0) ? 0u : 1u);
+  }
+}
+
+// ================================================================================================
+// Forward: per-row soft-max statistics
+// ================================================================================================
+//  MODE_CLIP partials (2): running max m (log2 units), sum 2^(x-m)        [+ diag dot product]
+//  MODE_SOFT partials (7): teacher m, Zt, Aq=sum w*q, Ap=sum w*p, Ar=sum w*r, student Zs, text Ztt
+//  (w = 2^(q-m); student/text use the fixed maximum log2(e)/tau, reached on the diagonal.)
+template <int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ FwdParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_1024(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F_STAGES * 2 * TILE_BYTES);
+  uint64_t* ring_full = bars;
+  uint64_t* ring_empty = bars + F_STAGES;
+  uint64_t* s_full = bars + 2 * F_STAGES;
+  uint64_t* s_empty = s_full + F_SLOTS;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(s_empty + F_SLOTS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rb = blockIdx.x;
+  const int split = blockIdx.y;
+  const int t0 = split * P.tiles_per_split;
+  const int t1 = min(t0 + P.tiles_per_split, P.ntiles);
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&maps.m[i]);
+    for (int i = 0; i < F_STAGES; ++i) {
+      mbar_init(smem_u32(&ring_full[i]), 1);
+      mbar_init(smem_u32(&ring_empty[i]), 1);
+    }
+    for (int i = 0; i < F_SLOTS; ++i) {
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&s_empty[i]), NUM_EPI_THREADS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_holder), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = t0; t < t1; ++t) {
+        for (int p = 0; p < P.nprod; ++p) {
+          const CUtensorMap* am = &maps.m[P.a_map[p]];
+          const CUtensorMap* bm = &maps.m[P.b_map[p]];
+          for (int kc = 0; kc < P.kchunks[p]; ++kc) {
+            mbar_wait(smem_u32(&ring_empty[stage]), phase ^ 1);
+            const uint32_t full = smem_u32(&ring_full[stage]);
+            const uint32_t a_dst = smem_u32(smem + stage * 2 * TILE_BYTES);
+            mbar_arrive_expect_tx(full, 2 * TILE_BYTES);
+            tma_load_2d(a_dst, am, full, kc * BK, P.row0 + rb * BM);
+            tma_load_2d(a_dst + TILE_BYTES, bm, full, kc * BK, P.col0 + t * BN);
+            if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = t0; t < t1; ++t) {
+        for (int p = 0; p < P.nprod; ++p, ++it) {
+          const int slot = it % F_SLOTS;
+          const uint32_t use = static_cast<uint32_t>(it / F_SLOTS);
+          mbar_wait(smem_u32(&s_empty[slot]), (use & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + slot * BN;
+          for (int kc = 0; kc < P.kchunks[p]; ++kc) {
+            mbar_wait(smem_u32(&ring_full[stage]), phase);
+            tc_fence_after();
+            const uint32_t a_smem = smem_u32(smem + stage * 2 * TILE_BYTES);
+            issue_s_stage(tmem_d, a_smem, a_smem + TILE_BYTES, kc == 0);
+            umma_commit(smem_u32(&ring_empty[stage]));
+            if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(smem_u32(&s_full[slot]));
+        }
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;
+    const int half = (warp - EPI_WARP0) >> 2;
+    const int row = q * 32 + lane;
+    const int li = rb * BM + row;  // local row
+    const int gi = P.row0 + li;    // global index of this row
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int sp = split * 2 + half;
+    float v[32];
+
+    if constexpr (MODE == MODE_RAW) {
+      int it = 0;
+      for (int t = t0; t < t1; ++t, ++it) {
+        const int slot = it % F_SLOTS;
+        const uint32_t use = static_cast<uint32_t>(it / F_SLOTS);
+        mbar_wait(smem_u32(&s_full[slot]), use & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          const int jrel0 = t * BN + half * 64 + c * 32;
+          tmem_ld32(lane_addr + slot * BN + half * 64 + c * 32, v);
+          if (li < P.b) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (jrel0 + e < P.ncols) P.part[static_cast<size_t>(li) * P.ncols + jrel0 + e] = v[e];
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(smem_u32(&s_empty[slot]));
+      }
+    } else if constexpr (MODE == MODE_CLIP) {
+      const float s2 = P.scal[SC_SCALE_L2];
+      float m = M_FLOOR, sum = 0.f, dg = 0.f;
+      bool have_dg = false;
+      int it = 0;
+      for (int t = t0; t < t1; ++t, ++it) {
+        const int slot = it % F_SLOTS;
+        const uint32_t use = static_cast<uint32_t>(it / F_SLOTS);
+        mbar_wait(smem_u32(&s_full[slot]), use & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          const int jrel0 = t * BN + half * 64 + c * 32;
+          const int gj0 = P.col0 + jrel0;
+          tmem_ld32(lane_addr + slot * BN + half * 64 + c * 32, v);
+          if (gi >= gj0 && gi < gj0 + 32) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (gj0 + e == gi) dg = v[e];
+            have_dg = true;
+          }
+          float x[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) x[e] = v[e] * s2;
+          if (jrel0 + 32 > P.ncols) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (jrel0 + e >= P.ncols) x[e] = NEG_BIG;
+          }
+          float cm[4] = {x[0], x[1], x[2], x[3]};
+#pragma unroll
+          for (int e = 4; e < 32; ++e) cm[e & 3] = fmaxf(cm[e & 3], x[e]);
+          const float mnew = fmaxf(m, fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])));
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int e = 0; e < 32; ++e) acc[e & 3] += fast_exp2(x[e] - mnew);
+          sum = sum * fast_exp2(m - mnew) + ((acc[0] + acc[1]) + (acc[2] + acc[3]));
+          m = mnew;
+        }
+        tc_fence_before();
+        mbar_arrive(smem_u32(&s_empty[slot]));
+      }
+      if (li < P.b) {
+        P.part[(0 * P.npart + sp) * P.b + li] = m;
+        P.part[(1 * P.npart + sp) * P.b + li] = sum;
+        if (have_dg) P.diag[li] = dg;
+      }
+    } else {
+      const float cq = P.rinv[0][gi] * P.scal[SC_ITT_L2];
+      const float cp = P.rinv[1][gi] * P.scal[SC_ITS_L2];
+      const float ms2 = P.scal[SC_ITS_L2];
+      const bool has_text = P.nprod == 3;
+      const float cr = has_text ? P.rinv[2][gi] * P.scal[SC_ITX_L2] : 0.f;
+      const float mx2 = P.scal[SC_ITX_L2];
+      float m = M_FLOOR, zt = 0.f, aq = 0.f, ap = 0.f, ar = 0.f, zs = 0.f, zx = 0.f;
+      float w[32];
+      int it = 0;
+      for (int t = t0; t < t1; ++t, it += P.nprod) {
+        for (int p = 0; p < P.nprod; ++p) {
+          const int slot = (it + p) % F_SLOTS;
+          const uint32_t use = static_cast<uint32_t>((it + p) / F_SLOTS);
+          mbar_wait(smem_u32(&s_full[slot]), use & 1);
+        }
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          const int jrel0 = t * BN + half * 64 + c * 32;
+          const int gj0 = P.col0 + jrel0;
+          const bool ragged = jrel0 + 32 > P.ncols;
+          const uint32_t coff = half * 64 + c * 32;
+          // ---- teacher: running max, w = 2^(q - m)
+          tmem_ld32(lane_addr + ((it + 0) % F_SLOTS) * BN + coff, v);
+          {
+            const float4* rc = reinterpret_cast<const float4*>(P.rinv[0] + gj0);
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const float4 r = __ldg(rc + e4);
+              w[4 * e4 + 0] = v[4 * e4 + 0] * cq * r.x;
+              w[4 * e4 + 1] = v[4 * e4 + 1] * cq * r.y;
+              w[4 * e4 + 2] = v[4 * e4 + 2] * cq * r.z;
+              w[4 * e4 + 3] = v[4 * e4 + 3] * cq * r.w;
+            }
+          }
+          if (ragged || (gi >= gj0 && gi < gj0 + 32)) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (jrel0 + e >= P.ncols || gj0 + e == gi) w[e] = NEG_BIG;  // teacher diag masked: loss.py:376-377
+          }
+          float cm[4] = {w[0], w[1], w[2], w[3]};
+#pragma unroll
+          for (int e = 4; e < 32; ++e) cm[e & 3] = fmaxf(cm[e & 3], w[e]);
+          const float mnew = fmaxf(m, fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])));
+          const float alpha = fast_exp2(m - mnew);
+          m = mnew;
+          float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float q2 = w[e];
+            const float we = fast_exp2(q2 - mnew);
+            a0[e & 3] += we;
+            a1[e & 3] = fmaf(we, q2, a1[e & 3]);
+            w[e] = we;
+          }
+          zt = zt * alpha + ((a0[0] + a0[1]) + (a0[2] + a0[3]));
+          aq = aq * alpha + ((a1[0] + a1[1]) + (a1[2] + a1[3]));
+          ap *= alpha;
+          ar *= alpha;
+          // ---- student: sum w*p and fixed-max exp sum
+          tmem_ld32(lane_addr + ((it + 1) % F_SLOTS) * BN + coff, v);
+          {
+            const float4* rc = reinterpret_cast<const float4*>(P.rinv[1] + gj0);
+            float b0[4] = {0.f, 0.f, 0.f, 0.f}, b1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const float4 r = __ldg(rc + e4);
+              const float rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int e = 4 * e4 + k;
+                float p2 = v[e] * cp * rr[k];
+                if (ragged && jrel0 + e >= P.ncols) p2 = NEG_BIG;
+                b0[k] += fast_exp2(p2 - ms2);
+                b1[k] = fmaf(w[e], p2, b1[k]);
+              }
+            }
+            zs += (b0[0] + b0[1]) + (b0[2] + b0[3]);
+            ap += (b1[0] + b1[1]) + (b1[2] + b1[3]);
+          }
+          // ---- text (loss.py:387-397): same teacher weights
+          if (has_text) {
+            tmem_ld32(lane_addr + ((it + 2) % F_SLOTS) * BN + coff, v);
+            const float4* rc = reinterpret_cast<const float4*>(P.rinv[2] + gj0);
+            float b0[4] = {0.f, 0.f, 0.f, 0.f}, b1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const float4 r = __ldg(rc + e4);
+              const float rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int e = 4 * e4 + k;
+                float r2 = v[e] * cr * rr[k];
+                if (ragged && jrel0 + e >= P.ncols) r2 = NEG_BIG;
+                b0[k] += fast_exp2(r2 - mx2);
+                b1[k] = fmaf(w[e], r2, b1[k]);
+              }
+            }
+            zx += (b0[0] + b0[1]) + (b0[2] + b0[3]);
+            ar += (b1[0] + b1[1]) + (b1[2] + b1[3]);
+          }
+        }
+        tc_fence_before();
+        for (int p = 0; p < P.nprod; ++p) mbar_arrive(smem_u32(&s_empty[(it + p) % F_SLOTS]));
+      }
+      if (li < P.b) {
+        const int o = sp * P.b + li;
+        const int st = P.npart * P.b;
+        P.part[0 * st + o] = m;
+        P.part[1 * st + o] = zt;
+        P.part[2 * st + o] = aq;
+        P.part[3 * st + o] = ap;
+        P.part[4 * st + o] = ar;
+        P.part[5 * st + o] = zs;
+        P.part[6 * st + o] = zx;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ================================================================================================
+// Backward: recompute tile -> G (bf16, smem) -> accumulate G . Y in TMEM
+// ================================================================================================
+//  MODE_CLIP: G_aj = 2^(x - lse_row_a) + 2^(x - lse_col_j)        (the -2*delta one-hot part and the
+//             s/(2b) factor are applied in fp32 by the finalize kernel)
+//  MODE_SOFT: G_aj = ry_j * [ (2^(p-ls_a) + 2^(p-ls_j)) - (2^(q-lt_a) + 2^(q-lt_j)) ],  q diag masked
+//  row_only drops the *_j (column-side) terms: gathered features are constants (gather_with_grad=0).
+template <int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ BwdParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_1024(smem_raw);
+  uint8_t* v_smem = smem + B_STAGES * 2 * TILE_BYTES;  // 4 boxes: 128 columns(j) x 256 features
+  uint8_t* g_smem = v_smem + 4 * TILE_BYTES;           // 2 boxes: 128 rows x 128 columns(j), bf16
+  uint64_t* bars = reinterpret_cast<uint64_t*>(g_smem + 2 * TILE_BYTES);
+  uint64_t* ring_full = bars;
+  uint64_t* ring_empty = bars + B_STAGES;
+  uint64_t* s_full = bars + 2 * B_STAGES;
+  uint64_t* s_empty = s_full + B_SLOTS;
+  uint64_t* v_full = s_empty + B_SLOTS;
+  uint64_t* v_empty = v_full + 1;
+  uint64_t* g_full = v_empty + 1;
+  uint64_t* g_empty = g_full + 1;
+  uint64_t* acc_full = g_empty + 1;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rb = blockIdx.x;
+  const int split = blockIdx.y;
+  const int chunk = blockIdx.z;
+  const int t0 = split * P.tiles_per_split;
+  const int t1 = min(t0 + P.tiles_per_split, P.ntiles);
+  const int f0 = chunk * CHUNK_F;                            // first gradient feature of this pass
+  const int nfb = min(4, (P.dout - f0 + BK - 1) / BK);       // 64-feature boxes in this pass
+  const int vmap = P.v_map;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&maps.m[i]);
+    for (int i = 0; i < B_STAGES; ++i) {
+      mbar_init(smem_u32(&ring_full[i]), 1);
+      mbar_init(smem_u32(&ring_empty[i]), 1);
+    }
+    for (int i = 0; i < B_SLOTS; ++i) {
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&s_empty[i]), NUM_EPI_THREADS);
+    }
+    mbar_init(smem_u32(v_full), 1);
+    mbar_init(smem_u32(v_empty), 1);
+    mbar_init(smem_u32(g_full), NUM_EPI_THREADS);
+    mbar_init(smem_u32(g_empty), 1);
+    mbar_init(smem_u32(acc_full), 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_holder), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int n = 0;
+      for (int t = t0; t < t1; ++t, ++n) {
+        for (int p = 0; p < P.nprod; ++p) {
+          const CUtensorMap* am = &maps.m[P.a_map[p]];
+          const CUtensorMap* bm = &maps.m[P.b_map[p]];
+          for (int kc = 0; kc < P.kchunks[p]; ++kc) {
+            mbar_wait(smem_u32(&ring_empty[stage]), phase ^ 1);
+            const uint32_t full = smem_u32(&ring_full[stage]);
+            const uint32_t a_dst = smem_u32(smem + stage * 2 * TILE_BYTES);
+            mbar_arrive_expect_tx(full, 2 * TILE_BYTES);
+            tma_load_2d(a_dst, am, full, kc * BK, P.row0 + rb * BM);
+            tma_load_2d(a_dst + TILE_BYTES, bm, full, kc * BK, P.col0 + t * BN);
+            if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        // gradient operand Y[j-tile, f0 : f0 + 64*nfb]  (same boxes as a B operand, used MN-major)
+        mbar_wait(smem_u32(v_empty), (static_cast<uint32_t>(n) & 1) ^ 1);
+        const uint32_t vf = smem_u32(v_full);
+        mbar_arrive_expect_tx(vf, nfb * TILE_BYTES);
+        for (int fb = 0; fb < nfb; ++fb)
+          tma_load_2d(smem_u32(v_smem + fb * TILE_BYTES), &maps.m[vmap], vf, f0 + fb * BK,
+                      P.col0 + t * BN);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      int n = 0;
+      const uint32_t idesc_g = make_idesc_bf16(BM, nfb * BK, 0, 1);  // A = G (K-major), B = Y (MN-major)
+      const uint32_t tmem_acc = tmem_base + ACC_COL;
+      auto issue_grad = [&](int mt) {
+        mbar_wait(smem_u32(g_full), static_cast<uint32_t>(mt) & 1);
+        mbar_wait(smem_u32(v_full), static_cast<uint32_t>(mt) & 1);
+        tc_fence_after();
+        const uint32_t g_addr = smem_u32(g_smem);
+        const uint32_t v_addr = smem_u32(v_smem);
+#pragma unroll
+        for (int kk = 0; kk < BN / 16; ++kk) {
+          // A: G[128 rows, 16 j]  -> box kk/4, 32-byte step inside the swizzled 128 B row
+          const uint64_t ad = make_smem_desc(g_addr + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 16, 1024);
+          // B: Y[16 j, 64*nfb features] MN-major: 16 j-rows = 2048 B; next 64-feature box = LBO
+          const uint64_t bd = make_smem_desc(v_addr + kk * 2048, TILE_BYTES, 1024);
+          umma_bf16(tmem_acc, ad, bd, idesc_g, (mt == 0 && kk == 0) ? 0u : 1u);
+        }
+        umma_commit(smem_u32(g_empty));
+        umma_commit(smem_u32(v_empty));
+      };
+      for (int t = t0; t < t1; ++t, ++n) {
+        for (int p = 0; p < P.nprod; ++p, ++it) {
+          const int slot = it % B_SLOTS;
+          const uint32_t use = static_cast<uint32_t>(it / B_SLOTS);
+          mbar_wait(smem_u32(&s_empty[slot]), (use & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + slot * BN;
+          for (int kc = 0; kc < P.kchunks[p]; ++kc) {
+            mbar_wait(smem_u32(&ring_full[stage]), phase);
+            tc_fence_after();
+            const uint32_t a_smem = smem_u32(smem + stage * 2 * TILE_BYTES);
+            issue_s_stage(tmem_d, a_smem, a_smem + TILE_BYTES, kc == 0);
+            umma_commit(smem_u32(&ring_empty[stage]));
+            if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(smem_u32(&s_full[slot]));
+        }
+        if (n > 0) issue_grad(n - 1);  // keep the tensor pipe busy while tile n's epilogue runs
+      }
+      if (n > 0) issue_grad(n - 1);
+      umma_commit(smem_u32(acc_full));
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;
+    const int half = (warp - EPI_WARP0) >> 2;
+    const int row = q * 32 + lane;
+    const int li = rb * BM + row;
+    const int lic = min(li, P.b - 1);  // clamped index for per-row constant loads
+    const int gi = P.row0 + li;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t g_row = smem_u32(g_smem) + half * TILE_BYTES + row * 128;
+    const int sw = row & 7;
+    const bool row_only = P.row_only != 0;
+    float v[32];
+    float dsacc = 0.f;
+
+    float c_a = 0.f, c_b = 0.f, l_a = 0.f, l_b = 0.f;
+    if constexpr (MODE == MODE_RAW) {
+      c_a = 1.f;
+    } else if constexpr (MODE == MODE_CLIP) {
+      c_a = P.scal[SC_SCALE_L2];
+      l_a = P.lse_row[lic];
+    } else {
+      c_a = P.rinv_d[gi] * P.scal[SC_ITT_L2];  // teacher
+      l_a = P.lse_t_row[lic];
+      c_b = P.rinv_y[gi] * P.scal[P.tau_idx];  // student / text
+      l_b = P.lse_y_row[lic];
+    }
+
+    int it = 0;
+    int n = 0;
+    for (int t = t0; t < t1; ++t, ++n, it += P.nprod) {
+      for (int p = 0; p < P.nprod; ++p) {
+        const int slot = (it + p) % B_SLOTS;
+        const uint32_t use = static_cast<uint32_t>((it + p) / B_SLOTS);
+        mbar_wait(smem_u32(&s_full[slot]), use & 1);
+      }
+      tc_fence_after();
+      mbar_wait(smem_u32(g_empty), (static_cast<uint32_t>(n) & 1) ^ 1);  // previous G consumed
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        const int jrel0 = t * BN + half * 64 + c * 32;
+        const int gj0 = P.col0 + jrel0;
+        const bool ragged = jrel0 + 32 > P.ncols;
+        const uint32_t coff = half * 64 + c * 32;
+        float g[32];
+        if constexpr (MODE == MODE_RAW) {
+          tmem_ld32(lane_addr + (it % B_SLOTS) * BN + coff, v);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) g[e] = v[e];
+        } else if constexpr (MODE == MODE_CLIP) {
+          tmem_ld32(lane_addr + (it % B_SLOTS) * BN + coff, v);
+          const float4* lc = reinterpret_cast<const float4*>(P.lse_col + gj0);
+#pragma unroll
+          for (int e4 = 0; e4 < 8; ++e4) {
+            const float4 l4 = __ldg(lc + e4);
+            const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int e = 4 * e4 + k;
+              const float x2 = v[e] * c_a;
+              const float e1 = fast_exp2(x2 - l_a);
+              const float e2 = row_only ? 0.f : fast_exp2(x2 - ll[k]);
+              dsacc = fmaf(e1, v[e], dsacc);
+              g[e] = e1 + e2;
+            }
+          }
+        } else {
+          // teacher part first (kept in g as a negative contribution)
+          tmem_ld32(lane_addr + ((it + 0) % B_SLOTS) * BN + coff, v);
+          {
+            const float4* rc = reinterpret_cast<const float4*>(P.rinv_d + gj0);
+            const float4* lc = reinterpret_cast<const float4*>(P.lse_t_col + gj0);
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const float4 r4 = __ldg(rc + e4);
+              const float4 l4 = __ldg(lc + e4);
+              const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+              const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int e = 4 * e4 + k;
+                const float q2 = v[e] * c_a * rr[k];
+                const float e1 = fast_exp2(q2 - l_a);
+                const float e2 = row_only ? 0.f : fast_exp2(q2 - ll[k]);
+                g[e] = (gj0 + e == gi) ? 0.f : -(e1 + e2);  // q_ii = 0 (teacher diag masked)
+              }
+            }
+          }
+          tmem_ld32(lane_addr + ((it + 1) % B_SLOTS) * BN + coff, v);
+          {
+            const float4* rc = reinterpret_cast<const float4*>(P.rinv_y + gj0);
+            const float4* lc = reinterpret_cast<const float4*>(P.lse_y_col + gj0);
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const float4 r4 = __ldg(rc + e4);
+              const float4 l4 = __ldg(lc + e4);
+              const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+              const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int e = 4 * e4 + k;
+                const float p2 = v[e] * c_b * rr[k];
+                const float e1 = fast_exp2(p2 - l_b);
+                const float e2 = row_only ? 0.f : fast_exp2(p2 - ll[k]);
+                g[e] = (g[e] + (e1 + e2)) * rr[k];  // fold the column's 1/||y_j|| into G
+              }
+            }
+          }
+        }
+        if (ragged) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (jrel0 + e >= P.ncols) g[e] = 0.f;
+        }
+        // 32 values -> 4 x 16-byte swizzled stores into the K-major SW128 A-operand layout
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const uint32_t w0 = pack_bf16x2(g[8 * k4 + 0], g[8 * k4 + 1]);
+          const uint32_t w1 = pack_bf16x2(g[8 * k4 + 2], g[8 * k4 + 3]);
+          const uint32_t w2 = pack_bf16x2(g[8 * k4 + 4], g[8 * k4 + 5]);
+          const uint32_t w3 = pack_bf16x2(g[8 * k4 + 6], g[8 * k4 + 7]);
+          const int chunk16 = c * 4 + k4;
+          st_shared_v4(g_row + ((chunk16 ^ sw) << 4), w0, w1, w2, w3);
+        }
+      }
+      tc_fence_before();
+      for (int p = 0; p < P.nprod; ++p) mbar_arrive(smem_u32(&s_empty[(it + p) % B_SLOTS]));
+      fence_proxy_async_smem();
+      mbar_arrive(smem_u32(g_full));
+    }
+
+    // ---- drain the accumulator: TMEM -> fp32 partial gradient
+    mbar_wait(smem_u32(acc_full), 0);
+    tc_fence_after();
+    if (n > 0) {
+      float* dst = P.acc_part + (static_cast<size_t>(split) * P.b + li) * P.dout + f0;
+      const int nvalid = min(nfb * BK, P.dout - f0);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int cf = half * 128 + c * 32;
+        if (cf >= nfb * BK) break;  // warp-uniform
+        tmem_ld32(lane_addr + ACC_COL + cf, v);
+        if (li < P.b) {
+          if (cf + 32 <= nvalid) {
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4)
+              *reinterpret_cast<float4*>(dst + cf + 4 * e4) =
+                  make_float4(v[4 * e4], v[4 * e4 + 1], v[4 * e4 + 2], v[4 * e4 + 3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (cf + e < nvalid) dst[cf + e] = v[e];
+          }
+        }
+      }
+    }
+    if (MODE == MODE_CLIP && P.want_ds && chunk == 0 && li < P.b)
+      P.ds_part[(split * 2 + half) * P.b + li] = dsacc;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+constexpr int FWD_SMEM_BYTES = F_STAGES * 2 * TILE_BYTES + 1024 + 256;
+constexpr int BWD_SMEM_BYTES = B_STAGES * 2 * TILE_BYTES + 4 * TILE_BYTES + 2 * TILE_BYTES + 1024 + 256;
+
+}  // namespace dsoft
