@@ -114,10 +114,10 @@ int dsoft_backward(const dsoft_plan_t* plan, const void* gathered_dev, const voi
 int dsoft_selftest_gemm(const void* a_bf16_dev, const void* b_bf16_dev, float* c_dev, int M, int N,
                         int K, void* stream);
 
-/* Test / bring-up helper: out[M][F] (fp32) = bf16(A . B^T) . V with A [M][K], B [N][K], V [N][F] bf16:
- * the backward data path (tile -> bf16 G tile in swizzled shared memory -> second tcgen05 GEMM with an
- * MN-major operand) without any soft-max arithmetic. */
-int dsoft_selftest_chain(const void* a_bf16_dev, const void* b_bf16_dev, const void* v_bf16_dev,
+/* Test / bring-up helper: out[M][F] (fp32) = fp16(A . B^T) . V with A [M][K], B [N][K] bf16 and
+ * V [N][F] fp16: the backward data path (tile -> fp16 G tile in swizzled shared memory -> second tcgen05
+ * GEMM with an MN-major fp16 operand) without any soft-max arithmetic. */
+int dsoft_selftest_chain(const void* a_bf16_dev, const void* b_bf16_dev, const void* v_fp16_dev,
                          float* out_dev, int M, int N, int K, int F, void* stream);
 
 #ifdef __cplusplus

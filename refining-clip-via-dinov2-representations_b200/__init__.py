@@ -1,0 +1,29 @@
+"""B200-native DINO-Soft loss path (drop-in for the reference's ``open_clip.loss.ClipLossWithDINOEnhancements``).
+
+Import as ``dinosoft_b200`` (see the shim at the repo root).  Contents:
+
+    loss.py      the nn.Module with the reference's ctor/forward signature, gather_features,
+                 compute_student_tau, install_into_open_clip
+    _cabi.py     ctypes binding of libdsoft.so (include/dsoft.h)
+    _build.py    nvcc recipe for csrc/ (sm_100a only)
+    csrc/        hand-written tcgen05 / TMEM / TMA kernels + the C ABI
+"""
+from . import _build, _cabi
+from ._build import build
+from .loss import (
+    ClipLossWithDINOEnhancements,
+    CudaBackend,
+    compute_student_tau,
+    gather_features,
+    install_into_open_clip,
+)
+
+__version__ = "0.1.0"
+__all__ = [
+    "ClipLossWithDINOEnhancements",
+    "CudaBackend",
+    "compute_student_tau",
+    "gather_features",
+    "install_into_open_clip",
+    "build",
+]

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -61,7 +62,9 @@ struct dsoft_plan {
   size_t st_scal, st_rinv_t, st_rinv_z, st_rinv_d, st_diag, st_lsecols, st_total;
   // scratch layout (float offsets)
   size_t sc_pc_it, sc_pc_ti, sc_ps, sc_rowloss, sc_acc1, sc_acc2, sc_acc3, sc_acc4, sc_ds1, sc_ds2,
-      sc_dsrow, sc_total;
+      sc_dsrow, sc_v16, sc_total;
+  // fp16 gradient-operand buffer [B][v_row]: text | image | normalised student | normalised text
+  int v_offT, v_offI, v_offZn, v_offTn, v_row;
 };
 
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -184,6 +187,12 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   p->sc_ds1 = take(2 * p->b_clip.nsplit * b);
   p->sc_ds2 = take(2 * p->b_clip.nsplit * b);
   p->sc_dsrow = take(b);
+  p->v_offT = 0;
+  p->v_offI = sh->D;
+  p->v_offZn = 2 * sh->D;
+  p->v_offTn = 2 * sh->D + (soft ? p->Dz : 0);
+  p->v_row = p->v_offTn + (p->have_text ? sh->D : 0);
+  p->sc_v16 = take(static_cast<size_t>(p->B) * p->v_row / 2 + 1);
   p->sc_total = o;
 
   *out = p;
@@ -215,7 +224,7 @@ extern "C" int dsoft_plan_launches_forward(const dsoft_plan_t* p) {
 }
 extern "C" int dsoft_plan_launches_backward(const dsoft_plan_t* p) {
   if (!p) return 0;
-  return 1 /*relayout*/ + 2 /*clip x2*/ + (p->have_soft ? 1 : 0) + (p->have_text ? 1 : 0) +
+  return 2 /*relayout, fp16 operands*/ + 2 /*clip x2*/ + (p->have_soft ? 1 : 0) + (p->have_text ? 1 : 0) +
          2 /*finalize, ds reduce*/;
 }
 
@@ -240,14 +249,15 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // bf16 matrix [rows][cols] with row pitch `pitch_elems`; box = 64 columns x 128 rows, 128B swizzle.
-static int make_map(CUtensorMap* map, const void* base, int rows, int cols, size_t pitch_elems) {
+static int make_map(CUtensorMap* map, const void* base, int rows, int cols, size_t pitch_elems,
+                    CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(DSOFT_ENODEV, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(pitch_elems) * 2};
   cuuint32_t box[2] = {BK, BM};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+  CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box,
                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -432,6 +442,36 @@ __global__ void lse_relayout_kernel(const float* __restrict__ lse_all, int W, in
     float v = 0.f;
     if (j < W * b) v = lse_all[(static_cast<size_t>(j / b) * 5 + k) * b + (j % b)];
     out[i] = v;
+  }
+}
+
+// fp16 copies of the gradient-GEMM operands, one warp per global row:
+//   text | image (as used in the CLIP logits) | student / ||student|| | text / ||text||
+// fp16 keeps 10 mantissa bits for the normalised rows and lets the G tile be fp16 as well.
+__global__ void make_v16_kernel(const __nv_bfloat16* __restrict__ gathered, int row_elems, int B, int D,
+                                int Dz, int offI, int offT, int offZ, int have_soft, int have_text,
+                                const float* __restrict__ rinv_z, const float* __restrict__ rinv_t,
+                                __half* __restrict__ v16, int v_row, int v_offT, int v_offI, int v_offZn,
+                                int v_offTn) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= B) return;
+  const __nv_bfloat16* src = gathered + static_cast<size_t>(r) * row_elems;
+  __half* dst = v16 + static_cast<size_t>(r) * v_row;
+  const float rt = have_text ? rinv_t[r] : 0.f;
+  const float rz = have_soft ? rinv_z[r] : 0.f;
+  for (int c = lane * 2; c < D; c += 64) {
+    const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src + offT + c));
+    const float2 im = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src + offI + c));
+    *reinterpret_cast<__half2*>(dst + v_offT + c) = __floats2half2_rn(t.x, t.y);
+    *reinterpret_cast<__half2*>(dst + v_offI + c) = __floats2half2_rn(im.x, im.y);
+    if (have_text) *reinterpret_cast<__half2*>(dst + v_offTn + c) = __floats2half2_rn(t.x * rt, t.y * rt);
+  }
+  if (have_soft) {
+    for (int c = lane * 2; c < Dz; c += 64) {
+      const float2 z = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src + offZ + c));
+      *reinterpret_cast<__half2*>(dst + v_offZn + c) = __floats2half2_rn(z.x * rz, z.y * rz);
+    }
   }
 }
 
@@ -746,6 +786,16 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
   lse_relayout_kernel<<<ceil_div(5 * p->Bcol, 256), 256, 0, st>>>(lse_all, p->sh.world, b, p->Bcol, lsec);
   CUDA_TRY(cudaGetLastError());
   const float* lse_loc = lse_all + static_cast<size_t>(p->sh.rank) * 5 * b;
+  __half* v16 = reinterpret_cast<__half*>(X + p->sc_v16);
+  make_v16_kernel<<<ceil_div(p->B, 8), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(gathered), p->row_elems, p->B, p->sh.D, p->Dz, p->offI, p->offT,
+      p->offZ, p->have_soft, p->have_text, S + p->st_rinv_z, S + p->st_rinv_t, v16, p->v_row, p->v_offT,
+      p->v_offI, p->v_offZn, p->v_offTn);
+  CUDA_TRY(cudaGetLastError());
+  CUtensorMap vmap;
+  auto vmap_for = [&](int voff, int cols) {
+    return make_map(&vmap, v16 + voff, p->B, cols, p->v_row, CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+  };
 
   if ((rc = set_smem(dsoft_bwd_kernel<MODE_CLIP>, BWD_SMEM_BYTES))) return rc;
   if ((rc = set_smem(dsoft_bwd_kernel<MODE_SOFT>, BWD_SMEM_BYTES))) return rc;
@@ -769,26 +819,26 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
   P.a_map[0] = 0;
   P.b_map[0] = 1;
   P.kchunks[0] = ceil_div(p->sh.D, BK);
-  P.v_map = 1;
   P.dout = p->sh.D;
   P.want_ds = 1;
+  if ((rc = vmap_for(p->v_offT, p->sh.D))) return rc;
   P.lse_row = lse_loc + 0 * b;
   P.lse_col = lsec + 1 * p->Bcol;
   P.acc_part = X + p->sc_acc1;
   P.ds_part = X + p->sc_ds1;
   dsoft_bwd_kernel<MODE_CLIP>
-      <<<dim3(rbs, p->b_clip.nsplit, p->nch_clip), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, P);
+      <<<dim3(rbs, p->b_clip.nsplit, p->nch_clip), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, vmap, P);
   CUDA_TRY(cudaGetLastError());
   // ---- CLIP, text rows
   P.a_map[0] = 1;
   P.b_map[0] = 0;
-  P.v_map = 0;
+  if ((rc = vmap_for(p->v_offI, p->sh.D))) return rc;
   P.lse_row = lse_loc + 1 * b;
   P.lse_col = lsec + 0 * p->Bcol;
   P.acc_part = X + p->sc_acc2;
   P.ds_part = X + p->sc_ds2;
   dsoft_bwd_kernel<MODE_CLIP>
-      <<<dim3(rbs, p->b_clip.nsplit, p->nch_clip), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, P);
+      <<<dim3(rbs, p->b_clip.nsplit, p->nch_clip), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, vmap, P);
   CUDA_TRY(cudaGetLastError());
 
   if (p->have_soft) {
@@ -798,8 +848,8 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
     P.kchunks[0] = ceil_div(p->sh.Dd, BK);
     P.a_map[1] = P.b_map[1] = 2;
     P.kchunks[1] = ceil_div(p->Dz, BK);
-    P.v_map = 2;
     P.dout = p->Dz;
+    if ((rc = vmap_for(p->v_offZn, p->Dz))) return rc;
     P.tau_idx = SC_ITS_L2;
     P.lse_t_row = lse_loc + 2 * b;
     P.lse_t_col = lsec + 2 * p->Bcol;
@@ -809,7 +859,7 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
     P.rinv_y = S + p->st_rinv_z;
     P.acc_part = X + p->sc_acc3;
     dsoft_bwd_kernel<MODE_SOFT>
-        <<<dim3(rbs, p->b_stu.nsplit, p->nch_stu), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, P);
+        <<<dim3(rbs, p->b_stu.nsplit, p->nch_stu), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, vmap, P);
     CUDA_TRY(cudaGetLastError());
     if (p->have_text) {
       base(p->b_txt, p->s_col0, p->s_ncols, p->ntiles_s);
@@ -818,8 +868,8 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
       P.kchunks[0] = ceil_div(p->sh.Dd, BK);
       P.a_map[1] = P.b_map[1] = 1;
       P.kchunks[1] = ceil_div(p->sh.D, BK);
-      P.v_map = 1;
       P.dout = p->sh.D;
+      if ((rc = vmap_for(p->v_offTn, p->sh.D))) return rc;
       P.tau_idx = SC_ITX_L2;
       P.lse_t_row = lse_loc + 2 * b;
       P.lse_t_col = lsec + 2 * p->Bcol;
@@ -829,7 +879,7 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
       P.rinv_y = S + p->st_rinv_t;
       P.acc_part = X + p->sc_acc4;
       dsoft_bwd_kernel<MODE_SOFT>
-          <<<dim3(rbs, p->b_txt.nsplit, p->nch_txt), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, P);
+          <<<dim3(rbs, p->b_txt.nsplit, p->nch_txt), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, vmap, P);
       CUDA_TRY(cudaGetLastError());
     }
   }
@@ -912,8 +962,8 @@ extern "C" int dsoft_selftest_gemm(const void* a, const void* bmat, float* c, in
   return 0;
 }
 
-// out[M][F] (fp32) = bf16(A . B^T) . V   with A [M][K], B [N][K], V [N][F] (bf16): the backward data path
-// (tile -> bf16 G in swizzled smem -> second tcgen05 GEMM with an MN-major operand) without any soft-max.
+// out[M][F] (fp32) = fp16(A . B^T) . V   with A [M][K], B [N][K] bf16 and V [N][F] fp16: the backward data
+// path (tile -> fp16 G in swizzled smem -> second tcgen05 GEMM with an MN-major operand) without any soft-max.
 extern "C" int dsoft_selftest_chain(const void* a, const void* bmat, const void* vmat, float* out, int M,
                                     int N, int K, int F, void* stream) {
   if (!a || !bmat || !vmat || !out || M <= 0 || N <= 0 || K <= 0 || K % 8 || F <= 0 || F % 8)
@@ -925,8 +975,10 @@ extern "C" int dsoft_selftest_chain(const void* a, const void* bmat, const void*
   TileMaps tm;
   if ((rc = make_map(&tm.m[0], a, M, K, K))) return rc;
   if ((rc = make_map(&tm.m[1], bmat, N, K, K))) return rc;
-  if ((rc = make_map(&tm.m[2], vmat, N, F, F))) return rc;
+  tm.m[2] = tm.m[0];
   tm.m[3] = tm.m[0];
+  CUtensorMap vmap;
+  if ((rc = make_map(&vmap, vmat, N, F, F, CU_TENSOR_MAP_DATA_TYPE_FLOAT16))) return rc;
   if ((rc = set_smem(dsoft_bwd_kernel<MODE_RAW>, BWD_SMEM_BYTES))) return rc;
   BwdParams P;
   memset(&P, 0, sizeof(P));
@@ -934,7 +986,6 @@ extern "C" int dsoft_selftest_chain(const void* a, const void* bmat, const void*
   P.a_map[0] = 0;
   P.b_map[0] = 1;
   P.kchunks[0] = ceil_div(K, BK);
-  P.v_map = 2;
   P.dout = F;
   P.row0 = 0;
   P.b = M;
@@ -945,7 +996,7 @@ extern "C" int dsoft_selftest_chain(const void* a, const void* bmat, const void*
   P.nsplit = 1;
   P.acc_part = out;
   dsoft_bwd_kernel<MODE_RAW>
-      <<<dim3(ceil_div(M, BM), 1, ceil_div(F, CHUNK_F)), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, P);
+      <<<dim3(ceil_div(M, BM), 1, ceil_div(F, CHUNK_F)), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, vmap, P);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -78,7 +78,6 @@ struct BwdParams {
   int a_map[2];
   int b_map[2];
   int kchunks[2];
-  int v_map;       // operand of the gradient GEMM (== column-side operand of the last product)
   int dout;        // feature width of the gradient
   int row0, b, col0, ncols, ntiles, tiles_per_split, nsplit;
   int row_only;    // gather_with_grad == False: gathered columns are constants
@@ -412,11 +411,15 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
 // ================================================================================================
 //  MODE_CLIP: G_aj = 2^(x - lse_row_a) + 2^(x - lse_col_j)        (the -2*delta one-hot part and the
 //             s/(2b) factor are applied in fp32 by the finalize kernel)
-//  MODE_SOFT: G_aj = ry_j * [ (2^(p-ls_a) + 2^(p-ls_j)) - (2^(q-lt_a) + 2^(q-lt_j)) ],  q diag masked
+//  MODE_SOFT: G_aj = (2^(p-ls_a) + 2^(p-ls_j)) - (2^(q-lt_a) + 2^(q-lt_j)),  q diag masked
+//  G is stored as fp16 (|G| <= 2, 10-bit mantissa) and multiplied with an fp16 copy of the gradient
+//  operand (already L2-normalised for the soft terms): bf16 G costs 8x the rounding error and mixed
+//  fp16 x bf16 operands are not accepted by tcgen05.mma.
 //  row_only drops the *_j (column-side) terms: gathered features are constants (gather_with_grad=0).
 template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ BwdParams P) {
+dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ CUtensorMap vmap,
+                 const __grid_constant__ BwdParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_1024(smem_raw);
   uint8_t* v_smem = smem + B_STAGES * 2 * TILE_BYTES;  // 4 boxes: 128 columns(j) x 256 features
@@ -442,10 +445,10 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   const int t1 = min(t0 + P.tiles_per_split, P.ntiles);
   const int f0 = chunk * CHUNK_F;                            // first gradient feature of this pass
   const int nfb = min(4, (P.dout - f0 + BK - 1) / BK);       // 64-feature boxes in this pass
-  const int vmap = P.v_map;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) tma_prefetch_desc(&maps.m[i]);
+    tma_prefetch_desc(&vmap);
     for (int i = 0; i < B_STAGES; ++i) {
       mbar_init(smem_u32(&ring_full[i]), 1);
       mbar_init(smem_u32(&ring_empty[i]), 1);
@@ -487,12 +490,12 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
             if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
           }
         }
-        // gradient operand Y[j-tile, f0 : f0 + 64*nfb]  (same boxes as a B operand, used MN-major)
+        // gradient operand Y16[j-tile, f0 : f0 + 64*nfb]  (fp16 copy, same box shape, used MN-major)
         mbar_wait(smem_u32(v_empty), (static_cast<uint32_t>(n) & 1) ^ 1);
         const uint32_t vf = smem_u32(v_full);
         mbar_arrive_expect_tx(vf, nfb * TILE_BYTES);
         for (int fb = 0; fb < nfb; ++fb)
-          tma_load_2d(smem_u32(v_smem + fb * TILE_BYTES), &maps.m[vmap], vf, f0 + fb * BK,
+          tma_load_2d(smem_u32(v_smem + fb * TILE_BYTES), &vmap, vf, f0 + fb * BK,
                       P.col0 + t * BN);
       }
     }
@@ -503,7 +506,7 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       uint32_t phase = 0;
       int it = 0;
       int n = 0;
-      const uint32_t idesc_g = make_idesc_bf16(BM, nfb * BK, 0, 1);  // A = G (K-major), B = Y (MN-major)
+      const uint32_t idesc_g = make_idesc_bf16(BM, nfb * BK, 0, 1, 1);  // fp16: A = G (K-major), B = Y16 (MN-major)
       const uint32_t tmem_acc = tmem_base + ACC_COL;
       auto issue_grad = [&](int mt) {
         mbar_wait(smem_u32(g_full), static_cast<uint32_t>(mt) & 1);
@@ -648,7 +651,7 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
                 const float p2 = v[e] * c_b * rr[k];
                 const float e1 = fast_exp2(p2 - l_b);
                 const float e2 = row_only ? 0.f : fast_exp2(p2 - ll[k]);
-                g[e] = (g[e] + (e1 + e2)) * rr[k];  // fold the column's 1/||y_j|| into G
+                g[e] = g[e] + (e1 + e2);  // 1/||y_j|| lives in the fp16 gradient operand
               }
             }
           }
@@ -661,10 +664,10 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
         // 32 values -> 4 x 16-byte swizzled stores into the K-major SW128 A-operand layout
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {
-          const uint32_t w0 = pack_bf16x2(g[8 * k4 + 0], g[8 * k4 + 1]);
-          const uint32_t w1 = pack_bf16x2(g[8 * k4 + 2], g[8 * k4 + 3]);
-          const uint32_t w2 = pack_bf16x2(g[8 * k4 + 4], g[8 * k4 + 5]);
-          const uint32_t w3 = pack_bf16x2(g[8 * k4 + 6], g[8 * k4 + 7]);
+          const uint32_t w0 = pack_f16x2(g[8 * k4 + 0], g[8 * k4 + 1]);
+          const uint32_t w1 = pack_f16x2(g[8 * k4 + 2], g[8 * k4 + 3]);
+          const uint32_t w2 = pack_f16x2(g[8 * k4 + 4], g[8 * k4 + 5]);
+          const uint32_t w3 = pack_f16x2(g[8 * k4 + 6], g[8 * k4 + 7]);
           const int chunk16 = c * 4 + k4;
           st_shared_v4(g_row + ((chunk16 ^ sw) << 4), w0, w1, w2, w3);
         }

@@ -134,8 +134,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 // Instruction descriptor for kind::f16 with bf16 operands and fp32 accumulation.
 //   bits [4,6) c_format (1 = f32), [7,10) a_format (1 = bf16), [10,13) b_format (1 = bf16),
 //   bit 15 a_major (0 = K-major), bit 16 b_major (1 = MN-major), [17,23) N>>3, [24,29) M>>4
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+//   f16 = 1 selects fp16 (format 0) for BOTH operands: the hardware rejects mixed fp16 x bf16
+//   (measured: cudaErrorIllegalInstruction), so A and B always share one format.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major,
+                                                       int f16 = 0) {
+  return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) |
+         (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
@@ -194,6 +198,13 @@ __device__ __forceinline__ float fast_log2(float x) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// two fp32 -> packed f16x2 (lo = first argument)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
 

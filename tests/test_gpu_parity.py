@@ -1,0 +1,121 @@
+"""Parity of the CUDA path (through the module -> C ABI) with the CPU oracle on identical inputs.
+
+Tolerances are north_star's: loss <= 1e-4 relative, gradients <= 1e-3 relative (max-abs over max-abs and
+L2 over L2), fp32 accumulation, bf16 operands."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import head_params_of, make_args, oracle_cfg, rel_err, synth
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-4
+GRAD_RTOL = 1e-3
+
+
+def run_cuda(pkg, img, txt, dino, scale, args, head_seed=7, **ctor):
+    dev = "cuda"
+    loss = pkg.ClipLossWithDINOEnhancements(**ctor)
+    im = img.to(dev).requires_grad_(True)
+    tx = txt.to(dev).requires_grad_(True)
+    sc = torch.tensor(scale, device=dev, requires_grad=True)
+    dn = None if dino is None else dino.to(dev)
+    if dn is not None and args.use_projection:
+        torch.manual_seed(head_seed)
+        loss.init_proj(img.shape[1], dino.shape[1], dev, args.projection_type,
+                       layernorm=getattr(args, "use_layernorm", False))
+    out = loss(im, tx, sc, dn, args, output_dict=True)
+    out["total_loss"].backward()
+    torch.cuda.synchronize()
+    return loss, out, im.grad, tx.grad, sc.grad
+
+
+def check_against_oracle(pkg, oracle, B, D, Dd, scale, args, seed=0, clustered=True):
+    img, txt, dino = synth(seed, B, D, Dd, clustered)
+    loss, out, gi, gt, gs = run_cuda(pkg, img, txt, dino, scale, args)
+    head = None
+    if args.use_projection and loss.image_to_dino_proj is not None:
+        head = {k: v.detach().cpu() for k, v in
+                head_params_of(loss.image_to_dino_proj, args.projection_type,
+                               getattr(args, "use_layernorm", False)).items()}
+    cfg = oracle_cfg(oracle, args, round_student_bf16=True)
+    ref = oracle.loss_and_grads(img, txt, scale, dino, cfg, proj_params=head,
+                                projection_type=args.projection_type, dtype=torch.float64)["ranks"][0]
+    for k in ("total_loss", "classic_loss", "soft_loss"):
+        got = float(out[k].detach())
+        print(f"[parity] B={B} D={D} Dd={Dd} s={scale} {k}: got={got:.7f} ref={ref[k]:.7f} rel={abs(got - ref[k]) / max(abs(ref[k]), 1e-30):.2e}")
+        assert got == pytest.approx(ref[k], rel=LOSS_RTOL, abs=1e-6), (k, got, ref[k])
+    for name, got, want in (("d_image", gi, ref["d_image"]), ("d_text", gt, ref["d_text"])):
+        linf, l2 = rel_err(got, want)
+        print(f"[parity] B={B} D={D} Dd={Dd} s={scale} {name}: linf={linf:.2e} l2={l2:.2e}")
+        assert linf < GRAD_RTOL and l2 < GRAD_RTOL, (name, linf, l2)
+    print(f"[parity] d_logit_scale got={float(gs):.6e} ref={ref['d_logit_scale']:.6e}")
+    assert float(gs) == pytest.approx(ref["d_logit_scale"], rel=GRAD_RTOL, abs=1e-7)
+    if head is not None and "d_proj" in ref:
+        got_head = head_params_of(loss.image_to_dino_proj, args.projection_type, getattr(args, "use_layernorm", False))
+        for k, want in ref["d_proj"].items():
+            if want is None:
+                continue
+            linf, l2 = rel_err(got_head[k].grad, want)
+            print(f"[parity] head {k}: linf={linf:.2e} l2={l2:.2e}")
+            assert linf < 3 * GRAD_RTOL and l2 < 3 * GRAD_RTOL, ("head " + k, linf, l2)
+    return out, ref
+
+
+def test_classic_only_small(pkg, oracle):
+    check_against_oracle(pkg, oracle, 256, 512, 768, 14.2857, make_args(lambda_soft=0.0, soft_mode="none"))
+
+
+def test_config1_noproj_text(pkg, oracle):
+    """BASELINE config 1 sizes (B=256, D=512, Dd=768), student = image features."""
+    check_against_oracle(pkg, oracle, 256, 512, 768, 14.2857, make_args())
+
+
+def test_config1_mlp_text(pkg, oracle):
+    check_against_oracle(pkg, oracle, 256, 512, 768, 14.2857, make_args(use_projection=True))
+
+
+def test_scale_100_linear_head(pkg, oracle):
+    check_against_oracle(pkg, oracle, 384, 512, 768, 100.0,
+                         make_args(use_projection=True, projection_type="linear", soft_dino_to_text=False))
+
+
+def test_iid_gaussian_flat_teacher(pkg, oracle):
+    check_against_oracle(pkg, oracle, 512, 256, 384, 30.0, make_args(), seed=3, clustered=False)
+
+
+@pytest.mark.parametrize("B,D,Dd", [(200, 72, 136), (130, 64, 64), (1000, 320, 200)])
+def test_ragged_sizes(pkg, oracle, B, D, Dd):
+    """Rows/columns that are not multiples of the 128 x 128 tile, K not a multiple of 64."""
+    check_against_oracle(pkg, oracle, B, D, Dd, 20.0, make_args(use_projection=True), seed=5)
+
+
+def test_column_split_many_tiles(pkg, oracle):
+    """B large enough that every kernel splits the column range over several CTAs."""
+    check_against_oracle(pkg, oracle, 2048, 128, 192, 50.0, make_args(use_projection=True), seed=9)
+
+
+def test_output_dict_false_returns_none(pkg):
+    img, txt, dino = synth(0, 128, 64, 64)
+    loss = pkg.ClipLossWithDINOEnhancements()
+    assert loss(img.cuda(), txt.cuda(), torch.tensor(10.0).cuda(), dino.cuda(), make_args()) is None
+
+
+def test_matches_golden_fixture_directly(pkg):
+    """CUDA path vs the reference-generated fixture (no projection, so no operand-rounding caveat)."""
+    import os
+    from conftest import GOLDEN_DIR
+
+    z = np.load(os.path.join(GOLDEN_DIR, "w1_noproj_text.npz"))
+    img, txt, dino = (torch.from_numpy(z[k]) for k in ("image", "text", "dino"))
+    args = make_args(use_projection=False)
+    _, out, gi, gt, gs = run_cuda(pkg, img, txt, dino, float(z["scale"]), args)
+    assert float(out["total_loss"]) == pytest.approx(float(z["f64_r0_total_loss"]), rel=LOSS_RTOL)
+    assert float(out["classic_loss"]) == pytest.approx(float(z["f64_r0_classic_loss"]), rel=LOSS_RTOL)
+    assert float(out["soft_loss"]) == pytest.approx(float(z["f64_r0_soft_loss"]), rel=LOSS_RTOL)
+    for got, key in ((gi, "d_image"), (gt, "d_text")):
+        linf, l2 = rel_err(got, torch.from_numpy(z["f64_r0_" + key]))
+        print(f"[parity] golden {key}: linf={linf:.2e} l2={l2:.2e}")
+        assert linf < GRAD_RTOL and l2 < GRAD_RTOL, (key, linf, l2)
+    assert float(gs) == pytest.approx(float(z["f64_r0_d_logit_scale"]), rel=GRAD_RTOL, abs=1e-7)
