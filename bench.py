@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""Benchmark of the DINO-Soft loss hot path (fwd + bwd), BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N = 1 (default): global batch B = 32768 (BASELINE config 3's batch, which fits one B200 because the
+B x B logits are never materialised), D = 512, DINO dim 768, MLP projection head, text-symmetric soft
+term.  N > 1 (launched by torchrun): the same global batch sharded by row block (strong scaling),
+one NCCL all-gather of the packed bf16 embeddings per step.
+
+One JSON line is printed by rank 0.  `value` = samples/s with inputs resident in HBM; `e2e` = the same
+metric through the module with pinned HOST inputs (H2D inside the timed region, loss read back);
+`roofline` = the dominant tile kernel against the measured bf16 tensor peak; `cpu_baseline` = the CPU
+oracle (a port of the reference loss) timed on this box's host cores on a bounded sample.
+`--impl reference` times only that CPU port (the reference itself is Python that cannot travel to the
+GPU box; the oracle is pinned to it by tests/golden).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import importlib.util
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+import types
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "dino_soft_loss_fwd_bwd_samples_per_sec"
+GLOBAL_B, D_CLIP, D_DINO = 32768, 512, 768
+KERNEL_NAMES = ["fwd_clip_i2t", "fwd_clip_t2i", "fwd_soft", "bwd_clip_image", "bwd_clip_text",
+                "bwd_student", "bwd_text"]
+LOSS_ARGS = dict(use_projection=True, projection_type="mlp", lambda_soft=0.5, soft_mode="kl_teacher",
+                 soft_dino_to_text=True, text_lambda=0.5, text_student_temp=0.02, teacher_temp=0.15,
+                 lambda_original=1.0, lambda_weighted=0.0)
+
+
+def load_oracle():
+    spec = importlib.util.spec_from_file_location("dinosoft_oracle", os.path.join(ROOT, "oracle", "dinosoft_oracle.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["dinosoft_oracle"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def synth(seed, rows, D, Dd, device, clustered=True):
+    """SURVEY.md 8(d) synthetic inputs: clustered embeddings, image/text L2-normalised, DINO raw."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    K = max(rows // 16, 2)
+    cid = torch.randint(0, K, (rows,), generator=g)
+
+    def make(d, scale=1.0):
+        cent = torch.randn(K, d, generator=g)
+        return (cent[cid] + 0.5 * torch.randn(rows, d, generator=g)) * scale
+
+    img = torch.nn.functional.normalize(make(D), dim=-1)
+    txt = torch.nn.functional.normalize(make(D), dim=-1)
+    dino = make(Dd, 3.0)
+    r = lambda x: x.to(torch.bfloat16).to(torch.float32)
+    return r(img).to(device), r(txt).to(device), r(dino).to(device)
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU port (oracle) timing
+# --------------------------------------------------------------------------------------------------
+def cpu_port_step(oracle, img, txt, dino, head, scale, cfg):
+    """One fwd+bwd of the reference algorithm (fp32, torch CPU ops, all host threads)."""
+    im = img.clone().requires_grad_(True)
+    tx = txt.clone().requires_grad_(True)
+    sc = torch.tensor(scale, requires_grad=True)
+    pp = {k: v.clone().requires_grad_(True) for k, v in head.items()}
+    student = oracle.mlp_head(im, pp, "mlp")
+    out = oracle.rank_loss(im, tx, sc, dino, student, cfg, rank=0)
+    out["total_loss"].backward()
+    return float(out["total_loss"].detach())
+
+
+def cpu_port_setup(oracle, B):
+    torch.manual_seed(0)
+    img, txt, dino = synth(4321, B, D_CLIP, D_DINO, "cpu")
+    H = (D_CLIP + D_DINO) // 2
+    l0, l1 = torch.nn.Linear(D_CLIP, H), torch.nn.Linear(H, D_DINO)
+    head = {"w0": l0.weight.detach(), "b0": l0.bias.detach(), "w1": l1.weight.detach(), "b1": l1.bias.detach()}
+    cfg = oracle.OracleConfig(lambda_soft=0.5, soft_mode="kl_teacher", soft_dino_to_text=True, text_lambda=0.5,
+                              text_student_temp=0.02, teacher_temp=0.15)
+    return img, txt, dino, head, cfg
+
+
+def time_cpu_port(sample_B, iters, warmup=1):
+    oracle = load_oracle()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    img, txt, dino, head, cfg = cpu_port_setup(oracle, sample_B)
+    for _ in range(warmup):
+        cpu_port_step(oracle, img, txt, dino, head, 14.2857, cfg)
+    times = []
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        cpu_port_step(oracle, img, txt, dino, head, 14.2857, cfg)
+        times.append(time.perf_counter() - t0)
+    return times, cores
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample: B = 2048 rows of the same workload per step (the full B = 32768 needs ~40 GiB of
+    # fp32 B x B intermediates and minutes per step on CPU); cost per sample grows linearly with B.
+    sample_B = 2048
+    times, cores = time_cpu_port(sample_B, args.steps, args.warmup)
+    total = sum(times)
+    value = sample_B * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"B={sample_B} rows per step of the same workload (D=512, Dd=768, MLP head, "
+                                   f"text-symmetric), fp32 torch CPU ops, {cores} threads"},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n):
+    return {
+        "workload": f"DINO-Soft loss fwd+bwd, global batch {GLOBAL_B} (BASELINE config 3 batch), D={D_CLIP}, "
+                    f"DINOv2 dim {D_DINO}, MLP projection head, text-symmetric soft term, logit_scale=14.2857",
+        "global_batch": GLOBAL_B, "local_batch": GLOBAL_B // n, "D": D_CLIP, "Dd": D_DINO,
+        "parallelism": f"row-block x{n}" if n > 1 else "single GPU",
+        "l2": "inputs larger than L2 (packed bf16 embeddings 168 MB, fp16 gradient operands 151 MB)",
+    }
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import dinosoft_b200 as pkg
+    from dinosoft_b200 import _cabi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA sm_100 device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert GLOBAL_B % world == 0
+    b = GLOBAL_B // world
+    lib = _cabi.lib()
+
+    img, txt, dino = synth(1234 + rank, b, D_CLIP, D_DINO, dev)
+    larg = types.SimpleNamespace(**LOSS_ARGS)
+    loss = pkg.ClipLossWithDINOEnhancements(local_loss=True, gather_with_grad=True, rank=rank, world_size=world)
+    torch.manual_seed(99)
+    loss.init_proj(D_CLIP, D_DINO, dev, "mlp")
+    scale = torch.tensor(14.2857, device=dev, requires_grad=True)
+    img.requires_grad_(True)
+    txt.requires_grad_(True)
+    params = list(loss.image_to_dino_proj.parameters())
+
+    def zero_grads():
+        img.grad = txt.grad = scale.grad = None
+        for p in params:
+            p.grad = None
+
+    def step(im, tx, dn):
+        out = loss(im, tx, scale, dn, larg, output_dict=True)
+        out["total_loss"].backward()
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for _ in range(max(args.warmup, 3)):
+        zero_grads()
+        step(img, txt, dino)
+    barrier()
+
+    # ---- timed region: resident inputs
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.dsoft_profile_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        zero_grads()
+        out = step(img, txt, dino)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_sum = (C.c_double * 7)()
+    cnt = (C.c_int * 7)()
+    _cabi.check(lib.dsoft_profile_read(ms_sum, cnt, 7), "dsoft_profile_read")
+    lib.dsoft_profile_enable(0)
+    final_loss = float(out["total_loss"].detach())
+
+    # ---- e2e: pinned host inputs -> H2D -> module -> loss scalars back to the host, every step
+    h_img = img.detach().cpu().pin_memory()
+    h_txt = txt.detach().cpu().pin_memory()
+    h_dino = dino.detach().cpu().pin_memory()
+    h2d_bytes = (h_img.numel() + h_txt.numel() + h_dino.numel()) * 4
+    host_out = torch.empty(3, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        zero_grads()
+        im = h_img.to(dev, non_blocking=True).requires_grad_(True)
+        tx = h_txt.to(dev, non_blocking=True).requires_grad_(True)
+        dn = h_dino.to(dev, non_blocking=True)
+        o = step(im, tx, dn)
+        host_out.copy_(torch.stack([o["total_loss"].detach(), o["classic_loss"].detach(), o["soft_loss"].detach()]),
+                       non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the training loop reads the loss every step (train.py:354)
+        return float(host_out[0])
+
+    ms_e2e = float("nan")
+    if not args.no_e2e:
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        f1.record()
+        barrier()
+        ms_e2e = f0.elapsed_time(f1)
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        from dinosoft_b200.loss import _cuda_backend
+
+        plan = next(iter(_cuda_backend._plans.values()))
+        alg = (C.c_double * 7)()
+        exe = (C.c_double * 7)()
+        _cabi.check(lib.dsoft_plan_kernel_flops(plan.handle, alg, exe, 7), "dsoft_plan_kernel_flops")
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_burst = peaks.get("bf16_tflops")
+        peak_sust = peaks.get("bf16_tflops_sustained")
+        peak_src = "MEASURED_PEAKS.json (bf16_tflops_sustained: kernels timed inside a long step)"
+        if not peak_sust:
+            peak_sust, peak_burst, peak_src = 1400.0, 1590.0, "fallback (B200_PROFILING.md: 1.59 PF burst / ~1.4 PF sustained)"
+        kern = {}
+        for k, name in enumerate(KERNEL_NAMES):
+            if cnt[k] == 0:
+                continue
+            avg_ms = ms_sum[k] / cnt[k]
+            kern[name] = {"ms": round(avg_ms, 4), "alg_tflops": round(alg[k] / avg_ms / 1e9, 1),
+                          "exec_tflops": round(exe[k] / avg_ms / 1e9, 1), "launches": cnt[k]}
+        dom = max(kern, key=lambda n: kern[n]["ms"])
+        dk = KERNEL_NAMES.index(dom)
+        dom_ms = ms_sum[dk] / cnt[dk]
+        achieved = alg[dk] / dom_ms / 1e9
+        tile_ms = sum(ms_sum[k] for k in range(7)) / args.steps
+        step_ms = ms / args.steps
+        step_alg_tflops = plan.flops / step_ms / 1e9  # this rank's algorithmic FLOPs / step time
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu_times, cores = time_cpu_port(4096, 2, 1)
+            cpu_baseline = {
+                "value": 4096 * len(cpu_times) / sum(cpu_times), "unit": "samples/s", "cores": cores, "kind": "port",
+                "sample": "B=4096 rows of the same workload (D=512, Dd=768, MLP head, text-symmetric), fp32 torch "
+                          "CPU ops, 1 warm-up + 2 timed fwd+bwd; per-sample cost grows linearly with B"}
+        launches_per_step = plan.launches_fwd + plan.launches_bwd + 4  # + 4 pack kernels
+        line = {
+            "metric": METRIC, "value": GLOBAL_B * args.steps / (ms / 1e3), "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(world),
+            "clocks": clocks,
+            "e2e": None if args.no_e2e else {
+                "value": GLOBAL_B * args.steps / (ms_e2e / 1e3), "unit": "samples/s",
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"bound": "tensor", "kernel": dom, "achieved": round(achieved, 1), "peak": peak_sust,
+                         "unit": "TFLOP/s", "frac": round(achieved / peak_sust, 4), "traffic": None,
+                         "peak_source": peak_src, "peak_burst": peak_burst,
+                         "executed_tflops": kern[dom]["exec_tflops"],
+                         "executed_frac": round(kern[dom]["exec_tflops"] / peak_sust, 4),
+                         "note": "achieved = algorithmic FLOPs of this launch (SURVEY 8d: each distinct product "
+                                 "once, tile recompute not counted) / its CUDA-event duration"},
+            "step_roofline": {"algorithmic_tflops_per_gpu": round(step_alg_tflops, 1),
+                              "frac_of_sustained_peak": round(step_alg_tflops / peak_sust, 4),
+                              "frac_of_burst_peak": round(step_alg_tflops / peak_burst, 4) if peak_burst else None,
+                              "tile_kernel_ms_per_step": round(tile_ms, 4),
+                              "tile_kernel_share_of_step": round(tile_ms / step_ms, 4)},
+            "kernels": kern,
+            "cpu_baseline": cpu_baseline,
+            "loss": final_loss,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    global GLOBAL_B
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU port timing (profiling runs)")
+    ap.add_argument("--batch", type=int, default=32768, help="global batch (default: BASELINE's 32768)")
+    args = ap.parse_args()
+    GLOBAL_B = args.batch
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

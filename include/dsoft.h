@@ -79,6 +79,11 @@ size_t dsoft_plan_state_bytes(const dsoft_plan_t* plan);
 size_t dsoft_plan_scratch_bytes(const dsoft_plan_t* plan);
 /* Algorithmic FLOPs of one fwd+bwd evaluation for this rank (SURVEY.md 8(d) formula / world). */
 double dsoft_plan_algorithmic_flops(const dsoft_plan_t* plan);
+/* FLOPs of the 7 tile-kernel launches of one fwd+bwd for this rank, in dsoft_profile_read order:
+ * fwd clip i->t, fwd clip t->i, fwd soft, bwd clip (image rows), bwd clip (text rows), bwd student,
+ * bwd text.  `algorithmic` follows SURVEY.md 8(d) (each distinct product once, no recompute);
+ * `executed` is what the tensor cores really do (tile recompute per 256-feature chunk included). */
+int dsoft_plan_kernel_flops(const dsoft_plan_t* plan, double* algorithmic, double* executed, int n);
 /* Number of CUDA kernels dsoft_forward / dsoft_backward launch (for bench.py's gpu_launches). */
 int dsoft_plan_launches_forward(const dsoft_plan_t* plan);
 int dsoft_plan_launches_backward(const dsoft_plan_t* plan);
@@ -108,6 +113,12 @@ int dsoft_backward(const dsoft_plan_t* plan, const void* gathered_dev, const voi
                    void* scratch_dev, const float* lse_all_dev, const float* gout_dev,
                    float* d_image_dev, float* d_text_dev, float* d_student_dev,
                    float* d_logit_scale_dev, void* stream);
+
+/* Optional timing of the tile kernels with CUDA events on the launching stream (bench.py roofline).
+ * dsoft_profile_read synchronises the device, returns summed milliseconds and launch counts per kernel
+ * kind (7 slots, order above) since the last read, and resets the recorder. */
+int dsoft_profile_enable(int on);
+int dsoft_profile_read(double* ms_sum, int* counts, int n);
 
 /* Test / bring-up helper: C[M][N] (fp32) = A[M][K] . B[N][K]^T with bf16 operands through the same
  * TMA + tcgen05 tile path the loss kernels use (128 x 128 tiles). */

@@ -37,6 +37,9 @@ PROTOTYPES = {
     "dsoft_plan_state_bytes": (C.c_size_t, [C.c_void_p]),
     "dsoft_plan_scratch_bytes": (C.c_size_t, [C.c_void_p]),
     "dsoft_plan_algorithmic_flops": (C.c_double, [C.c_void_p]),
+    "dsoft_plan_kernel_flops": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]),
+    "dsoft_profile_enable": (C.c_int, [C.c_int]),
+    "dsoft_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]),
     "dsoft_plan_launches_forward": (C.c_int, [C.c_void_p]),
     "dsoft_plan_launches_backward": (C.c_int, [C.c_void_p]),
     "dsoft_pack": (C.c_int, [C.c_void_p,

@@ -217,6 +217,29 @@ extern "C" double dsoft_plan_algorithmic_flops(const dsoft_plan_t* p) {
   if (p->have_text) f += 2.0 * b * cols_s * (2.0 * p->sh.D);
   return f;
 }
+// Per tile-kernel FLOP accounting (index = profile kind): algorithmic share per SURVEY 8(d) and the FLOPs
+// the kernel really executes (recompute per 256-feature chunk included).  Both for this rank.
+extern "C" int dsoft_plan_kernel_flops(const dsoft_plan_t* p, double* algorithmic, double* executed, int n) {
+  if (!p || !algorithmic || !executed || n < 7) return fail(DSOFT_EINVAL, "need 7 slots");
+  const double b = p->sh.b, Bc = p->B, Bs = p->s_ncols, D = p->sh.D, Dz = p->Dz, Dd = p->sh.Dd;
+  for (int k = 0; k < n; ++k) algorithmic[k] = executed[k] = 0.0;
+  // forward CLIP: the two directions are exact transposes -> one algorithmic product, two executed
+  algorithmic[0] = algorithmic[1] = b * Bc * D;
+  executed[0] = executed[1] = 2.0 * b * Bc * D;
+  algorithmic[3] = algorithmic[4] = 2.0 * b * Bc * D;
+  executed[3] = executed[4] = 2.0 * b * Bc * D * (p->nch_clip + 1.0);
+  if (p->have_soft) {
+    algorithmic[2] = executed[2] = 2.0 * b * Bs * (Dz + Dd + (p->have_text ? D : 0.0));
+    algorithmic[5] = 2.0 * b * Bs * Dz;
+    executed[5] = 2.0 * b * Bs * (p->nch_stu * (Dz + Dd) + Dz);
+  }
+  if (p->have_text) {
+    algorithmic[6] = 2.0 * b * Bs * D;
+    executed[6] = 2.0 * b * Bs * (p->nch_txt * (D + Dd) + D);
+  }
+  return 0;
+}
+
 extern "C" int dsoft_plan_launches_forward(const dsoft_plan_t* p) {
   if (!p) return 0;
   return 1 /*scalars*/ + (p->have_soft ? 3 : 1) /*norms*/ + 2 /*clip x2*/ + (p->have_soft ? 1 : 0) +
@@ -310,7 +333,7 @@ __global__ void pack_rows_kernel(const T* __restrict__ src, int64_t ld, __nv_bfl
 
 // one warp per row: out[r] = 1 / max(||row||, 1e-12)  (F.normalize eps, loss.py:345-359, 392)
 __global__ void rinv_kernel(const __nv_bfloat16* __restrict__ mat, int64_t ld, int rows, int cols,
-                            float* __restrict__ out, int out_len) {
+                            float* __restrict__ out, int out_len, float* __restrict__ rmin) {
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= out_len) return;
@@ -327,7 +350,11 @@ __global__ void rinv_kernel(const __nv_bfloat16* __restrict__ mat, int64_t ld, i
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) out[r] = 1.f / fmaxf(sqrtf(acc), 1e-12f);
+  if (lane == 0) {
+    const float rv = 1.f / fmaxf(sqrtf(acc), 1e-12f);
+    out[r] = rv;
+    atomicMin(reinterpret_cast<int*>(rmin), __float_as_int(rv));  // positive floats order like ints
+  }
 }
 
 // compute_student_tau (loss.py:166-175) + temperature reciprocals, all on device
@@ -348,6 +375,7 @@ __global__ void prep_scalars_kernel(const float* __restrict__ logit_scale, float
   scal[SC_ITT_L2] = teacher_temp > 0.f ? L2E / teacher_temp : 0.f;
   scal[SC_ITX] = text_temp > 0.f ? 1.f / text_temp : 0.f;
   scal[SC_ITX_L2] = text_temp > 0.f ? L2E / text_temp : 0.f;
+  scal[SC_RMIN_T] = scal[SC_RMIN_Z] = scal[SC_RMIN_D] = __int_as_float(0x7f800000);  // +inf
 }
 
 struct FinFwdArgs {
@@ -446,31 +474,32 @@ __global__ void lse_relayout_kernel(const float* __restrict__ lse_all, int W, in
 }
 
 // fp16 copies of the gradient-GEMM operands, one warp per global row:
-//   text | image (as used in the CLIP logits) | student / ||student|| | text / ||text||
-// fp16 keeps 10 mantissa bits for the normalised rows and lets the G tile be fp16 as well.
+//   text | image (as used in the CLIP logits) | student * sigma_z | text * sigma_t
+// sigma = 2^floor(log2(min_j 1/||row_j||)): a power-of-two scaling is exact, and bf16 -> fp16 is exact for
+// |x| in [2^-14, 65504), so the operands reach the tensor core unrounded; 1/(||row_j|| sigma) is folded
+// into the fp16 G tile instead.
 __global__ void make_v16_kernel(const __nv_bfloat16* __restrict__ gathered, int row_elems, int B, int D,
                                 int Dz, int offI, int offT, int offZ, int have_soft, int have_text,
-                                const float* __restrict__ rinv_z, const float* __restrict__ rinv_t,
-                                __half* __restrict__ v16, int v_row, int v_offT, int v_offI, int v_offZn,
-                                int v_offTn) {
+                                const float* __restrict__ scal, __half* __restrict__ v16, int v_row,
+                                int v_offT, int v_offI, int v_offZn, int v_offTn) {
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= B) return;
   const __nv_bfloat16* src = gathered + static_cast<size_t>(r) * row_elems;
   __half* dst = v16 + static_cast<size_t>(r) * v_row;
-  const float rt = have_text ? rinv_t[r] : 0.f;
-  const float rz = have_soft ? rinv_z[r] : 0.f;
+  const float st = have_text ? pow2_floor(scal[SC_RMIN_T]) : 0.f;
+  const float sz = have_soft ? pow2_floor(scal[SC_RMIN_Z]) : 0.f;
   for (int c = lane * 2; c < D; c += 64) {
     const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src + offT + c));
     const float2 im = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src + offI + c));
     *reinterpret_cast<__half2*>(dst + v_offT + c) = __floats2half2_rn(t.x, t.y);
     *reinterpret_cast<__half2*>(dst + v_offI + c) = __floats2half2_rn(im.x, im.y);
-    if (have_text) *reinterpret_cast<__half2*>(dst + v_offTn + c) = __floats2half2_rn(t.x * rt, t.y * rt);
+    if (have_text) *reinterpret_cast<__half2*>(dst + v_offTn + c) = __floats2half2_rn(t.x * st, t.y * st);
   }
   if (have_soft) {
     for (int c = lane * 2; c < Dz; c += 64) {
       const float2 z = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src + offZ + c));
-      *reinterpret_cast<__half2*>(dst + v_offZn + c) = __floats2half2_rn(z.x * rz, z.y * rz);
+      *reinterpret_cast<__half2*>(dst + v_offZn + c) = __floats2half2_rn(z.x * sz, z.y * sz);
     }
   }
 }
@@ -491,6 +520,7 @@ struct FinBwdArgs {
   const float* rinv_z;
   const float* rinv_t;
   const float* gout;  // [3]
+  const float* lse_loc;  // [5][b] this rank's row LSEs (log2)
   float* d_image;
   float* d_text;
   float* d_student;
@@ -516,7 +546,13 @@ __global__ void __launch_bounds__(128) finalize_bwd_kernel(FinBwdArgs a) {
   const float inv_b = 1.f / static_cast<float>(a.b);
   const float gc = a.gout[0], gs = a.gout[1], gx = a.gout[2];
   const float coefc = gc * a.scal[SC_SCALE] * 0.5f * inv_b;
-  const float onehot = a.row_only ? 1.f : 2.f;
+  // diagonal entry of the CE logit gradient, (p_it_aa - 1) + (p_ti_aa - 1), in fp32 via expm1
+  const float LN2 = 0.6931471805599453f;
+  const float xd = a.scal[SC_SCALE_L2] * a.diag[i];
+  const float dm_it = expm1f(LN2 * (xd - a.lse_loc[0 * a.b + i]));
+  const float dm_ti = expm1f(LN2 * (xd - a.lse_loc[1 * a.b + i]));
+  const float dg_img = a.row_only ? dm_it : dm_it + dm_ti;
+  const float dg_txt = a.row_only ? dm_ti : dm_it + dm_ti;
 
   // ---- CLIP part (loss.py:317-319 backward)
   for (int f = threadIdx.x; f < a.D; f += blockDim.x) {
@@ -527,8 +563,8 @@ __global__ void __launch_bounds__(128) finalize_bwd_kernel(FinBwdArgs a) {
     }
     const float tf = __bfloat162float(rowp[a.offT + f]);
     const float imf = __bfloat162float(rowp[a.offI + f]);
-    a.d_image[static_cast<size_t>(i) * a.D + f] = coefc * (u1 - onehot * tf);
-    a.d_text[static_cast<size_t>(i) * a.D + f] = coefc * (u2 - onehot * imf);
+    a.d_image[static_cast<size_t>(i) * a.D + f] = coefc * fmaf(dg_img, tf, u1);
+    a.d_text[static_cast<size_t>(i) * a.D + f] = coefc * fmaf(dg_txt, imf, u2);
   }
   if (threadIdx.x == 0) {
     float d = 0.f;
@@ -599,6 +635,60 @@ __global__ void reduce_ds_kernel(const float* __restrict__ dsrow, int b, const f
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (threadIdx.x == 0) out[0] = static_cast<float>(v * static_cast<double>(gout[0]) * 0.5 / b);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// optional per-kernel timing (bench.py's roofline): CUDA events around each tile-kernel launch
+// ------------------------------------------------------------------------------------------------
+enum { PK_FWD_CLIP_IT = 0, PK_FWD_CLIP_TI, PK_FWD_SOFT, PK_BWD_CLIP_I, PK_BWD_CLIP_T, PK_BWD_STU, PK_BWD_TXT,
+       PK_COUNT };
+static const int PROF_MAX = 4096;
+static struct {
+  int on = 0;
+  int n = 0;
+  cudaEvent_t ev0[PROF_MAX], ev1[PROF_MAX];
+  int kind[PROF_MAX];
+  int created = 0;
+} g_prof;
+
+struct ProfScope {
+  int idx = -1;
+  cudaStream_t st;
+  ProfScope(int kind, cudaStream_t s) : st(s) {
+    if (!g_prof.on || g_prof.n >= PROF_MAX) return;
+    if (g_prof.created <= g_prof.n) {
+      cudaEventCreate(&g_prof.ev0[g_prof.n]);
+      cudaEventCreate(&g_prof.ev1[g_prof.n]);
+      g_prof.created = g_prof.n + 1;
+    }
+    idx = g_prof.n++;
+    g_prof.kind[idx] = kind;
+    cudaEventRecord(g_prof.ev0[idx], st);
+  }
+  ~ProfScope() {
+    if (idx >= 0) cudaEventRecord(g_prof.ev1[idx], st);
+  }
+};
+
+extern "C" int dsoft_profile_enable(int on) {
+  g_prof.on = on;
+  g_prof.n = 0;
+  return 0;
+}
+
+// Synchronises the device, sums the recorded durations per kernel kind and resets the recorder.
+extern "C" int dsoft_profile_read(double* ms_sum, int* counts, int n) {
+  if (!ms_sum || !counts || n < PK_COUNT) return fail(DSOFT_EINVAL, "need %d slots", PK_COUNT);
+  CUDA_TRY(cudaDeviceSynchronize());
+  for (int k = 0; k < n; ++k) { ms_sum[k] = 0.0; counts[k] = 0; }
+  for (int i = 0; i < g_prof.n; ++i) {
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, g_prof.ev0[i], g_prof.ev1[i]));
+    ms_sum[g_prof.kind[i]] += ms;
+    counts[g_prof.kind[i]] += 1;
+  }
+  g_prof.n = 0;
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -698,12 +788,12 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
     const int wpb = 8;
     const int blocks = ceil_div(p->Bcol, wpb);
     rinv_kernel<<<blocks, wpb * 32, 0, st>>>(g + p->offT, p->row_elems, p->B, p->sh.D, S + p->st_rinv_t,
-                                             p->Bcol);
+                                             p->Bcol, S + p->st_scal + SC_RMIN_T);
     if (p->have_soft) {
       rinv_kernel<<<blocks, wpb * 32, 0, st>>>(g + p->offZ, p->row_elems, p->B, p->Dz, S + p->st_rinv_z,
-                                               p->Bcol);
+                                               p->Bcol, S + p->st_scal + SC_RMIN_Z);
       rinv_kernel<<<blocks, wpb * 32, 0, st>>>(g + p->offD, p->row_elems, p->B, p->sh.Dd,
-                                               S + p->st_rinv_d, p->Bcol);
+                                               S + p->st_rinv_d, p->Bcol, S + p->st_scal + SC_RMIN_D);
     }
     CUDA_TRY(cudaGetLastError());
   }
@@ -714,10 +804,16 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
   FwdParams P;
   // image -> text (loss.py:266/272) and text -> image (loss.py:267/273)
   fill_clip_fwd(p, P, 0, 1, S + p->st_scal, X + p->sc_pc_it, S + p->st_diag);
-  dsoft_fwd_kernel<MODE_CLIP><<<dim3(rbs, p->f_clip.nsplit), NUM_THREADS, FWD_SMEM_BYTES, st>>>(tm, P);
+  {
+    ProfScope ps(PK_FWD_CLIP_IT, st);
+    dsoft_fwd_kernel<MODE_CLIP><<<dim3(rbs, p->f_clip.nsplit), NUM_THREADS, FWD_SMEM_BYTES, st>>>(tm, P);
+  }
   CUDA_TRY(cudaGetLastError());
   fill_clip_fwd(p, P, 1, 0, S + p->st_scal, X + p->sc_pc_ti, S + p->st_diag);
-  dsoft_fwd_kernel<MODE_CLIP><<<dim3(rbs, p->f_clip.nsplit), NUM_THREADS, FWD_SMEM_BYTES, st>>>(tm, P);
+  {
+    ProfScope ps(PK_FWD_CLIP_TI, st);
+    dsoft_fwd_kernel<MODE_CLIP><<<dim3(rbs, p->f_clip.nsplit), NUM_THREADS, FWD_SMEM_BYTES, st>>>(tm, P);
+  }
   CUDA_TRY(cudaGetLastError());
 
   if (p->have_soft) {
@@ -741,7 +837,10 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
     P.rinv[1] = S + p->st_rinv_z;
     P.rinv[2] = S + p->st_rinv_t;
     P.part = X + p->sc_ps;
-    dsoft_fwd_kernel<MODE_SOFT><<<dim3(rbs, p->f_soft.nsplit), NUM_THREADS, FWD_SMEM_BYTES, st>>>(tm, P);
+    {
+      ProfScope ps(PK_FWD_SOFT, st);
+      dsoft_fwd_kernel<MODE_SOFT><<<dim3(rbs, p->f_soft.nsplit), NUM_THREADS, FWD_SMEM_BYTES, st>>>(tm, P);
+    }
     CUDA_TRY(cudaGetLastError());
   }
 
@@ -789,8 +888,8 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
   __half* v16 = reinterpret_cast<__half*>(X + p->sc_v16);
   make_v16_kernel<<<ceil_div(p->B, 8), 256, 0, st>>>(
       static_cast<const __nv_bfloat16*>(gathered), p->row_elems, p->B, p->sh.D, p->Dz, p->offI, p->offT,
-      p->offZ, p->have_soft, p->have_text, S + p->st_rinv_z, S + p->st_rinv_t, v16, p->v_row, p->v_offT,
-      p->v_offI, p->v_offZn, p->v_offTn);
+      p->offZ, p->have_soft, p->have_text, S + p->st_scal, v16, p->v_row, p->v_offT, p->v_offI, p->v_offZn,
+      p->v_offTn);
   CUDA_TRY(cudaGetLastError());
   CUtensorMap vmap;
   auto vmap_for = [&](int voff, int cols) {
@@ -826,8 +925,11 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
   P.lse_col = lsec + 1 * p->Bcol;
   P.acc_part = X + p->sc_acc1;
   P.ds_part = X + p->sc_ds1;
-  dsoft_bwd_kernel<MODE_CLIP>
-      <<<dim3(rbs, p->b_clip.nsplit, p->nch_clip), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, vmap, P);
+  {
+    ProfScope ps(PK_BWD_CLIP_I, st);
+    dsoft_bwd_kernel<MODE_CLIP>
+        <<<dim3(rbs, p->b_clip.nsplit, p->nch_clip), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, vmap, P);
+  }
   CUDA_TRY(cudaGetLastError());
   // ---- CLIP, text rows
   P.a_map[0] = 1;
@@ -837,8 +939,11 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
   P.lse_col = lsec + 0 * p->Bcol;
   P.acc_part = X + p->sc_acc2;
   P.ds_part = X + p->sc_ds2;
-  dsoft_bwd_kernel<MODE_CLIP>
-      <<<dim3(rbs, p->b_clip.nsplit, p->nch_clip), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, vmap, P);
+  {
+    ProfScope ps(PK_BWD_CLIP_T, st);
+    dsoft_bwd_kernel<MODE_CLIP>
+        <<<dim3(rbs, p->b_clip.nsplit, p->nch_clip), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, vmap, P);
+  }
   CUDA_TRY(cudaGetLastError());
 
   if (p->have_soft) {
@@ -851,6 +956,7 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
     P.dout = p->Dz;
     if ((rc = vmap_for(p->v_offZn, p->Dz))) return rc;
     P.tau_idx = SC_ITS_L2;
+    P.rmin_idx = SC_RMIN_Z;
     P.lse_t_row = lse_loc + 2 * b;
     P.lse_t_col = lsec + 2 * p->Bcol;
     P.lse_y_row = lse_loc + 3 * b;
@@ -858,8 +964,11 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
     P.rinv_d = S + p->st_rinv_d;
     P.rinv_y = S + p->st_rinv_z;
     P.acc_part = X + p->sc_acc3;
-    dsoft_bwd_kernel<MODE_SOFT>
-        <<<dim3(rbs, p->b_stu.nsplit, p->nch_stu), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, vmap, P);
+    {
+      ProfScope ps(PK_BWD_STU, st);
+      dsoft_bwd_kernel<MODE_SOFT>
+          <<<dim3(rbs, p->b_stu.nsplit, p->nch_stu), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, vmap, P);
+    }
     CUDA_TRY(cudaGetLastError());
     if (p->have_text) {
       base(p->b_txt, p->s_col0, p->s_ncols, p->ntiles_s);
@@ -871,6 +980,7 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
       P.dout = p->sh.D;
       if ((rc = vmap_for(p->v_offTn, p->sh.D))) return rc;
       P.tau_idx = SC_ITX_L2;
+      P.rmin_idx = SC_RMIN_T;
       P.lse_t_row = lse_loc + 2 * b;
       P.lse_t_col = lsec + 2 * p->Bcol;
       P.lse_y_row = lse_loc + 4 * b;
@@ -878,8 +988,11 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
       P.rinv_d = S + p->st_rinv_d;
       P.rinv_y = S + p->st_rinv_t;
       P.acc_part = X + p->sc_acc4;
-      dsoft_bwd_kernel<MODE_SOFT>
-          <<<dim3(rbs, p->b_txt.nsplit, p->nch_txt), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, vmap, P);
+      {
+        ProfScope ps(PK_BWD_TXT, st);
+        dsoft_bwd_kernel<MODE_SOFT>
+            <<<dim3(rbs, p->b_txt.nsplit, p->nch_txt), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, vmap, P);
+      }
       CUDA_TRY(cudaGetLastError());
     }
   }
@@ -913,6 +1026,7 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
   fa.rinv_z = S + p->st_rinv_z;
   fa.rinv_t = S + p->st_rinv_t;
   fa.gout = gout;
+  fa.lse_loc = lse_loc;
   fa.d_image = d_image;
   fa.d_text = d_text;
   fa.d_student = d_student;

@@ -48,8 +48,15 @@ enum {
   SC_ITT_L2 = 5,
   SC_ITX = 6,       // 1/tau_txt          (text_student_temp, loss.py:391-393)
   SC_ITX_L2 = 7,
-  SC_COUNT = 8
+  SC_RMIN_T = 8,    // min_j 1/||text_j||    (atomicMin by rinv_kernel; +inf until then)
+  SC_RMIN_Z = 9,    // min_j 1/||student_j||
+  SC_RMIN_D = 10,   // min_j 1/||dino_j||
+  SC_COUNT = 12
 };
+
+// Power-of-two scale sigma <= min_j rinv_j: operand rows times sigma have norm <= 1, and the scaling is
+// exact in fp16, so the fp16 gradient operand carries the bf16 features without any rounding.
+__device__ __forceinline__ float pow2_floor(float x) { return exp2f(floorf(log2f(x))); }
 
 struct TileMaps {
   CUtensorMap m[4];  // 0 = image, 1 = text, 2 = student, 3 = dino; box = 64 features x 128 rows, SW128
@@ -84,6 +91,7 @@ struct BwdParams {
   int want_ds;     // clip: also accumulate the d(logit_scale) row term
   const float* scal;
   int tau_idx;             // soft: SC_ITS_L2 or SC_ITX_L2
+  int rmin_idx;            // soft: SC_RMIN_Z or SC_RMIN_T (scale of the fp16 gradient operand)
   const float* lse_row;    // clip: this direction's row LSE (log2), local rows
   const float* lse_col;    // clip: other direction's LSE by global column (padded)
   const float* lse_t_row;  // soft: teacher LSE, local rows
@@ -409,12 +417,14 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
 // ================================================================================================
 // Backward: recompute tile -> G (bf16, smem) -> accumulate G . Y in TMEM
 // ================================================================================================
-//  MODE_CLIP: G_aj = 2^(x - lse_row_a) + 2^(x - lse_col_j)        (the -2*delta one-hot part and the
-//             s/(2b) factor are applied in fp32 by the finalize kernel)
-//  MODE_SOFT: G_aj = (2^(p-ls_a) + 2^(p-ls_j)) - (2^(q-lt_a) + 2^(q-lt_j)),  q diag masked
-//  G is stored as fp16 (|G| <= 2, 10-bit mantissa) and multiplied with an fp16 copy of the gradient
-//  operand (already L2-normalised for the soft terms): bf16 G costs 8x the rounding error and mixed
-//  fp16 x bf16 operands are not accepted by tcgen05.mma.
+//  MODE_CLIP: G_aj = 2^(x - lse_row_a) + 2^(x - lse_col_j), j != a   (the diagonal entry incl. its
+//             -2 one-hot part and the s/(2b) factor are applied in fp32 by the finalize kernel)
+//  MODE_SOFT: G_aj = (2^(p-ls_a) + 2^(p-ls_j)) - (2^(q-lt_a) + 2^(q-lt_j)), j != a  (diagonal dropped:
+//             it is parallel to y_a and vanishes in the normalise backward)
+//  G is stored as fp16 (10-bit mantissa) and multiplied with an EXACT fp16 copy of the gradient operand
+//  (bf16 features times a power of two sigma; the soft terms fold 1/(||y_j|| sigma) into G): bf16 G costs
+//  8x the rounding error, mixed fp16 x bf16 operands are not accepted by tcgen05.mma, and a rounded
+//  (normalised) operand would put the same error into every row's gradient.
 //  row_only drops the *_j (column-side) terms: gathered features are constants (gather_with_grad=0).
 template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -562,7 +572,7 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     float v[32];
     float dsacc = 0.f;
 
-    float c_a = 0.f, c_b = 0.f, l_a = 0.f, l_b = 0.f;
+    float c_a = 0.f, c_b = 0.f, l_a = 0.f, l_b = 0.f, inv_sigma = 1.f;
     if constexpr (MODE == MODE_RAW) {
       c_a = 1.f;
     } else if constexpr (MODE == MODE_CLIP) {
@@ -573,6 +583,7 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       l_a = P.lse_t_row[lic];
       c_b = P.rinv_y[gi] * P.scal[P.tau_idx];  // student / text
       l_b = P.lse_y_row[lic];
+      inv_sigma = 1.f / pow2_floor(P.scal[P.rmin_idx]);
     }
 
     int it = 0;
@@ -613,6 +624,12 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
               g[e] = e1 + e2;
             }
           }
+          if (gi >= gj0 && gi < gj0 + 32) {
+            // the diagonal entry (p_aa close to 1 once trained) is applied in fp32 by finalize_bwd_kernel
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (gj0 + e == gi) g[e] = 0.f;
+          }
         } else {
           // teacher part first (kept in g as a negative contribution)
           tmem_ld32(lane_addr + ((it + 0) % B_SLOTS) * BN + coff, v);
@@ -651,7 +668,10 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
                 const float p2 = v[e] * c_b * rr[k];
                 const float e1 = fast_exp2(p2 - l_b);
                 const float e2 = row_only ? 0.f : fast_exp2(p2 - ll[k]);
-                g[e] = g[e] + (e1 + e2);  // 1/||y_j|| lives in the fp16 gradient operand
+                // diagonal: its contribution is parallel to y_a and is annihilated exactly by the
+                // normalise backward (I - y y^T); dropping it removes pure rounding noise
+                // the fp16 operand row is y_j * sigma (exact), so G carries 1/(||y_j|| sigma) <= ~1
+                g[e] = (gj0 + e == gi) ? 0.f : (g[e] + (e1 + e2)) * fminf(rr[k] * inv_sigma, 1.0e4f);
               }
             }
           }

@@ -22,6 +22,16 @@ def synth(seed, B, D, Dd, clustered=True, device="cpu"):
     return r(img), r(txt), r(dino)
 
 
+def synth_aligned(seed, B, D, Dd, noise=0.3, device="cpu"):
+    """Near-converged regime: text_i ~ image_i, so p_ii -> 1 and the CE gradient is a small residual."""
+    g = torch.Generator().manual_seed(seed)
+    r = lambda x: x.to(torch.bfloat16).to(torch.float32).to(device)
+    img = torch.nn.functional.normalize(torch.randn(B, D, generator=g), dim=-1)
+    txt = torch.nn.functional.normalize(img + noise * torch.randn(B, D, generator=g) / D ** 0.5 * 4, dim=-1)
+    dino = 3.0 * torch.randn(B, Dd, generator=g)
+    return r(img), r(txt), r(dino)
+
+
 def make_args(**kw):
     base = dict(use_projection=False, projection_type="mlp", lambda_soft=0.5, soft_mode="kl_teacher",
                 soft_dino_to_text=True, text_lambda=0.5, text_student_temp=0.02, teacher_temp=0.15,

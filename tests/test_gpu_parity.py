@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from gpu_util import head_params_of, make_args, oracle_cfg, rel_err, synth
+from gpu_util import head_params_of, make_args, oracle_cfg, rel_err, synth, synth_aligned
 
 pytestmark = pytest.mark.gpu
 
@@ -31,8 +31,8 @@ def run_cuda(pkg, img, txt, dino, scale, args, head_seed=7, **ctor):
     return loss, out, im.grad, tx.grad, sc.grad
 
 
-def check_against_oracle(pkg, oracle, B, D, Dd, scale, args, seed=0, clustered=True):
-    img, txt, dino = synth(seed, B, D, Dd, clustered)
+def check_against_oracle(pkg, oracle, B, D, Dd, scale, args, seed=0, clustered=True, inputs=None):
+    img, txt, dino = synth(seed, B, D, Dd, clustered) if inputs is None else inputs
     loss, out, gi, gt, gs = run_cuda(pkg, img, txt, dino, scale, args)
     head = None
     if args.use_projection and loss.image_to_dino_proj is not None:
@@ -45,7 +45,8 @@ def check_against_oracle(pkg, oracle, B, D, Dd, scale, args, seed=0, clustered=T
     for k in ("total_loss", "classic_loss", "soft_loss"):
         got = float(out[k].detach())
         print(f"[parity] B={B} D={D} Dd={Dd} s={scale} {k}: got={got:.7f} ref={ref[k]:.7f} rel={abs(got - ref[k]) / max(abs(ref[k]), 1e-30):.2e}")
-        assert got == pytest.approx(ref[k], rel=LOSS_RTOL, abs=1e-6), (k, got, ref[k])
+        # abs floor: logits of magnitude ~scale carry an fp32 ulp of up to 8e-6 into (lse - L_ii)
+        assert got == pytest.approx(ref[k], rel=LOSS_RTOL, abs=1e-5), (k, got, ref[k])
     for name, got, want in (("d_image", gi, ref["d_image"]), ("d_text", gt, ref["d_text"])):
         linf, l2 = rel_err(got, want)
         print(f"[parity] B={B} D={D} Dd={Dd} s={scale} {name}: linf={linf:.2e} l2={l2:.2e}")
@@ -94,6 +95,14 @@ def test_ragged_sizes(pkg, oracle, B, D, Dd):
 def test_column_split_many_tiles(pkg, oracle):
     """B large enough that every kernel splits the column range over several CTAs."""
     check_against_oracle(pkg, oracle, 2048, 128, 192, 50.0, make_args(use_projection=True), seed=9)
+
+
+@pytest.mark.parametrize("scale,noise", [(14.2857, 0.3), (100.0, 0.3), (100.0, 1.0)])
+def test_near_converged_pairs(pkg, oracle, scale, noise):
+    """p_ii ~ 1: the CE gradient is the small residual (p_ii - 1) t_i + ...; the diagonal is handled in fp32."""
+    inputs = synth_aligned(11, 256, 128, 192, noise)
+    check_against_oracle(pkg, oracle, 256, 128, 192, scale, make_args(), inputs=inputs)
+    check_against_oracle(pkg, oracle, 256, 128, 192, scale, make_args(use_projection=True), inputs=inputs)
 
 
 def test_output_dict_false_returns_none(pkg):
