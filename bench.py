@@ -226,7 +226,10 @@ def run_ours(args):
             p.grad = None
 
     def step(im, tx, dn):
-        out = loss(im, tx, scale, dn, larg, output_dict=True)
+        # the reference calls the loss inside torch.autocast (open_clip_train/train.py:285): the projection
+        # head runs in bf16 on cuBLAS; the fused loss kernels are unaffected (bf16 operands, fp32 math)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = loss(im, tx, scale, dn, larg, output_dict=True)
         out["total_loss"].backward()
         return out
 

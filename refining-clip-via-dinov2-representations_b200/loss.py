@@ -216,7 +216,7 @@ class _DinoSoftFn(torch.autograd.Function):
                 None if dino is None or not soft else dino.detach(), gathered)
         if W > 1:
             # the only feature exchange of the path: one all-gather of the packed bf16 rows (loss.py:23-81)
-            dist.all_gather_into_tensor(gathered, gathered[r * b:(r + 1) * b], group=cfg.group)
+            dist.all_gather_into_tensor(gathered.view(-1), gathered[r * b:(r + 1) * b].view(-1), group=cfg.group)
         state = torch.empty(plan.state_numel, dtype=torch.float32, device=dev)
         scratch = torch.empty(plan.scratch_numel, dtype=torch.float32, device=dev)
         lse_all = torch.empty((W, 5, b), dtype=torch.float32, device=dev)
@@ -226,7 +226,7 @@ class _DinoSoftFn(torch.autograd.Function):
         needs_grad = any(ctx.needs_input_grad[:4])
         if W > 1 and needs_grad:
             # column-side soft-max statistics of the other ranks' rows (5 floats per sample)
-            dist.all_gather_into_tensor(lse_all, lse_all[r], group=cfg.group)
+            dist.all_gather_into_tensor(lse_all.view(-1), lse_all[r].view(-1), group=cfg.group)
         ctx.save_for_backward(gathered, state, lse_all)
         ctx.plan, ctx.cfg = plan, cfg
         ctx.meta = (image.dtype, text.dtype, logit_scale.dtype, logit_scale.shape,

@@ -1,0 +1,104 @@
+"""TEST DOUBLE (lives under tests/ on purpose): a stand-in for the CUDA backend built on the CPU oracle.
+
+It lets the host-side logic of the loss module (packing layout, the all-gather plumbing, rank / label
+handling, flag decoding, autograd wiring, loss composition) run under `gloo` on a CPU-only box.  The
+product never selects it: `ClipLossWithDINOEnhancements` resolves its backend to the C-ABI CUDA backend
+and raises on non-CUDA tensors; tests inject this object through the private `_backend` attribute."""
+import torch
+
+F_SOFT, F_TEXT, F_SOFT_LOCAL, F_ROW_ONLY = 1, 2, 4, 8
+
+
+class _Plan:
+    pass
+
+
+class OracleBackend:
+    name = "oracle-test-double"
+
+    def __init__(self, oracle):
+        self.oracle = oracle
+        self.calls = []
+
+    def plan(self, shape):
+        p = _Plan()
+        p.shape = shape
+        p.soft = bool(shape.flags & F_SOFT)
+        p.proj = p.soft and shape.Dp > 0
+        p.offI, p.offT = 0, shape.D
+        p.offZ = 2 * shape.D if p.proj else 0
+        p.offD = 2 * shape.D + (shape.Dp if p.proj else 0)
+        p.row_elems = p.offD + (shape.Dd if p.soft else 0)
+        p.state_numel = 8
+        p.scratch_numel = 8
+        p.flops, p.launches_fwd, p.launches_bwd = 0.0, 0, 0
+        return p
+
+    def pack(self, plan, image, text, student, dino, gathered):
+        s = plan.shape
+        rows = slice(s.rank * s.b, (s.rank + 1) * s.b)
+        gathered[rows, plan.offI:plan.offI + s.D] = image.to(torch.bfloat16)
+        gathered[rows, plan.offT:plan.offT + s.D] = text.to(torch.bfloat16)
+        if plan.proj:
+            gathered[rows, plan.offZ:plan.offZ + s.Dp] = student.to(torch.bfloat16)
+        if plan.soft:
+            gathered[rows, plan.offD:plan.offD + s.Dd] = dino.to(torch.bfloat16)
+        self.calls.append("pack")
+
+    def _decode(self, plan, gathered):
+        s = plan.shape
+        g = gathered.to(torch.float64)
+        img = g[:, plan.offI:plan.offI + s.D]
+        txt = g[:, plan.offT:plan.offT + s.D]
+        stu = g[:, plan.offZ:plan.offZ + s.Dp] if plan.proj else None
+        dino = g[:, plan.offD:plan.offD + s.Dd] if plan.soft else None
+        return img, txt, stu, dino
+
+    def _cfg(self, plan):
+        s = plan.shape
+        return self.oracle.OracleConfig(
+            lambda_original=1.0, lambda_soft=1.0 if plan.soft else 0.0,
+            soft_mode="kl_teacher" if plan.soft else "none", teacher_temp=s.teacher_temp,
+            soft_dino_to_text=bool(s.flags & F_TEXT), text_lambda=1.0, text_student_temp=s.text_temp or 0.05,
+            world_size=s.world, local_loss=True, gather_with_grad=not (s.flags & F_ROW_ONLY),
+            soft_scope="local" if (s.flags & F_SOFT_LOCAL) else "global")
+
+    def forward(self, plan, gathered, logit_scale, state, scratch, lse_local, losses):
+        img, txt, stu, dino = self._decode(plan, gathered)
+        out = self.oracle.rank_loss(img, txt, logit_scale.double()[0], dino, stu, self._cfg(plan), rank=plan.shape.rank)
+        losses[0], losses[1], losses[2] = float(out["classic_loss"]), float(out["soft_img"]), float(out["soft_txt"])
+        lse_local.zero_()
+        state[0] = float(logit_scale[0])
+        self.calls.append("forward")
+
+    @torch.enable_grad()  # called from inside autograd.Function.backward, where grad mode is off
+    def backward(self, plan, gathered, state, scratch, lse_all, gout, d_image, d_text, d_student, d_scale):
+        s = plan.shape
+        cfg = self._cfg(plan)
+        img, txt, stu, dino = (None if t is None else t.clone() for t in self._decode(plan, gathered))
+        img.requires_grad_(True)
+        txt.requires_grad_(True)
+        if stu is not None:
+            stu.requires_grad_(True)
+        sc = torch.tensor(float(state[0]), dtype=torch.float64, requires_grad=True)
+        g = gout.double()
+
+        def weighted(rank):
+            o = self.oracle.rank_loss(img, txt, sc, dino, stu, cfg, rank=rank)
+            return g[0] * o["classic_loss"] + g[1] * o["soft_img"] + g[2] * o["soft_txt"]
+
+        own = weighted(s.rank)
+        gs, = torch.autograd.grad(own, sc, retain_graph=True)
+        total = own
+        if cfg.gather_with_grad and s.world > 1:
+            for k in range(s.world):
+                if k != s.rank:
+                    total = total + weighted(k)
+        total.backward()
+        rows = slice(s.rank * s.b, (s.rank + 1) * s.b)
+        d_image.copy_(img.grad[rows])
+        d_text.copy_(txt.grad[rows])
+        if d_student is not None:
+            d_student.copy_(stu.grad[rows])
+        d_scale[0] = float(gs)
+        self.calls.append("backward")

@@ -1,0 +1,86 @@
+"""CUDA path at world_size 2 (NCCL, one process per GPU) against the oracle.  Skipped with < 2 GPUs."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+from gpu_util import make_args, oracle_cfg, rel_err, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, B, D, Dd, scale, argd, ctor, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import dinosoft_b200 as pkg
+
+    args = make_args(**argd)
+    img, txt, dino = synth(21, B, D, Dd)
+    b = B // world
+    rows = slice(rank * b, (rank + 1) * b)
+    dev = torch.device("cuda", rank)
+    m = pkg.ClipLossWithDINOEnhancements(rank=rank, world_size=world, **ctor)
+    if args.use_projection:
+        torch.manual_seed(5)
+        m.init_proj(D, Dd, dev, args.projection_type)
+    im = img[rows].to(dev).requires_grad_(True)
+    tx = txt[rows].to(dev).requires_grad_(True)
+    sc = torch.tensor(scale, device=dev, requires_grad=True)
+    out = m(im, tx, sc, dino[rows].to(dev), args, output_dict=True)
+    out["total_loss"].backward()
+    torch.cuda.synchronize()
+    head = None
+    if args.use_projection:
+        from gpu_util import head_params_of
+
+        head = {k: v.detach().cpu() for k, v in head_params_of(m.image_to_dino_proj, args.projection_type).items()}
+    ret[rank] = dict(total=float(out["total_loss"].detach()), classic=float(out["classic_loss"].detach()),
+                     soft=float(out["soft_loss"].detach()), d_image=im.grad.cpu(), d_text=tx.grad.cpu(),
+                     d_scale=float(sc.grad), head=head)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ctor,argd", [
+    (dict(local_loss=True, gather_with_grad=True, soft_scope="global"), dict(use_projection=True)),
+    (dict(local_loss=True, gather_with_grad=True, soft_scope="local"), dict(use_projection=False)),
+    (dict(local_loss=True, gather_with_grad=False, soft_scope="global"), dict(use_projection=False)),
+])
+def test_two_gpu_parity(oracle, ctor, argd):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    B, D, Dd, scale, world = 512, 128, 192, 30.0, 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), B, D, Dd, scale, argd, ctor, ret), nprocs=world, join=True)
+    args = make_args(**argd)
+    img, txt, dino = synth(21, B, D, Dd)
+    cfg = oracle_cfg(oracle, args, world_size=world, local_loss=True, gather_with_grad=ctor["gather_with_grad"],
+                     soft_scope=ctor["soft_scope"], round_student_bf16=True)
+    ref = oracle.loss_and_grads(img, txt, scale, dino, cfg, proj_params=ret[0]["head"],
+                                projection_type=args.projection_type)["ranks"]
+    for r in range(world):
+        o, want = ret[r], ref[r]
+        assert o["total"] == pytest.approx(want["total_loss"], rel=1e-4)
+        assert o["classic"] == pytest.approx(want["classic_loss"], rel=1e-4)
+        assert o["soft"] == pytest.approx(want["soft_loss"], rel=1e-4)
+        for k in ("d_image", "d_text"):
+            linf, l2 = rel_err(o[k], want[k])
+            print(f"[parity-w2] rank {r} {k}: linf={linf:.2e} l2={l2:.2e}")
+            assert linf < 1e-3 and l2 < 1e-3, (r, k, linf, l2)
+        assert o["d_scale"] == pytest.approx(want["d_logit_scale"], rel=1e-3, abs=1e-7)
