@@ -68,6 +68,9 @@ struct dsoft_plan {
 };
 
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
+// feature chunks are processed by clusters of at most X_MAXC CTAs; nch chunks -> `groups` launches
+static int chunk_groups(int nch) { return ceil_div(nch, X_MAXC); }
+static int chunk_cluster(int nch) { return ceil_div(nch, chunk_groups(nch)); }
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Choose the column split so that (row blocks x splits x chunks) CTAs fill the SMs in whole waves.
@@ -184,8 +187,8 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   p->sc_acc2 = take(static_cast<size_t>(p->b_clip.nsplit) * b * sh->D);
   p->sc_acc3 = take(soft ? static_cast<size_t>(p->b_stu.nsplit) * b * p->Dz : 0);
   p->sc_acc4 = take(p->have_text ? static_cast<size_t>(p->b_txt.nsplit) * b * sh->D : 0);
-  p->sc_ds1 = take(2 * p->b_clip.nsplit * b);
-  p->sc_ds2 = take(2 * p->b_clip.nsplit * b);
+  p->sc_ds1 = take(2 * X_MAXC * p->b_clip.nsplit * b);
+  p->sc_ds2 = take(2 * X_MAXC * p->b_clip.nsplit * b);
   p->sc_dsrow = take(b);
   p->v_offT = 0;
   p->v_offI = sh->D;
@@ -227,15 +230,15 @@ extern "C" int dsoft_plan_kernel_flops(const dsoft_plan_t* p, double* algorithmi
   algorithmic[0] = algorithmic[1] = b * Bc * D;
   executed[0] = executed[1] = 2.0 * b * Bc * D;
   algorithmic[3] = algorithmic[4] = 2.0 * b * Bc * D;
-  executed[3] = executed[4] = 2.0 * b * Bc * D * (p->nch_clip + 1.0);
+  executed[3] = executed[4] = 2.0 * b * Bc * D * (chunk_groups(p->nch_clip) + 1.0);
   if (p->have_soft) {
     algorithmic[2] = executed[2] = 2.0 * b * Bs * (Dz + Dd + (p->have_text ? D : 0.0));
     algorithmic[5] = 2.0 * b * Bs * Dz;
-    executed[5] = 2.0 * b * Bs * (p->nch_stu * (Dz + Dd) + Dz);
+    executed[5] = 2.0 * b * Bs * (chunk_groups(p->nch_stu) * (Dz + Dd) + Dz);
   }
   if (p->have_text) {
     algorithmic[6] = 2.0 * b * Bs * D;
-    executed[6] = 2.0 * b * Bs * (p->nch_txt * (D + Dd) + D);
+    executed[6] = 2.0 * b * Bs * (chunk_groups(p->nch_txt) * (D + Dd) + D);
   }
   return 0;
 }
@@ -273,12 +276,12 @@ static EncodeTiledFn get_encode_fn() {
 
 // bf16 matrix [rows][cols] with row pitch `pitch_elems`; box = 64 columns x 128 rows, 128B swizzle.
 static int make_map(CUtensorMap* map, const void* base, int rows, int cols, size_t pitch_elems,
-                    CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
+                    CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, int box_rows = BM) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(DSOFT_ENODEV, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(pitch_elems) * 2};
-  cuuint32_t box[2] = {BK, BM};
+  cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box,
                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -508,6 +511,7 @@ struct FinBwdArgs {
   int b, D, Dz, row0, row_elems, offI, offT, offZ;
   int have_soft, have_text, have_proj, row_only;
   int ns_c, ns_s, ns_x;
+  int nds;  // d(logit_scale) partials per row: nsplit x cluster size x 2 halves
   const __nv_bfloat16* gathered;
   const float* acc1;  // [ns_c][b][D]   sum_j G_clip . T_j   (image rows)
   const float* acc2;  // [ns_c][b][D]   sum_j G_clip' . I_j  (text rows)
@@ -568,7 +572,7 @@ __global__ void __launch_bounds__(128) finalize_bwd_kernel(FinBwdArgs a) {
   }
   if (threadIdx.x == 0) {
     float d = 0.f;
-    for (int s = 0; s < 2 * a.ns_c; ++s) d += a.ds1[s * a.b + i] + a.ds2[s * a.b + i];
+    for (int s = 0; s < a.nds; ++s) d += a.ds1[s * a.b + i] + a.ds2[s * a.b + i];
     a.dsrow[i] = d - 2.f * a.diag[i];
   }
   __syncthreads();
@@ -694,6 +698,32 @@ extern "C" int dsoft_profile_read(double* ms_sum, int* counts, int n) {
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
+// Backward tile kernel: the feature chunks of one (row block, column split) form a cluster along grid.x.
+// More than X_MAXC chunks are split into several launches (each recomputes the S tiles once).
+template <typename K>
+static int launch_bwd(K kernel, int nch, int rbs, int nsplit, cudaStream_t st, const TileMaps& tm,
+                      const CUtensorMap& vmap, BwdParams P) {
+  const int csz = chunk_cluster(nch);
+  for (int c0 = 0; c0 < nch; c0 += csz) {
+    const int cg = std::min(csz, nch - c0);
+    P.chunk0 = c0;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(cg, rbs, nsplit);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = BWD_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cg;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, tm, vmap, P));
+  }
+  return 0;
+}
+
 template <typename K>
 static int set_smem(K kernel, int bytes) {
   CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -893,7 +923,7 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
   CUDA_TRY(cudaGetLastError());
   CUtensorMap vmap;
   auto vmap_for = [&](int voff, int cols) {
-    return make_map(&vmap, v16 + voff, p->B, cols, p->v_row, CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+    return make_map(&vmap, v16 + voff, p->B, cols, p->v_row, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 64);
   };
 
   if ((rc = set_smem(dsoft_bwd_kernel<MODE_CLIP>, BWD_SMEM_BYTES))) return rc;
@@ -927,8 +957,7 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
   P.ds_part = X + p->sc_ds1;
   {
     ProfScope ps(PK_BWD_CLIP_I, st);
-    dsoft_bwd_kernel<MODE_CLIP>
-        <<<dim3(rbs, p->b_clip.nsplit, p->nch_clip), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, vmap, P);
+    if ((rc = launch_bwd(dsoft_bwd_kernel<MODE_CLIP>, p->nch_clip, rbs, p->b_clip.nsplit, st, tm, vmap, P))) return rc;
   }
   CUDA_TRY(cudaGetLastError());
   // ---- CLIP, text rows
@@ -941,8 +970,7 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
   P.ds_part = X + p->sc_ds2;
   {
     ProfScope ps(PK_BWD_CLIP_T, st);
-    dsoft_bwd_kernel<MODE_CLIP>
-        <<<dim3(rbs, p->b_clip.nsplit, p->nch_clip), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, vmap, P);
+    if ((rc = launch_bwd(dsoft_bwd_kernel<MODE_CLIP>, p->nch_clip, rbs, p->b_clip.nsplit, st, tm, vmap, P))) return rc;
   }
   CUDA_TRY(cudaGetLastError());
 
@@ -966,8 +994,7 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
     P.acc_part = X + p->sc_acc3;
     {
       ProfScope ps(PK_BWD_STU, st);
-      dsoft_bwd_kernel<MODE_SOFT>
-          <<<dim3(rbs, p->b_stu.nsplit, p->nch_stu), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, vmap, P);
+      if ((rc = launch_bwd(dsoft_bwd_kernel<MODE_SOFT>, p->nch_stu, rbs, p->b_stu.nsplit, st, tm, vmap, P))) return rc;
     }
     CUDA_TRY(cudaGetLastError());
     if (p->have_text) {
@@ -990,8 +1017,8 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
       P.acc_part = X + p->sc_acc4;
       {
         ProfScope ps(PK_BWD_TXT, st);
-        dsoft_bwd_kernel<MODE_SOFT>
-            <<<dim3(rbs, p->b_txt.nsplit, p->nch_txt), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, vmap, P);
+        if ((rc = launch_bwd(dsoft_bwd_kernel<MODE_SOFT>, p->nch_txt, rbs, p->b_txt.nsplit, st, tm, vmap, P)))
+          return rc;
       }
       CUDA_TRY(cudaGetLastError());
     }
@@ -1012,6 +1039,7 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
   fa.have_proj = p->have_proj;
   fa.row_only = p->row_only;
   fa.ns_c = p->b_clip.nsplit;
+  fa.nds = 2 * p->b_clip.nsplit * chunk_cluster(p->nch_clip);
   fa.ns_s = p->b_stu.nsplit;
   fa.ns_x = p->b_txt.nsplit;
   fa.gathered = static_cast<const __nv_bfloat16*>(gathered);
@@ -1092,7 +1120,7 @@ extern "C" int dsoft_selftest_chain(const void* a, const void* bmat, const void*
   tm.m[2] = tm.m[0];
   tm.m[3] = tm.m[0];
   CUtensorMap vmap;
-  if ((rc = make_map(&vmap, vmat, N, F, F, CU_TENSOR_MAP_DATA_TYPE_FLOAT16))) return rc;
+  if ((rc = make_map(&vmap, vmat, N, F, F, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 64))) return rc;
   if ((rc = set_smem(dsoft_bwd_kernel<MODE_RAW>, BWD_SMEM_BYTES))) return rc;
   BwdParams P;
   memset(&P, 0, sizeof(P));
@@ -1109,8 +1137,7 @@ extern "C" int dsoft_selftest_chain(const void* a, const void* bmat, const void*
   P.tiles_per_split = P.ntiles;  // single split: `out` is the only partial
   P.nsplit = 1;
   P.acc_part = out;
-  dsoft_bwd_kernel<MODE_RAW>
-      <<<dim3(ceil_div(M, BM), 1, ceil_div(F, CHUNK_F)), NUM_THREADS, BWD_SMEM_BYTES, st>>>(tm, vmap, P);
-  CUDA_TRY(cudaGetLastError());
+  if ((rc = launch_bwd(dsoft_bwd_kernel<MODE_RAW>, ceil_div(F, CHUNK_F), ceil_div(M, BM), 1, st, tm, vmap, P)))
+    return rc;
   return 0;
 }

@@ -87,6 +87,7 @@ struct BwdParams {
   int kchunks[2];
   int dout;        // feature width of the gradient
   int row0, b, col0, ncols, ntiles, tiles_per_split, nsplit;
+  int chunk0;      // first feature chunk of this launch (cluster rank c handles chunk0 + c)
   int row_only;    // gather_with_grad == False: gathered columns are constants
   int want_ds;     // clip: also accumulate the d(logit_scale) row term
   const float* scal;
@@ -101,7 +102,7 @@ struct BwdParams {
   const float* rinv_d;     // by global index
   const float* rinv_y;
   float* acc_part;         // [nsplit][b][dout] fp32
-  float* ds_part;          // [nsplit*2][b]
+  float* ds_part;          // [nsplit * C * 2][b]
 };
 
 __device__ __forceinline__ uint8_t* align_1024(uint8_t* p) {
@@ -415,51 +416,72 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
 }
 
 // ================================================================================================
-// Backward: recompute tile -> G (bf16, smem) -> accumulate G . Y in TMEM
+// Backward: recompute tile -> G (fp16, smem) -> accumulate G . Y in TMEM
 // ================================================================================================
 //  MODE_CLIP: G_aj = 2^(x - lse_row_a) + 2^(x - lse_col_j), j != a   (the diagonal entry incl. its
 //             -2 one-hot part and the s/(2b) factor are applied in fp32 by the finalize kernel)
-//  MODE_SOFT: G_aj = (2^(p-ls_a) + 2^(p-ls_j)) - (2^(q-lt_a) + 2^(q-lt_j)), j != a  (diagonal dropped:
-//             it is parallel to y_a and vanishes in the normalise backward)
-//  G is stored as fp16 (10-bit mantissa) and multiplied with an EXACT fp16 copy of the gradient operand
-//  (bf16 features times a power of two sigma; the soft terms fold 1/(||y_j|| sigma) into G): bf16 G costs
-//  8x the rounding error, mixed fp16 x bf16 operands are not accepted by tcgen05.mma, and a rounded
-//  (normalised) operand would put the same error into every row's gradient.
+//  MODE_SOFT: G_aj = [(2^(p-ls_a) + 2^(p-ls_j)) - (2^(q-lt_a) + 2^(q-lt_j))] / (||y_j|| sigma), j != a
+//             (diagonal dropped: it is parallel to y_a and vanishes in the normalise backward)
 //  row_only drops the *_j (column-side) terms: gathered features are constants (gather_with_grad=0).
+//  G is stored as fp16 (10-bit mantissa) and multiplied with an EXACT fp16 copy of the gradient operand
+//  (bf16 features times a power of two sigma): bf16 G costs 8x the rounding error, mixed fp16 x bf16
+//  operands are not accepted by tcgen05.mma, and a rounded (normalised) operand would put the same
+//  error into every row's gradient.
+//
+//  The gradient of a 128-row block is [128 x Dout] fp32; only 256 of its columns fit in TMEM next to the
+//  S tiles.  The Dout/256 feature chunks of one (row block, column split) are therefore the CTAs of one
+//  thread-block CLUSTER (C <= 3): CTA c owns accumulator columns [256c, 256c+256), computes the S tile
+//  and G only for the column tiles t = t0 + r*C + c ("its" tile of round r), and ships that fp16 G tile
+//  to the other CTAs with a DSMEM bulk copy (cp.async.bulk.shared::cluster).  Every CTA then multiplies
+//  all C tiles of the round with its own feature chunk of Y.  No S tile is ever recomputed per chunk.
+//
+//  shared memory (7 slabs of 32 KiB): G[C] | V ring (2 half tiles: 64 j x 256 features) | S-operand ring
+//  warps: 0 = S-operand TMA, 1 = MMA issuer, 2 = TMEM alloc + V TMA, 3 = G sender, 4..11 = epilogue
+constexpr int X_MAXC = 3;
+constexpr int SLAB = 2 * TILE_BYTES;   // 32 KiB
+constexpr int X_SLABS = 7;
+constexpr int X_NV = 2;
+
 template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ CUtensorMap vmap,
                  const __grid_constant__ BwdParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_1024(smem_raw);
-  uint8_t* v_smem = smem + B_STAGES * 2 * TILE_BYTES;  // 4 boxes: 128 columns(j) x 256 features
-  uint8_t* g_smem = v_smem + 4 * TILE_BYTES;           // 2 boxes: 128 rows x 128 columns(j), bf16
-  uint64_t* bars = reinterpret_cast<uint64_t*>(g_smem + 2 * TILE_BYTES);
-  uint64_t* ring_full = bars;
-  uint64_t* ring_empty = bars + B_STAGES;
-  uint64_t* s_full = bars + 2 * B_STAGES;
-  uint64_t* s_empty = s_full + B_SLOTS;
-  uint64_t* v_full = s_empty + B_SLOTS;
-  uint64_t* v_empty = v_full + 1;
-  uint64_t* g_full = v_empty + 1;
-  uint64_t* g_empty = g_full + 1;
-  uint64_t* acc_full = g_empty + 1;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int csize = gridDim.x;           // cluster size == feature chunks handled by this launch
+  const int crank = blockIdx.x;          // == %cluster_ctarank
+  const int ns = X_SLABS - X_NV - csize; // S-operand ring stages (4 / 3 / 2)
+  uint8_t* g_smem = smem;                          // csize slabs: G tile of producer k at slab k
+  uint8_t* v_smem = smem + csize * SLAB;           // X_NV slabs
+  uint8_t* s_smem = v_smem + X_NV * SLAB;          // ns slabs: A box | B box
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + X_SLABS * SLAB);
+  uint64_t* ring_full = bars;           // [4]
+  uint64_t* ring_empty = bars + 4;      // [4]
+  uint64_t* s_full = bars + 8;          // [2]
+  uint64_t* s_empty = bars + 10;        // [2]
+  uint64_t* v_full = bars + 12;         // [2]
+  uint64_t* v_empty = bars + 14;        // [2]
+  uint64_t* g_written = bars + 16;      // own G tile stored (256 epilogue arrivals)
+  uint64_t* g_in = bars + 17;           // [3] G tile of producer k landed (tx bytes)
+  uint64_t* g_free = bars + 20;         // own G tile consumed by all C CTAs (multicast commits)
+  uint64_t* acc_full = bars + 21;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int rb = blockIdx.x;
-  const int split = blockIdx.y;
-  const int chunk = blockIdx.z;
+  const int rb = blockIdx.y;
+  const int split = blockIdx.z;
+  const int chunk = P.chunk0 + crank;
   const int t0 = split * P.tiles_per_split;
   const int t1 = min(t0 + P.tiles_per_split, P.ntiles);
-  const int f0 = chunk * CHUNK_F;                            // first gradient feature of this pass
-  const int nfb = min(4, (P.dout - f0 + BK - 1) / BK);       // 64-feature boxes in this pass
+  const int nrounds = (t1 - t0 + csize - 1) / csize;
+  const int f0 = chunk * CHUNK_F;                            // first gradient feature of this CTA
+  const int nfb = min(4, (P.dout - f0 + BK - 1) / BK);       // 64-feature boxes of this CTA
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) tma_prefetch_desc(&maps.m[i]);
     tma_prefetch_desc(&vmap);
-    for (int i = 0; i < B_STAGES; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(smem_u32(&ring_full[i]), 1);
       mbar_init(smem_u32(&ring_empty[i]), 1);
     }
@@ -467,46 +489,78 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       mbar_init(smem_u32(&s_full[i]), 1);
       mbar_init(smem_u32(&s_empty[i]), NUM_EPI_THREADS);
     }
-    mbar_init(smem_u32(v_full), 1);
-    mbar_init(smem_u32(v_empty), 1);
-    mbar_init(smem_u32(g_full), NUM_EPI_THREADS);
-    mbar_init(smem_u32(g_empty), 1);
+    for (int i = 0; i < X_NV; ++i) {
+      mbar_init(smem_u32(&v_full[i]), 1);
+      mbar_init(smem_u32(&v_empty[i]), 1);
+    }
+    mbar_init(smem_u32(g_written), NUM_EPI_THREADS);
+    for (int i = 0; i < X_MAXC; ++i) mbar_init(smem_u32(&g_in[i]), 1);
+    mbar_init(smem_u32(g_free), csize);
     mbar_init(smem_u32(acc_full), 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(tmem_holder), TMEM_COLS);
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // peers' mbarriers must exist before any DSMEM copy / multicast commit reaches them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ S-operand TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      int n = 0;
-      for (int t = t0; t < t1; ++t, ++n) {
+      for (int r = 0; r < nrounds; ++r) {
+        const int t = t0 + r * csize + crank;
+        if (t >= t1) break;
         for (int p = 0; p < P.nprod; ++p) {
           const CUtensorMap* am = &maps.m[P.a_map[p]];
           const CUtensorMap* bm = &maps.m[P.b_map[p]];
           for (int kc = 0; kc < P.kchunks[p]; ++kc) {
             mbar_wait(smem_u32(&ring_empty[stage]), phase ^ 1);
             const uint32_t full = smem_u32(&ring_full[stage]);
-            const uint32_t a_dst = smem_u32(smem + stage * 2 * TILE_BYTES);
+            const uint32_t a_dst = smem_u32(s_smem + stage * SLAB);
             mbar_arrive_expect_tx(full, 2 * TILE_BYTES);
             tma_load_2d(a_dst, am, full, kc * BK, P.row0 + rb * BM);
             tma_load_2d(a_dst + TILE_BYTES, bm, full, kc * BK, P.col0 + t * BN);
-            if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == ns) { stage = 0; phase ^= 1; }
           }
         }
-        // gradient operand Y16[j-tile, f0 : f0 + 64*nfb]  (fp16 copy, same box shape, used MN-major)
-        mbar_wait(smem_u32(v_empty), (static_cast<uint32_t>(n) & 1) ^ 1);
-        const uint32_t vf = smem_u32(v_full);
-        mbar_arrive_expect_tx(vf, nfb * TILE_BYTES);
-        for (int fb = 0; fb < nfb; ++fb)
-          tma_load_2d(smem_u32(v_smem + fb * TILE_BYTES), &vmap, vf, f0 + fb * BK,
-                      P.col0 + t * BN);
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ gradient-operand (Y16) TMA producer
+    // same order as the MMA issuer consumes: round, producer k, half (64 columns j each)
+    if (lane == 0) {
+      int vs = 0;
+      uint32_t vphase = 0;
+      for (int r = 0; r < nrounds; ++r) {
+        for (int k = 0; k < csize; ++k) {
+          const int t = t0 + r * csize + k;
+          if (t >= t1) break;
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(smem_u32(&v_empty[vs]), vphase ^ 1);
+            const uint32_t vf = smem_u32(&v_full[vs]);
+            mbar_arrive_expect_tx(vf, nfb * (TILE_BYTES / 2));
+            for (int fb = 0; fb < nfb; ++fb)
+              tma_load_2d(smem_u32(v_smem + vs * SLAB + fb * (TILE_BYTES / 2)), &vmap, vf, f0 + fb * BK,
+                          P.col0 + t * BN + h * 64);
+            if (++vs == X_NV) { vs = 0; vphase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ G sender (DSMEM bulk copies)
+    if (lane == 0 && csize > 1) {
+      const uint32_t src = smem_u32(g_smem + crank * SLAB);
+      for (int r = 0; r < nrounds; ++r) {
+        if (t0 + r * csize + crank >= t1) break;
+        mbar_wait(smem_u32(g_written), static_cast<uint32_t>(r) & 1);
+        for (int k = 0; k < csize; ++k) {
+          if (k == crank) continue;
+          bulk_copy_to_peer(mapa_shared(src, k), src, SLAB, mapa_shared(smem_u32(&g_in[crank]), k));
+        }
       }
     }
   } else if (warp == 1) {
@@ -515,46 +569,69 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      int n = 0;
+      int vs = 0;
+      uint32_t vphase = 0;
+      bool first_grad = true;
       const uint32_t idesc_g = make_idesc_bf16(BM, nfb * BK, 0, 1, 1);  // fp16: A = G (K-major), B = Y16 (MN-major)
       const uint32_t tmem_acc = tmem_base + ACC_COL;
-      auto issue_grad = [&](int mt) {
-        mbar_wait(smem_u32(g_full), static_cast<uint32_t>(mt) & 1);
-        mbar_wait(smem_u32(v_full), static_cast<uint32_t>(mt) & 1);
-        tc_fence_after();
-        const uint32_t g_addr = smem_u32(g_smem);
-        const uint32_t v_addr = smem_u32(v_smem);
-#pragma unroll
-        for (int kk = 0; kk < BN / 16; ++kk) {
-          // A: G[128 rows, 16 j]  -> box kk/4, 32-byte step inside the swizzled 128 B row
-          const uint64_t ad = make_smem_desc(g_addr + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 16, 1024);
-          // B: Y[16 j, 64*nfb features] MN-major: 16 j-rows = 2048 B; next 64-feature box = LBO
-          const uint64_t bd = make_smem_desc(v_addr + kk * 2048, TILE_BYTES, 1024);
-          umma_bf16(tmem_acc, ad, bd, idesc_g, (mt == 0 && kk == 0) ? 0u : 1u);
-        }
-        umma_commit(smem_u32(g_empty));
-        umma_commit(smem_u32(v_empty));
-      };
-      for (int t = t0; t < t1; ++t, ++n) {
-        for (int p = 0; p < P.nprod; ++p, ++it) {
-          const int slot = it % B_SLOTS;
-          const uint32_t use = static_cast<uint32_t>(it / B_SLOTS);
-          mbar_wait(smem_u32(&s_empty[slot]), (use & 1) ^ 1);
-          tc_fence_after();
-          const uint32_t tmem_d = tmem_base + slot * BN;
-          for (int kc = 0; kc < P.kchunks[p]; ++kc) {
-            mbar_wait(smem_u32(&ring_full[stage]), phase);
-            tc_fence_after();
-            const uint32_t a_smem = smem_u32(smem + stage * 2 * TILE_BYTES);
-            issue_s_stage(tmem_d, a_smem, a_smem + TILE_BYTES, kc == 0);
-            umma_commit(smem_u32(&ring_empty[stage]));
-            if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+      for (int k = 0; k < csize; ++k)
+        if (k != crank && t0 + k < t1) mbar_arrive_expect_tx(smem_u32(&g_in[k]), SLAB);
+      auto issue_grads = [&](int r) {
+        for (int k = 0; k < csize; ++k) {
+          if (t0 + r * csize + k >= t1) break;
+          if (k == crank) {
+            mbar_wait(smem_u32(g_written), static_cast<uint32_t>(r) & 1);
+          } else {
+            mbar_wait(smem_u32(&g_in[k]), static_cast<uint32_t>(r) & 1);
+            // re-arm for the next round now: producer k cannot send before this CTA's commit below
+            if (t0 + (r + 1) * csize + k < t1) mbar_arrive_expect_tx(smem_u32(&g_in[k]), SLAB);
           }
-          umma_commit(smem_u32(&s_full[slot]));
+          tc_fence_after();
+          const uint32_t g_addr = smem_u32(g_smem + k * SLAB);
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(smem_u32(&v_full[vs]), vphase);
+            tc_fence_after();
+            const uint32_t v_addr = smem_u32(v_smem + vs * SLAB);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              // A: G[128 rows, 16 j] in K-block h; B: Y16[16 j, 64*nfb features] MN-major (8 KiB boxes)
+              const uint64_t ad = make_smem_desc(g_addr + h * TILE_BYTES + kk * 32, 16, 1024);
+              const uint64_t bd = make_smem_desc(v_addr + kk * 2048, TILE_BYTES / 2, 1024);
+              umma_bf16(tmem_acc, ad, bd, idesc_g, (first_grad && h == 0 && kk == 0) ? 0u : 1u);
+            }
+            umma_commit(smem_u32(&v_empty[vs]));
+            if (++vs == X_NV) { vs = 0; vphase ^= 1; }
+          }
+          first_grad = false;
+          if (csize > 1)
+            umma_commit_mc(smem_u32(g_free), static_cast<uint16_t>(1u << k));  // tell producer k
+          else
+            umma_commit(smem_u32(g_free));
         }
-        if (n > 0) issue_grad(n - 1);  // keep the tensor pipe busy while tile n's epilogue runs
+      };
+      for (int r = 0; r < nrounds; ++r) {
+        const int t = t0 + r * csize + crank;
+        if (t < t1) {
+          for (int p = 0; p < P.nprod; ++p, ++it) {
+            const int slot = it % B_SLOTS;
+            const uint32_t use = static_cast<uint32_t>(it / B_SLOTS);
+            mbar_wait(smem_u32(&s_empty[slot]), (use & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + slot * BN;
+            for (int kc = 0; kc < P.kchunks[p]; ++kc) {
+              mbar_wait(smem_u32(&ring_full[stage]), phase);
+              tc_fence_after();
+              const uint32_t a_smem = smem_u32(s_smem + stage * SLAB);
+              issue_s_stage(tmem_d, a_smem, a_smem + TILE_BYTES, kc == 0);
+              umma_commit(smem_u32(&ring_empty[stage]));
+              if (++stage == ns) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(smem_u32(&s_full[slot]));
+          }
+        }
+        if (r > 0) issue_grads(r - 1);  // keeps the tensor pipe busy while this round's epilogue runs
       }
-      if (n > 0) issue_grad(n - 1);
+      issue_grads(nrounds - 1);
       umma_commit(smem_u32(acc_full));
     }
   } else if (warp >= EPI_WARP0) {
@@ -566,7 +643,7 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     const int lic = min(li, P.b - 1);  // clamped index for per-row constant loads
     const int gi = P.row0 + li;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const uint32_t g_row = smem_u32(g_smem) + half * TILE_BYTES + row * 128;
+    const uint32_t g_row = smem_u32(g_smem + crank * SLAB) + half * TILE_BYTES + row * 128;
     const int sw = row & 7;
     const bool row_only = P.row_only != 0;
     float v[32];
@@ -587,15 +664,17 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     }
 
     int it = 0;
-    int n = 0;
-    for (int t = t0; t < t1; ++t, ++n, it += P.nprod) {
+    for (int r = 0; r < nrounds; ++r, it += P.nprod) {
+      const int t = t0 + r * csize + crank;
+      if (t >= t1) break;
       for (int p = 0; p < P.nprod; ++p) {
         const int slot = (it + p) % B_SLOTS;
         const uint32_t use = static_cast<uint32_t>((it + p) / B_SLOTS);
         mbar_wait(smem_u32(&s_full[slot]), use & 1);
       }
       tc_fence_after();
-      mbar_wait(smem_u32(g_empty), (static_cast<uint32_t>(n) & 1) ^ 1);  // previous G consumed
+      // previous own G tile consumed by every CTA of the cluster (local and remote copies are free)
+      if (r > 0) mbar_wait(smem_u32(g_free), static_cast<uint32_t>(r - 1) & 1);
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         const int jrel0 = t * BN + half * 64 + c * 32;
@@ -648,7 +727,7 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
                 const float q2 = v[e] * c_a * rr[k];
                 const float e1 = fast_exp2(q2 - l_a);
                 const float e2 = row_only ? 0.f : fast_exp2(q2 - ll[k]);
-                g[e] = (gj0 + e == gi) ? 0.f : -(e1 + e2);  // q_ii = 0 (teacher diag masked)
+                g[e] = -(e1 + e2);
               }
             }
           }
@@ -668,9 +747,8 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
                 const float p2 = v[e] * c_b * rr[k];
                 const float e1 = fast_exp2(p2 - l_b);
                 const float e2 = row_only ? 0.f : fast_exp2(p2 - ll[k]);
-                // diagonal: its contribution is parallel to y_a and is annihilated exactly by the
-                // normalise backward (I - y y^T); dropping it removes pure rounding noise
-                // the fp16 operand row is y_j * sigma (exact), so G carries 1/(||y_j|| sigma) <= ~1
+                // the fp16 operand row is y_j * sigma (exact), so G carries 1/(||y_j|| sigma) <= ~1;
+                // diagonal (teacher masked, student parallel to y_a) dropped
                 g[e] = (gj0 + e == gi) ? 0.f : (g[e] + (e1 + e2)) * fminf(rr[k] * inv_sigma, 1.0e4f);
               }
             }
@@ -695,13 +773,13 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       tc_fence_before();
       for (int p = 0; p < P.nprod; ++p) mbar_arrive(smem_u32(&s_empty[(it + p) % B_SLOTS]));
       fence_proxy_async_smem();
-      mbar_arrive(smem_u32(g_full));
+      mbar_arrive(smem_u32(g_written));
     }
 
     // ---- drain the accumulator: TMEM -> fp32 partial gradient
     mbar_wait(smem_u32(acc_full), 0);
     tc_fence_after();
-    if (n > 0) {
+    {
       float* dst = P.acc_part + (static_cast<size_t>(split) * P.b + li) * P.dout + f0;
       const int nvalid = min(nfb * BK, P.dout - f0);
 #pragma unroll 1
@@ -723,16 +801,18 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
         }
       }
     }
-    if (MODE == MODE_CLIP && P.want_ds && chunk == 0 && li < P.b)
-      P.ds_part[(split * 2 + half) * P.b + li] = dsacc;
+    // d(logit_scale) row term: this CTA saw only its own column tiles -> one partial per (split, cluster
+    // rank, half); written by the CTAs of the first chunk group only
+    if (MODE == MODE_CLIP && P.want_ds && P.chunk0 == 0 && li < P.b)
+      P.ds_part[((split * csize + crank) * 2 + half) * P.b + li] = dsacc;
   }
 
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // nobody leaves while a peer may still copy into / signal this CTA
   if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 constexpr int FWD_SMEM_BYTES = F_STAGES * 2 * TILE_BYTES + 1024 + 256;
-constexpr int BWD_SMEM_BYTES = B_STAGES * 2 * TILE_BYTES + 4 * TILE_BYTES + 2 * TILE_BYTES + 1024 + 256;
+constexpr int BWD_SMEM_BYTES = X_SLABS * SLAB + 1024 + 256;
 
 }  // namespace dsoft
