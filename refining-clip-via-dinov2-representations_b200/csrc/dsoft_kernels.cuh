@@ -663,115 +663,138 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       inv_sigma = 1.f / pow2_floor(P.scal[P.rmin_idx]);
     }
 
+    // 32 fp32 -> fp16, 4 x 16-byte swizzled stores into the K-major SW128 A-operand layout
+    auto store_g = [&](const float (&g)[32], int c) {
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const uint32_t w0 = pack_f16x2(g[8 * k4 + 0], g[8 * k4 + 1]);
+        const uint32_t w1 = pack_f16x2(g[8 * k4 + 2], g[8 * k4 + 3]);
+        const uint32_t w2 = pack_f16x2(g[8 * k4 + 4], g[8 * k4 + 5]);
+        const uint32_t w3 = pack_f16x2(g[8 * k4 + 6], g[8 * k4 + 7]);
+        const int chunk16 = c * 4 + k4;
+        st_shared_v4(g_row + ((chunk16 ^ sw) << 4), w0, w1, w2, w3);
+      }
+    };
+
     int it = 0;
     for (int r = 0; r < nrounds; ++r, it += P.nprod) {
       const int t = t0 + r * csize + crank;
       if (t >= t1) break;
-      for (int p = 0; p < P.nprod; ++p) {
-        const int slot = (it + p) % B_SLOTS;
-        const uint32_t use = static_cast<uint32_t>((it + p) / B_SLOTS);
-        mbar_wait(smem_u32(&s_full[slot]), use & 1);
-      }
-      tc_fence_after();
-      // previous own G tile consumed by every CTA of the cluster (local and remote copies are free)
-      if (r > 0) mbar_wait(smem_u32(g_free), static_cast<uint32_t>(r - 1) & 1);
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        const int jrel0 = t * BN + half * 64 + c * 32;
-        const int gj0 = P.col0 + jrel0;
-        const bool ragged = jrel0 + 32 > P.ncols;
-        const uint32_t coff = half * 64 + c * 32;
-        float g[32];
-        if constexpr (MODE == MODE_RAW) {
-          tmem_ld32(lane_addr + (it % B_SLOTS) * BN + coff, v);
+      const int slot0 = it % B_SLOTS;
+      const int jt0 = t * BN + half * 64;  // first column (relative to col0) of this thread's 64 columns
+
+      if constexpr (MODE == MODE_SOFT) {
+        // ---- teacher tile first: E = -(2^(q-lt_a) + 2^(q-lt_j)) stays in registers and the TMEM slot is
+        // handed back at once, so the next tile's teacher MMAs overlap the rest of this epilogue
+        float E[64];
+        const int slot1 = (it + 1) % B_SLOTS;
+        mbar_wait(smem_u32(&s_full[slot0]), static_cast<uint32_t>(it / B_SLOTS) & 1);
+        tc_fence_after();
 #pragma unroll
-          for (int e = 0; e < 32; ++e) g[e] = v[e];
-        } else if constexpr (MODE == MODE_CLIP) {
-          tmem_ld32(lane_addr + (it % B_SLOTS) * BN + coff, v);
-          const float4* lc = reinterpret_cast<const float4*>(P.lse_col + gj0);
+        for (int c = 0; c < 2; ++c) {
+          const int gj0 = P.col0 + jt0 + c * 32;
+          tmem_ld32(lane_addr + slot0 * BN + half * 64 + c * 32, v);
+          const float4* rc = reinterpret_cast<const float4*>(P.rinv_d + gj0);
+          const float4* lc = reinterpret_cast<const float4*>(P.lse_t_col + gj0);
 #pragma unroll
           for (int e4 = 0; e4 < 8; ++e4) {
+            const float4 r4 = __ldg(rc + e4);
             const float4 l4 = __ldg(lc + e4);
+            const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
             const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const int e = 4 * e4 + k;
-              const float x2 = v[e] * c_a;
-              const float e1 = fast_exp2(x2 - l_a);
-              const float e2 = row_only ? 0.f : fast_exp2(x2 - ll[k]);
-              dsacc = fmaf(e1, v[e], dsacc);
-              g[e] = e1 + e2;
+              const float q2 = v[e] * c_a * rr[k];
+              const float e1 = fast_exp2(q2 - l_a);
+              const float e2 = row_only ? 0.f : fast_exp2(q2 - ll[k]);
+              E[c * 32 + e] = -(e1 + e2);
             }
           }
-          if (gi >= gj0 && gi < gj0 + 32) {
-            // the diagonal entry (p_aa close to 1 once trained) is applied in fp32 by finalize_bwd_kernel
+        }
+        tc_fence_before();
+        mbar_arrive(smem_u32(&s_empty[slot0]));
+        // ---- student / text tile
+        mbar_wait(smem_u32(&s_full[slot1]), static_cast<uint32_t>((it + 1) / B_SLOTS) & 1);
+        tc_fence_after();
+        if (r > 0) mbar_wait(smem_u32(g_free), static_cast<uint32_t>(r - 1) & 1);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int jrel0 = jt0 + c * 32;
+          const int gj0 = P.col0 + jrel0;
+          float g[32];
+          tmem_ld32(lane_addr + slot1 * BN + half * 64 + c * 32, v);
+          const float4* rc = reinterpret_cast<const float4*>(P.rinv_y + gj0);
+          const float4* lc = reinterpret_cast<const float4*>(P.lse_y_col + gj0);
+#pragma unroll
+          for (int e4 = 0; e4 < 8; ++e4) {
+            const float4 r4 = __ldg(rc + e4);
+            const float4 l4 = __ldg(lc + e4);
+            const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+            const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int e = 4 * e4 + k;
+              const float p2 = v[e] * c_b * rr[k];
+              const float e1 = fast_exp2(p2 - l_b);
+              const float e2 = row_only ? 0.f : fast_exp2(p2 - ll[k]);
+              // the fp16 operand row is y_j * sigma (exact), so G carries 1/(||y_j|| sigma) <= ~1;
+              // diagonal (teacher masked, student parallel to y_a) and ragged columns dropped
+              const bool dead = (gj0 + e == gi) || (jrel0 + e >= P.ncols);
+              g[e] = dead ? 0.f : (E[c * 32 + e] + (e1 + e2)) * fminf(rr[k] * inv_sigma, 1.0e4f);
+            }
+          }
+          store_g(g, c);
+        }
+        tc_fence_before();
+        mbar_arrive(smem_u32(&s_empty[slot1]));
+      } else {
+        mbar_wait(smem_u32(&s_full[slot0]), static_cast<uint32_t>(it / B_SLOTS) & 1);
+        tc_fence_after();
+        // previous own G tile consumed by every CTA of the cluster (local and remote copies are free)
+        if (r > 0) mbar_wait(smem_u32(g_free), static_cast<uint32_t>(r - 1) & 1);
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          const int jrel0 = jt0 + c * 32;
+          const int gj0 = P.col0 + jrel0;
+          float g[32];
+          tmem_ld32(lane_addr + slot0 * BN + half * 64 + c * 32, v);
+          if constexpr (MODE == MODE_RAW) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) g[e] = v[e];
+          } else {
+            const float4* lc = reinterpret_cast<const float4*>(P.lse_col + gj0);
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const float4 l4 = __ldg(lc + e4);
+              const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int e = 4 * e4 + k;
+                const float x2 = v[e] * c_a;
+                const float e1 = fast_exp2(x2 - l_a);
+                const float e2 = row_only ? 0.f : fast_exp2(x2 - ll[k]);
+                dsacc = fmaf(e1, v[e], dsacc);
+                g[e] = e1 + e2;
+              }
+            }
+            if (gi >= gj0 && gi < gj0 + 32) {
+              // the diagonal entry (p_aa close to 1 once trained) is applied in fp32 by finalize_bwd_kernel
+#pragma unroll
+              for (int e = 0; e < 32; ++e)
+                if (gj0 + e == gi) g[e] = 0.f;
+            }
+          }
+          if (jrel0 + 32 > P.ncols) {
 #pragma unroll
             for (int e = 0; e < 32; ++e)
-              if (gj0 + e == gi) g[e] = 0.f;
+              if (jrel0 + e >= P.ncols) g[e] = 0.f;
           }
-        } else {
-          // teacher part first (kept in g as a negative contribution)
-          tmem_ld32(lane_addr + ((it + 0) % B_SLOTS) * BN + coff, v);
-          {
-            const float4* rc = reinterpret_cast<const float4*>(P.rinv_d + gj0);
-            const float4* lc = reinterpret_cast<const float4*>(P.lse_t_col + gj0);
-#pragma unroll
-            for (int e4 = 0; e4 < 8; ++e4) {
-              const float4 r4 = __ldg(rc + e4);
-              const float4 l4 = __ldg(lc + e4);
-              const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
-              const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int e = 4 * e4 + k;
-                const float q2 = v[e] * c_a * rr[k];
-                const float e1 = fast_exp2(q2 - l_a);
-                const float e2 = row_only ? 0.f : fast_exp2(q2 - ll[k]);
-                g[e] = -(e1 + e2);
-              }
-            }
-          }
-          tmem_ld32(lane_addr + ((it + 1) % B_SLOTS) * BN + coff, v);
-          {
-            const float4* rc = reinterpret_cast<const float4*>(P.rinv_y + gj0);
-            const float4* lc = reinterpret_cast<const float4*>(P.lse_y_col + gj0);
-#pragma unroll
-            for (int e4 = 0; e4 < 8; ++e4) {
-              const float4 r4 = __ldg(rc + e4);
-              const float4 l4 = __ldg(lc + e4);
-              const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
-              const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int e = 4 * e4 + k;
-                const float p2 = v[e] * c_b * rr[k];
-                const float e1 = fast_exp2(p2 - l_b);
-                const float e2 = row_only ? 0.f : fast_exp2(p2 - ll[k]);
-                // the fp16 operand row is y_j * sigma (exact), so G carries 1/(||y_j|| sigma) <= ~1;
-                // diagonal (teacher masked, student parallel to y_a) dropped
-                g[e] = (gj0 + e == gi) ? 0.f : (g[e] + (e1 + e2)) * fminf(rr[k] * inv_sigma, 1.0e4f);
-              }
-            }
-          }
+          store_g(g, c);
         }
-        if (ragged) {
-#pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (jrel0 + e >= P.ncols) g[e] = 0.f;
-        }
-        // 32 values -> 4 x 16-byte swizzled stores into the K-major SW128 A-operand layout
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-          const uint32_t w0 = pack_f16x2(g[8 * k4 + 0], g[8 * k4 + 1]);
-          const uint32_t w1 = pack_f16x2(g[8 * k4 + 2], g[8 * k4 + 3]);
-          const uint32_t w2 = pack_f16x2(g[8 * k4 + 4], g[8 * k4 + 5]);
-          const uint32_t w3 = pack_f16x2(g[8 * k4 + 6], g[8 * k4 + 7]);
-          const int chunk16 = c * 4 + k4;
-          st_shared_v4(g_row + ((chunk16 ^ sw) << 4), w0, w1, w2, w3);
-        }
+        tc_fence_before();
+        mbar_arrive(smem_u32(&s_empty[slot0]));
       }
-      tc_fence_before();
-      for (int p = 0; p < P.nprod; ++p) mbar_arrive(smem_u32(&s_empty[(it + p) % B_SLOTS]));
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(g_written));
     }
