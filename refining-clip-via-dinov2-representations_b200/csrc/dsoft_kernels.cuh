@@ -435,12 +435,15 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
 //  to the other CTAs with a DSMEM bulk copy (cp.async.bulk.shared::cluster).  Every CTA then multiplies
 //  all C tiles of the round with its own feature chunk of Y.  No S tile is ever recomputed per chunk.
 //
-//  shared memory (7 slabs of 32 KiB): G[C] | V ring (2 half tiles: 64 j x 256 features) | S-operand ring
-//  warps: 0 = S-operand TMA, 1 = MMA issuer, 2 = TMEM alloc + V TMA, 3 = G sender, 4..11 = epilogue
+//  shared memory (7 slabs of 32 KiB): G[C] | one operand ring of 7 - C stages.  A ring stage holds either
+//  an S-operand pair (A box | B box, 64 features) or a gradient-operand half tile (64 j x 256 features);
+//  the TMA producer fills stages in exactly the order the MMA issuer consumes them, so every phase of the
+//  kernel has the whole ring (up to 192 KiB) in flight.
+//  warps: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM alloc, 3 = G sender, 4..11 = epilogue
 constexpr int X_MAXC = 3;
 constexpr int SLAB = 2 * TILE_BYTES;   // 32 KiB
 constexpr int X_SLABS = 7;
-constexpr int X_NV = 2;
+constexpr int X_MAXSTAGES = 6;
 
 template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -450,17 +453,14 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   uint8_t* smem = align_1024(smem_raw);
   const int csize = gridDim.x;           // cluster size == feature chunks handled by this launch
   const int crank = blockIdx.x;          // == %cluster_ctarank
-  const int ns = X_SLABS - X_NV - csize; // S-operand ring stages (4 / 3 / 2)
+  const int ns = X_SLABS - csize;        // operand ring stages (6 / 5 / 4)
   uint8_t* g_smem = smem;                          // csize slabs: G tile of producer k at slab k
-  uint8_t* v_smem = smem + csize * SLAB;           // X_NV slabs
-  uint8_t* s_smem = v_smem + X_NV * SLAB;          // ns slabs: A box | B box
+  uint8_t* s_smem = smem + csize * SLAB;           // ns slabs
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + X_SLABS * SLAB);
-  uint64_t* ring_full = bars;           // [4]
-  uint64_t* ring_empty = bars + 4;      // [4]
-  uint64_t* s_full = bars + 8;          // [2]
-  uint64_t* s_empty = bars + 10;        // [2]
-  uint64_t* v_full = bars + 12;         // [2]
-  uint64_t* v_empty = bars + 14;        // [2]
+  uint64_t* ring_full = bars;           // [6]
+  uint64_t* ring_empty = bars + 6;      // [6]
+  uint64_t* s_full = bars + 12;         // [2]
+  uint64_t* s_empty = bars + 14;        // [2]
   uint64_t* g_written = bars + 16;      // own G tile stored (256 epilogue arrivals)
   uint64_t* g_in = bars + 17;           // [3] G tile of producer k landed (tx bytes)
   uint64_t* g_free = bars + 20;         // own G tile consumed by all C CTAs (multicast commits)
@@ -481,17 +481,13 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) tma_prefetch_desc(&maps.m[i]);
     tma_prefetch_desc(&vmap);
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < X_MAXSTAGES; ++i) {
       mbar_init(smem_u32(&ring_full[i]), 1);
       mbar_init(smem_u32(&ring_empty[i]), 1);
     }
     for (int i = 0; i < B_SLOTS; ++i) {
       mbar_init(smem_u32(&s_full[i]), 1);
       mbar_init(smem_u32(&s_empty[i]), NUM_EPI_THREADS);
-    }
-    for (int i = 0; i < X_NV; ++i) {
-      mbar_init(smem_u32(&v_full[i]), 1);
-      mbar_init(smem_u32(&v_empty[i]), 1);
     }
     mbar_init(smem_u32(g_written), NUM_EPI_THREADS);
     for (int i = 0; i < X_MAXC; ++i) mbar_init(smem_u32(&g_in[i]), 1);
@@ -506,49 +502,45 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_holder;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ S-operand TMA producer
+    // ------------------------------------------------------------------ TMA producer (one ring, MMA order)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int r = 0; r < nrounds; ++r) {
-        const int t = t0 + r * csize + crank;
-        if (t >= t1) break;
-        for (int p = 0; p < P.nprod; ++p) {
-          const CUtensorMap* am = &maps.m[P.a_map[p]];
-          const CUtensorMap* bm = &maps.m[P.b_map[p]];
-          for (int kc = 0; kc < P.kchunks[p]; ++kc) {
-            mbar_wait(smem_u32(&ring_empty[stage]), phase ^ 1);
-            const uint32_t full = smem_u32(&ring_full[stage]);
-            const uint32_t a_dst = smem_u32(s_smem + stage * SLAB);
-            mbar_arrive_expect_tx(full, 2 * TILE_BYTES);
-            tma_load_2d(a_dst, am, full, kc * BK, P.row0 + rb * BM);
-            tma_load_2d(a_dst + TILE_BYTES, bm, full, kc * BK, P.col0 + t * BN);
-            if (++stage == ns) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == 2) {
-    // ------------------------------------------------------------------ gradient-operand (Y16) TMA producer
-    // same order as the MMA issuer consumes: round, producer k, half (64 columns j each)
-    if (lane == 0) {
-      int vs = 0;
-      uint32_t vphase = 0;
-      for (int r = 0; r < nrounds; ++r) {
+      auto load_grad_operands = [&](int r) {  // Y16 half tiles for the gradient GEMMs of round r
         for (int k = 0; k < csize; ++k) {
           const int t = t0 + r * csize + k;
           if (t >= t1) break;
           for (int h = 0; h < 2; ++h) {
-            mbar_wait(smem_u32(&v_empty[vs]), vphase ^ 1);
-            const uint32_t vf = smem_u32(&v_full[vs]);
-            mbar_arrive_expect_tx(vf, nfb * (TILE_BYTES / 2));
+            mbar_wait(smem_u32(&ring_empty[stage]), phase ^ 1);
+            const uint32_t full = smem_u32(&ring_full[stage]);
+            const uint32_t dst = smem_u32(s_smem + stage * SLAB);
+            mbar_arrive_expect_tx(full, nfb * (TILE_BYTES / 2));
             for (int fb = 0; fb < nfb; ++fb)
-              tma_load_2d(smem_u32(v_smem + vs * SLAB + fb * (TILE_BYTES / 2)), &vmap, vf, f0 + fb * BK,
-                          P.col0 + t * BN + h * 64);
-            if (++vs == X_NV) { vs = 0; vphase ^= 1; }
+              tma_load_2d(dst + fb * (TILE_BYTES / 2), &vmap, full, f0 + fb * BK, P.col0 + t * BN + h * 64);
+            if (++stage == ns) { stage = 0; phase ^= 1; }
           }
         }
+      };
+      for (int r = 0; r < nrounds; ++r) {
+        const int t = t0 + r * csize + crank;
+        if (t < t1) {
+          for (int p = 0; p < P.nprod; ++p) {
+            const CUtensorMap* am = &maps.m[P.a_map[p]];
+            const CUtensorMap* bm = &maps.m[P.b_map[p]];
+            for (int kc = 0; kc < P.kchunks[p]; ++kc) {
+              mbar_wait(smem_u32(&ring_empty[stage]), phase ^ 1);
+              const uint32_t full = smem_u32(&ring_full[stage]);
+              const uint32_t a_dst = smem_u32(s_smem + stage * SLAB);
+              mbar_arrive_expect_tx(full, 2 * TILE_BYTES);
+              tma_load_2d(a_dst, am, full, kc * BK, P.row0 + rb * BM);
+              tma_load_2d(a_dst + TILE_BYTES, bm, full, kc * BK, P.col0 + t * BN);
+              if (++stage == ns) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+        if (r > 0) load_grad_operands(r - 1);
       }
+      load_grad_operands(nrounds - 1);
     }
   } else if (warp == 3) {
     // ------------------------------------------------------------------ G sender (DSMEM bulk copies)
@@ -569,8 +561,6 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      int vs = 0;
-      uint32_t vphase = 0;
       bool first_grad = true;
       const uint32_t idesc_g = make_idesc_bf16(BM, nfb * BK, 0, 1, 1);  // fp16: A = G (K-major), B = Y16 (MN-major)
       const uint32_t tmem_acc = tmem_base + ACC_COL;
@@ -589,9 +579,9 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
           tc_fence_after();
           const uint32_t g_addr = smem_u32(g_smem + k * SLAB);
           for (int h = 0; h < 2; ++h) {
-            mbar_wait(smem_u32(&v_full[vs]), vphase);
+            mbar_wait(smem_u32(&ring_full[stage]), phase);
             tc_fence_after();
-            const uint32_t v_addr = smem_u32(v_smem + vs * SLAB);
+            const uint32_t v_addr = smem_u32(s_smem + stage * SLAB);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               // A: G[128 rows, 16 j] in K-block h; B: Y16[16 j, 64*nfb features] MN-major (8 KiB boxes)
@@ -599,8 +589,8 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
               const uint64_t bd = make_smem_desc(v_addr + kk * 2048, TILE_BYTES / 2, 1024);
               umma_bf16(tmem_acc, ad, bd, idesc_g, (first_grad && h == 0 && kk == 0) ? 0u : 1u);
             }
-            umma_commit(smem_u32(&v_empty[vs]));
-            if (++vs == X_NV) { vs = 0; vphase ^= 1; }
+            umma_commit(smem_u32(&ring_empty[stage]));
+            if (++stage == ns) { stage = 0; phase ^= 1; }
           }
           first_grad = false;
           if (csize > 1)
