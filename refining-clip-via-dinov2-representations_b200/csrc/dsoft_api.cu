@@ -784,6 +784,7 @@ static void fill_clip_fwd(const dsoft_plan* p, FwdParams& P, int amap, int bmap,
   P.a_map[0] = amap;
   P.b_map[0] = bmap;
   P.kchunks[0] = ceil_div(p->sh.D, BK);
+  P.resident = P.kchunks[0] <= 8;
   P.row0 = p->sh.rank * p->sh.b;
   P.b = p->sh.b;
   P.col0 = 0;

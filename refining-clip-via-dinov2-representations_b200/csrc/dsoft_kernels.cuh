@@ -74,6 +74,8 @@ struct FwdParams {
   int ntiles;       // ceil(ncols / 128)
   int tiles_per_split;
   int npart;        // nsplit * 2 (two column halves per split)
+  int resident;     // single product with K <= 512: the row block's operand stays in smem (8 boxes),
+                    // only the column operand streams through a ring of 16 KiB stages
   const float* scal;
   const float* rinv[3];  // per product: inverse L2 norms by global index (soft only)
   float* part;           // partial statistics [nstat][npart][b]
@@ -134,12 +136,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ FwdParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_1024(smem_raw);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F_STAGES * 2 * TILE_BYTES);
-  uint64_t* ring_full = bars;
-  uint64_t* ring_empty = bars + F_STAGES;
-  uint64_t* s_full = bars + 2 * F_STAGES;
+  // streaming mode: F_STAGES stages of (A box | B box); resident mode: 8 A boxes, then 6 B-box stages
+  const bool resident = P.resident != 0;
+  const int nstages = resident ? 6 : 7;
+  const int stage_bytes = resident ? TILE_BYTES : 2 * TILE_BYTES;
+  uint8_t* ring = resident ? smem + 8 * TILE_BYTES : smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F_STAGES * 2 * TILE_BYTES + 2 * TILE_BYTES);
+  uint64_t* ring_full = bars;        // [8]
+  uint64_t* ring_empty = bars + 8;   // [8]
+  uint64_t* s_full = bars + 16;
   uint64_t* s_empty = s_full + F_SLOTS;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(s_empty + F_SLOTS);
+  uint64_t* a_full = s_empty + F_SLOTS;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -150,7 +158,7 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) tma_prefetch_desc(&maps.m[i]);
-    for (int i = 0; i < F_STAGES; ++i) {
+    for (int i = 0; i < 8; ++i) {
       mbar_init(smem_u32(&ring_full[i]), 1);
       mbar_init(smem_u32(&ring_empty[i]), 1);
     }
@@ -158,6 +166,7 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       mbar_init(smem_u32(&s_full[i]), 1);
       mbar_init(smem_u32(&s_empty[i]), NUM_EPI_THREADS);
     }
+    mbar_init(smem_u32(a_full), 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(tmem_holder), TMEM_COLS);
@@ -167,48 +176,68 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_holder;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = t0; t < t1; ++t) {
-        for (int p = 0; p < P.nprod; ++p) {
-          const CUtensorMap* am = &maps.m[P.a_map[p]];
-          const CUtensorMap* bm = &maps.m[P.b_map[p]];
-          for (int kc = 0; kc < P.kchunks[p]; ++kc) {
-            mbar_wait(smem_u32(&ring_empty[stage]), phase ^ 1);
+    // ------------------------------------------------------------------ TMA producer (warp-uniform loop)
+    int stage = 0;
+    uint32_t phase = 0;
+    if (resident && elect_one()) {
+      const uint32_t af = smem_u32(a_full);
+      mbar_arrive_expect_tx(af, P.kchunks[0] * TILE_BYTES);
+      for (int kc = 0; kc < P.kchunks[0]; ++kc)
+        tma_load_2d(smem_u32(smem + kc * TILE_BYTES), &maps.m[P.a_map[0]], af, kc * BK, P.row0 + rb * BM);
+    }
+    __syncwarp();
+    for (int t = t0; t < t1; ++t) {
+      for (int p = 0; p < P.nprod; ++p) {
+        const CUtensorMap* am = &maps.m[P.a_map[p]];
+        const CUtensorMap* bm = &maps.m[P.b_map[p]];
+        for (int kc = 0; kc < P.kchunks[p]; ++kc) {
+          mbar_wait(smem_u32(&ring_empty[stage]), phase ^ 1);
+          if (elect_one()) {
             const uint32_t full = smem_u32(&ring_full[stage]);
-            const uint32_t a_dst = smem_u32(smem + stage * 2 * TILE_BYTES);
-            mbar_arrive_expect_tx(full, 2 * TILE_BYTES);
-            tma_load_2d(a_dst, am, full, kc * BK, P.row0 + rb * BM);
-            tma_load_2d(a_dst + TILE_BYTES, bm, full, kc * BK, P.col0 + t * BN);
-            if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+            const uint32_t dst = smem_u32(ring + stage * stage_bytes);
+            mbar_arrive_expect_tx(full, stage_bytes);
+            if (resident) {
+              tma_load_2d(dst, bm, full, kc * BK, P.col0 + t * BN);
+            } else {
+              tma_load_2d(dst, am, full, kc * BK, P.row0 + rb * BM);
+              tma_load_2d(dst + TILE_BYTES, bm, full, kc * BK, P.col0 + t * BN);
+            }
           }
+          __syncwarp();
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int t = t0; t < t1; ++t) {
-        for (int p = 0; p < P.nprod; ++p, ++it) {
-          const int slot = it % F_SLOTS;
-          const uint32_t use = static_cast<uint32_t>(it / F_SLOTS);
-          mbar_wait(smem_u32(&s_empty[slot]), (use & 1) ^ 1);
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop)
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    if (resident) {
+      mbar_wait(smem_u32(a_full), 0);
+      tc_fence_after();
+    }
+    for (int t = t0; t < t1; ++t) {
+      for (int p = 0; p < P.nprod; ++p, ++it) {
+        const int slot = it % F_SLOTS;
+        const uint32_t use = static_cast<uint32_t>(it / F_SLOTS);
+        mbar_wait(smem_u32(&s_empty[slot]), (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + slot * BN;
+        for (int kc = 0; kc < P.kchunks[p]; ++kc) {
+          mbar_wait(smem_u32(&ring_full[stage]), phase);
           tc_fence_after();
-          const uint32_t tmem_d = tmem_base + slot * BN;
-          for (int kc = 0; kc < P.kchunks[p]; ++kc) {
-            mbar_wait(smem_u32(&ring_full[stage]), phase);
-            tc_fence_after();
-            const uint32_t a_smem = smem_u32(smem + stage * 2 * TILE_BYTES);
-            issue_s_stage(tmem_d, a_smem, a_smem + TILE_BYTES, kc == 0);
+          if (elect_one()) {
+            const uint32_t st_smem = smem_u32(ring + stage * stage_bytes);
+            if (resident)
+              issue_s_stage(tmem_d, smem_u32(smem + kc * TILE_BYTES), st_smem, kc == 0);
+            else
+              issue_s_stage(tmem_d, st_smem, st_smem + TILE_BYTES, kc == 0);
             umma_commit(smem_u32(&ring_empty[stage]));
-            if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+            if (kc == P.kchunks[p] - 1) umma_commit(smem_u32(&s_full[slot]));
           }
-          umma_commit(smem_u32(&s_full[slot]));
+          __syncwarp();
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -503,84 +532,95 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one ring, MMA order)
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      auto load_grad_operands = [&](int r) {  // Y16 half tiles for the gradient GEMMs of round r
-        for (int k = 0; k < csize; ++k) {
-          const int t = t0 + r * csize + k;
-          if (t >= t1) break;
-          for (int h = 0; h < 2; ++h) {
-            mbar_wait(smem_u32(&ring_empty[stage]), phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    auto load_grad_operands = [&](int r) {  // Y16 half tiles for the gradient GEMMs of round r
+      for (int k = 0; k < csize; ++k) {
+        const int t = t0 + r * csize + k;
+        if (t >= t1) break;
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(smem_u32(&ring_empty[stage]), phase ^ 1);
+          if (elect_one()) {
             const uint32_t full = smem_u32(&ring_full[stage]);
             const uint32_t dst = smem_u32(s_smem + stage * SLAB);
             mbar_arrive_expect_tx(full, nfb * (TILE_BYTES / 2));
             for (int fb = 0; fb < nfb; ++fb)
               tma_load_2d(dst + fb * (TILE_BYTES / 2), &vmap, full, f0 + fb * BK, P.col0 + t * BN + h * 64);
-            if (++stage == ns) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == ns) { stage = 0; phase ^= 1; }
         }
-      };
-      for (int r = 0; r < nrounds; ++r) {
-        const int t = t0 + r * csize + crank;
-        if (t < t1) {
-          for (int p = 0; p < P.nprod; ++p) {
-            const CUtensorMap* am = &maps.m[P.a_map[p]];
-            const CUtensorMap* bm = &maps.m[P.b_map[p]];
-            for (int kc = 0; kc < P.kchunks[p]; ++kc) {
-              mbar_wait(smem_u32(&ring_empty[stage]), phase ^ 1);
+      }
+    };
+    for (int r = 0; r < nrounds; ++r) {
+      const int t = t0 + r * csize + crank;
+      if (t < t1) {
+        for (int p = 0; p < P.nprod; ++p) {
+          const CUtensorMap* am = &maps.m[P.a_map[p]];
+          const CUtensorMap* bm = &maps.m[P.b_map[p]];
+          for (int kc = 0; kc < P.kchunks[p]; ++kc) {
+            mbar_wait(smem_u32(&ring_empty[stage]), phase ^ 1);
+            if (elect_one()) {
               const uint32_t full = smem_u32(&ring_full[stage]);
               const uint32_t a_dst = smem_u32(s_smem + stage * SLAB);
               mbar_arrive_expect_tx(full, 2 * TILE_BYTES);
               tma_load_2d(a_dst, am, full, kc * BK, P.row0 + rb * BM);
               tma_load_2d(a_dst + TILE_BYTES, bm, full, kc * BK, P.col0 + t * BN);
-              if (++stage == ns) { stage = 0; phase ^= 1; }
             }
+            __syncwarp();
+            if (++stage == ns) { stage = 0; phase ^= 1; }
           }
         }
-        if (r > 0) load_grad_operands(r - 1);
       }
-      load_grad_operands(nrounds - 1);
+      if (r > 0) load_grad_operands(r - 1);
     }
+    load_grad_operands(nrounds - 1);
   } else if (warp == 3) {
     // ------------------------------------------------------------------ G sender (DSMEM bulk copies)
-    if (lane == 0 && csize > 1) {
+    if (csize > 1) {
       const uint32_t src = smem_u32(g_smem + crank * SLAB);
       for (int r = 0; r < nrounds; ++r) {
         if (t0 + r * csize + crank >= t1) break;
         mbar_wait(smem_u32(g_written), static_cast<uint32_t>(r) & 1);
-        for (int k = 0; k < csize; ++k) {
-          if (k == crank) continue;
-          bulk_copy_to_peer(mapa_shared(src, k), src, SLAB, mapa_shared(smem_u32(&g_in[crank]), k));
+        if (elect_one()) {
+          for (int k = 0; k < csize; ++k) {
+            if (k == crank) continue;
+            bulk_copy_to_peer(mapa_shared(src, k), src, SLAB, mapa_shared(smem_u32(&g_in[crank]), k));
+          }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      bool first_grad = true;
-      const uint32_t idesc_g = make_idesc_bf16(BM, nfb * BK, 0, 1, 1);  // fp16: A = G (K-major), B = Y16 (MN-major)
-      const uint32_t tmem_acc = tmem_base + ACC_COL;
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop)
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    bool first_grad = true;
+    const uint32_t idesc_g = make_idesc_bf16(BM, nfb * BK, 0, 1, 1);  // fp16: A = G (K-major), B = Y16 (MN-major)
+    const uint32_t tmem_acc = tmem_base + ACC_COL;
+    if (elect_one()) {
       for (int k = 0; k < csize; ++k)
         if (k != crank && t0 + k < t1) mbar_arrive_expect_tx(smem_u32(&g_in[k]), SLAB);
-      auto issue_grads = [&](int r) {
-        for (int k = 0; k < csize; ++k) {
-          if (t0 + r * csize + k >= t1) break;
-          if (k == crank) {
-            mbar_wait(smem_u32(g_written), static_cast<uint32_t>(r) & 1);
-          } else {
-            mbar_wait(smem_u32(&g_in[k]), static_cast<uint32_t>(r) & 1);
-            // re-arm for the next round now: producer k cannot send before this CTA's commit below
-            if (t0 + (r + 1) * csize + k < t1) mbar_arrive_expect_tx(smem_u32(&g_in[k]), SLAB);
-          }
+    }
+    __syncwarp();
+    auto issue_grads = [&](int r) {
+      for (int k = 0; k < csize; ++k) {
+        if (t0 + r * csize + k >= t1) break;
+        if (k == crank) {
+          mbar_wait(smem_u32(g_written), static_cast<uint32_t>(r) & 1);
+        } else {
+          mbar_wait(smem_u32(&g_in[k]), static_cast<uint32_t>(r) & 1);
+          // re-arm for the next round now: producer k cannot send before this CTA's commit below
+          if (t0 + (r + 1) * csize + k < t1 && elect_one()) mbar_arrive_expect_tx(smem_u32(&g_in[k]), SLAB);
+          __syncwarp();
+        }
+        tc_fence_after();
+        const uint32_t g_addr = smem_u32(g_smem + k * SLAB);
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(smem_u32(&ring_full[stage]), phase);
           tc_fence_after();
-          const uint32_t g_addr = smem_u32(g_smem + k * SLAB);
-          for (int h = 0; h < 2; ++h) {
-            mbar_wait(smem_u32(&ring_full[stage]), phase);
-            tc_fence_after();
+          if (elect_one()) {
             const uint32_t v_addr = smem_u32(s_smem + stage * SLAB);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
@@ -590,40 +630,47 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
               umma_bf16(tmem_acc, ad, bd, idesc_g, (first_grad && h == 0 && kk == 0) ? 0u : 1u);
             }
             umma_commit(smem_u32(&ring_empty[stage]));
-            if (++stage == ns) { stage = 0; phase ^= 1; }
+            if (h == 1) {
+              if (csize > 1)
+                umma_commit_mc(smem_u32(g_free), static_cast<uint16_t>(1u << k));  // tell producer k
+              else
+                umma_commit(smem_u32(g_free));
+            }
           }
-          first_grad = false;
-          if (csize > 1)
-            umma_commit_mc(smem_u32(g_free), static_cast<uint16_t>(1u << k));  // tell producer k
-          else
-            umma_commit(smem_u32(g_free));
+          __syncwarp();
+          if (++stage == ns) { stage = 0; phase ^= 1; }
         }
-      };
-      for (int r = 0; r < nrounds; ++r) {
-        const int t = t0 + r * csize + crank;
-        if (t < t1) {
-          for (int p = 0; p < P.nprod; ++p, ++it) {
-            const int slot = it % B_SLOTS;
-            const uint32_t use = static_cast<uint32_t>(it / B_SLOTS);
-            mbar_wait(smem_u32(&s_empty[slot]), (use & 1) ^ 1);
+        first_grad = false;
+      }
+    };
+    for (int r = 0; r < nrounds; ++r) {
+      const int t = t0 + r * csize + crank;
+      if (t < t1) {
+        for (int p = 0; p < P.nprod; ++p, ++it) {
+          const int slot = it % B_SLOTS;
+          const uint32_t use = static_cast<uint32_t>(it / B_SLOTS);
+          mbar_wait(smem_u32(&s_empty[slot]), (use & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + slot * BN;
+          for (int kc = 0; kc < P.kchunks[p]; ++kc) {
+            mbar_wait(smem_u32(&ring_full[stage]), phase);
             tc_fence_after();
-            const uint32_t tmem_d = tmem_base + slot * BN;
-            for (int kc = 0; kc < P.kchunks[p]; ++kc) {
-              mbar_wait(smem_u32(&ring_full[stage]), phase);
-              tc_fence_after();
+            if (elect_one()) {
               const uint32_t a_smem = smem_u32(s_smem + stage * SLAB);
               issue_s_stage(tmem_d, a_smem, a_smem + TILE_BYTES, kc == 0);
               umma_commit(smem_u32(&ring_empty[stage]));
-              if (++stage == ns) { stage = 0; phase ^= 1; }
+              if (kc == P.kchunks[p] - 1) umma_commit(smem_u32(&s_full[slot]));
             }
-            umma_commit(smem_u32(&s_full[slot]));
+            __syncwarp();
+            if (++stage == ns) { stage = 0; phase ^= 1; }
           }
         }
-        if (r > 0) issue_grads(r - 1);  // keeps the tensor pipe busy while this round's epilogue runs
       }
-      issue_grads(nrounds - 1);
-      umma_commit(smem_u32(acc_full));
+      if (r > 0) issue_grads(r - 1);  // keeps the tensor pipe busy while this round's epilogue runs
     }
+    issue_grads(nrounds - 1);
+    if (elect_one()) umma_commit(smem_u32(acc_full));
+    __syncwarp();
   } else if (warp >= EPI_WARP0) {
     // ------------------------------------------------------------------ epilogue
     const int q = warp & 3;
@@ -825,7 +872,7 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-constexpr int FWD_SMEM_BYTES = F_STAGES * 2 * TILE_BYTES + 1024 + 256;
+constexpr int FWD_SMEM_BYTES = F_STAGES * 2 * TILE_BYTES + 2 * TILE_BYTES + 1024 + 256;  // 7 slabs
 constexpr int BWD_SMEM_BYTES = X_SLABS * SLAB + 1024 + 256;
 
 }  // namespace dsoft

@@ -14,6 +14,22 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a fully converged warp.  The producer / MMA-issuer warps run their loops warp-uniformly and
+// predicate only the issue instructions with this: inside a divergent `if (lane == 0)` the compiler cannot
+// keep descriptors in uniform registers and wraps every UTCHMMA / UTMALDG in an ELECT + R2UR waterfall loop
+// (measured: the issuing thread, not the tensor pipe or L2, then bounds the kernel at ~40 %).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
