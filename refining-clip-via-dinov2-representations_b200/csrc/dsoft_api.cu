@@ -159,7 +159,7 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   p->nch_clip = ceil_div(sh->D, CHUNK_F);
   p->nch_stu = ceil_div(p->Dz, CHUNK_F);
   p->nch_txt = ceil_div(sh->D, CHUNK_F);
-  p->f_clip = choose_split(rbs, 1, p->ntiles_g, sms);
+  p->f_clip = choose_split(rbs, 1, ceil_div(p->B, 2 * BN), sms);  // forward CLIP kernel uses 256-column tiles
   p->f_soft = choose_split(rbs, 1, p->ntiles_s, sms);
   p->b_clip = choose_split(rbs, p->nch_clip, p->ntiles_g, sms);
   p->b_stu = choose_split(rbs, p->nch_stu, p->ntiles_s, sms);
@@ -785,11 +785,12 @@ static void fill_clip_fwd(const dsoft_plan* p, FwdParams& P, int amap, int bmap,
   P.b_map[0] = bmap;
   P.kchunks[0] = ceil_div(p->sh.D, BK);
   P.resident = P.kchunks[0] <= 8;
+  P.bn = 2 * BN;
   P.row0 = p->sh.rank * p->sh.b;
   P.b = p->sh.b;
   P.col0 = 0;
   P.ncols = p->B;
-  P.ntiles = p->ntiles_g;
+  P.ntiles = ceil_div(p->B, 2 * BN);
   P.tiles_per_split = p->f_clip.tps;
   P.npart = 2 * p->f_clip.nsplit;
   P.scal = scal;
@@ -850,6 +851,7 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
   if (p->have_soft) {
     memset(&P, 0, sizeof(P));
     P.nprod = p->have_text ? 3 : 2;
+    P.bn = BN;
     P.a_map[0] = P.b_map[0] = 3;  // teacher: dino . dino^T       (loss.py:373)
     P.a_map[1] = P.b_map[1] = 2;  // student: Zs . Zs^T           (loss.py:372)
     P.a_map[2] = P.b_map[2] = 1;  // text:    Tn . Tn^T           (loss.py:394)
@@ -1090,11 +1092,15 @@ extern "C" int dsoft_selftest_gemm(const void* a, const void* bmat, float* c, in
   P.a_map[0] = 0;
   P.b_map[0] = 1;
   P.kchunks[0] = ceil_div(K, BK);
+  // exercise all four operand-staging modes of the forward kernel (resident / streamed row operand,
+  // 128- / 256-column tiles) across the test shapes
+  P.bn = (K % 128 == 0) ? 2 * BN : BN;
+  P.resident = (P.kchunks[0] <= 8 && (M / BM) % 2 == 0) ? 1 : 0;
   P.row0 = 0;
   P.b = M;
   P.col0 = 0;
   P.ncols = N;
-  P.ntiles = ceil_div(N, BN);
+  P.ntiles = ceil_div(N, P.bn);
   const int nsplit = std::min(P.ntiles, 3);
   P.tiles_per_split = ceil_div(P.ntiles, nsplit);
   P.npart = 0;

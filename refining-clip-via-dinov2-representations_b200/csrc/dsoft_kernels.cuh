@@ -74,6 +74,7 @@ struct FwdParams {
   int ntiles;       // ceil(ncols / 128)
   int tiles_per_split;
   int npart;        // nsplit * 2 (two column halves per split)
+  int bn;           // columns per tile: 128, or 256 (clip only: one N=256 MMA per K step, 2 TMEM slots)
   int resident;     // single product with K <= 512: the row block's operand stays in smem (8 boxes),
                     // only the column operand streams through a ring of 16 KiB stages
   const float* scal;
@@ -112,10 +113,11 @@ __device__ __forceinline__ uint8_t* align_1024(uint8_t* p) {
   return reinterpret_cast<uint8_t*>((a + 1023) & ~static_cast<uintptr_t>(1023));
 }
 
-// S tile (128 x 128, K = 64 slice): 4 tcgen05.mma of K=16, both operands K-major SW128.
+// S tile (128 x n, K = 64 slice; n = 128 or 256 columns): 4 tcgen05.mma of K=16, both operands K-major
+// SW128 (a 256-column B operand is two stacked 128-row boxes = 32 contiguous 8-row swizzle groups).
 __device__ __forceinline__ void issue_s_stage(uint32_t tmem_d, uint32_t a_smem, uint32_t b_smem,
-                                              bool first_stage) {
-  constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+                                              bool first_stage, int n = BN) {
+  const uint32_t idesc = make_idesc_bf16(BM, n, 0, 0);
   const uint64_t ad = make_smem_desc(a_smem, 16, 1024);
   const uint64_t bd = make_smem_desc(b_smem, 16, 1024);
 #pragma unroll
@@ -138,8 +140,11 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   uint8_t* smem = align_1024(smem_raw);
   // streaming mode: F_STAGES stages of (A box | B box); resident mode: 8 A boxes, then 6 B-box stages
   const bool resident = P.resident != 0;
-  const int nstages = resident ? 6 : 7;
-  const int stage_bytes = resident ? TILE_BYTES : 2 * TILE_BYTES;
+  const int bn = P.bn;
+  const int nbox = bn / BN;  // 128-row boxes of the column operand per stage
+  const int stage_bytes = (resident ? 0 : TILE_BYTES) + nbox * TILE_BYTES;
+  const int nstages = min(8, (resident ? 6 : 14) * TILE_BYTES / stage_bytes);
+  const int nslots = TMEM_COLS / bn;  // 4 x 128 or 2 x 256 columns
   uint8_t* ring = resident ? smem + 8 * TILE_BYTES : smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F_STAGES * 2 * TILE_BYTES + 2 * TILE_BYTES);
   uint64_t* ring_full = bars;        // [8]
@@ -196,12 +201,13 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
             const uint32_t full = smem_u32(&ring_full[stage]);
             const uint32_t dst = smem_u32(ring + stage * stage_bytes);
             mbar_arrive_expect_tx(full, stage_bytes);
-            if (resident) {
-              tma_load_2d(dst, bm, full, kc * BK, P.col0 + t * BN);
-            } else {
+            uint32_t bdst = dst;
+            if (!resident) {
               tma_load_2d(dst, am, full, kc * BK, P.row0 + rb * BM);
-              tma_load_2d(dst + TILE_BYTES, bm, full, kc * BK, P.col0 + t * BN);
+              bdst += TILE_BYTES;
             }
+            for (int i = 0; i < nbox; ++i)
+              tma_load_2d(bdst + i * TILE_BYTES, bm, full, kc * BK, P.col0 + t * bn + i * BN);
           }
           __syncwarp();
           if (++stage == nstages) { stage = 0; phase ^= 1; }
@@ -219,20 +225,20 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     }
     for (int t = t0; t < t1; ++t) {
       for (int p = 0; p < P.nprod; ++p, ++it) {
-        const int slot = it % F_SLOTS;
-        const uint32_t use = static_cast<uint32_t>(it / F_SLOTS);
+        const int slot = it % nslots;
+        const uint32_t use = static_cast<uint32_t>(it / nslots);
         mbar_wait(smem_u32(&s_empty[slot]), (use & 1) ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + slot * BN;
+        const uint32_t tmem_d = tmem_base + slot * bn;
         for (int kc = 0; kc < P.kchunks[p]; ++kc) {
           mbar_wait(smem_u32(&ring_full[stage]), phase);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t st_smem = smem_u32(ring + stage * stage_bytes);
             if (resident)
-              issue_s_stage(tmem_d, smem_u32(smem + kc * TILE_BYTES), st_smem, kc == 0);
+              issue_s_stage(tmem_d, smem_u32(smem + kc * TILE_BYTES), st_smem, kc == 0, bn);
             else
-              issue_s_stage(tmem_d, st_smem, st_smem + TILE_BYTES, kc == 0);
+              issue_s_stage(tmem_d, st_smem, st_smem + TILE_BYTES, kc == 0, bn);
             umma_commit(smem_u32(&ring_empty[stage]));
             if (kc == P.kchunks[p] - 1) umma_commit(smem_u32(&s_full[slot]));
           }
@@ -255,14 +261,14 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     if constexpr (MODE == MODE_RAW) {
       int it = 0;
       for (int t = t0; t < t1; ++t, ++it) {
-        const int slot = it % F_SLOTS;
-        const uint32_t use = static_cast<uint32_t>(it / F_SLOTS);
+        const int slot = it % nslots;
+        const uint32_t use = static_cast<uint32_t>(it / nslots);
         mbar_wait(smem_u32(&s_full[slot]), use & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          const int jrel0 = t * BN + half * 64 + c * 32;
-          tmem_ld32(lane_addr + slot * BN + half * 64 + c * 32, v);
+        for (int c = 0; c < bn / 64; ++c) {
+          const int jrel0 = t * bn + half * (bn / 2) + c * 32;
+          tmem_ld32(lane_addr + slot * bn + half * (bn / 2) + c * 32, v);
           if (li < P.b) {
 #pragma unroll
             for (int e = 0; e < 32; ++e)
@@ -278,15 +284,15 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       bool have_dg = false;
       int it = 0;
       for (int t = t0; t < t1; ++t, ++it) {
-        const int slot = it % F_SLOTS;
-        const uint32_t use = static_cast<uint32_t>(it / F_SLOTS);
+        const int slot = it % nslots;
+        const uint32_t use = static_cast<uint32_t>(it / nslots);
         mbar_wait(smem_u32(&s_full[slot]), use & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          const int jrel0 = t * BN + half * 64 + c * 32;
+        for (int c = 0; c < bn / 64; ++c) {
+          const int jrel0 = t * bn + half * (bn / 2) + c * 32;
           const int gj0 = P.col0 + jrel0;
-          tmem_ld32(lane_addr + slot * BN + half * 64 + c * 32, v);
+          tmem_ld32(lane_addr + slot * bn + half * (bn / 2) + c * 32, v);
           if (gi >= gj0 && gi < gj0 + 32) {
 #pragma unroll
             for (int e = 0; e < 32; ++e)

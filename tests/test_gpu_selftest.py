@@ -11,7 +11,8 @@ def _lib():
     return _cabi, _cabi.lib()
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 512), (200, 300, 72), (128, 1000, 768)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 512), (200, 300, 72), (128, 1000, 768), (256, 256, 64),
+                                   (512, 1100, 256)])
 def test_selftest_gemm_matches_torch(M, N, K):
     cabi, lib = _lib()
     torch.manual_seed(0)
