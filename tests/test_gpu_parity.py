@@ -128,3 +128,14 @@ def test_matches_golden_fixture_directly(pkg):
         print(f"[parity] golden {key}: linf={linf:.2e} l2={l2:.2e}")
         assert linf < GRAD_RTOL and l2 < GRAD_RTOL, (key, linf, l2)
     assert float(gs) == pytest.approx(float(z["f64_r0_d_logit_scale"]), rel=GRAD_RTOL, abs=1e-7)
+
+
+def test_config2_b4096_mlp_head(pkg, oracle):
+    """BASELINE config 2: global batch 4096, D=512, DINOv2-B dim 768, MLP head (fp64 oracle, ~2 GB host RAM)."""
+    check_against_oracle(pkg, oracle, 4096, 512, 768, 14.2857, make_args(use_projection=True), seed=2)
+
+
+def test_config4_dims_vitl(pkg, oracle):
+    """BASELINE config 4 feature dims (ViT-L/14: D=768, DINOv2-L: 1024, four 256-feature chunks with the head)."""
+    check_against_oracle(pkg, oracle, 640, 768, 1024, 50.0, make_args(use_projection=False), seed=4)
+    check_against_oracle(pkg, oracle, 384, 768, 1024, 50.0, make_args(use_projection=True), seed=4)
