@@ -292,15 +292,17 @@ static int make_map(CUtensorMap* map, const void* base, int rows, int cols, size
   return 0;
 }
 
-static int make_maps(const dsoft_plan* p, const void* gathered, TileMaps* tm) {
+// box_rows: 128 = one TMA box per operand tile; 64 = half tiles (CTA pairs stage half a column tile each)
+static int make_maps(const dsoft_plan* p, const void* gathered, TileMaps* tm, int box_rows = BM) {
   const __nv_bfloat16* g = static_cast<const __nv_bfloat16*>(gathered);
   if (reinterpret_cast<uintptr_t>(g) % 16) return fail(DSOFT_EINVAL, "gathered buffer must be 16-byte aligned");
+  const CUtensorMapDataType bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   int rc;
-  if ((rc = make_map(&tm->m[0], g + p->offI, p->B, p->sh.D, p->row_elems))) return rc;
-  if ((rc = make_map(&tm->m[1], g + p->offT, p->B, p->sh.D, p->row_elems))) return rc;
-  if ((rc = make_map(&tm->m[2], g + p->offZ, p->B, p->Dz, p->row_elems))) return rc;
+  if ((rc = make_map(&tm->m[0], g + p->offI, p->B, p->sh.D, p->row_elems, bf, box_rows))) return rc;
+  if ((rc = make_map(&tm->m[1], g + p->offT, p->B, p->sh.D, p->row_elems, bf, box_rows))) return rc;
+  if ((rc = make_map(&tm->m[2], g + p->offZ, p->B, p->Dz, p->row_elems, bf, box_rows))) return rc;
   if (p->have_soft) {
-    if ((rc = make_map(&tm->m[3], g + p->offD, p->B, p->sh.Dd, p->row_elems))) return rc;
+    if ((rc = make_map(&tm->m[3], g + p->offD, p->B, p->sh.Dd, p->row_elems, bf, box_rows))) return rc;
   } else {
     tm->m[3] = tm->m[0];
   }
@@ -698,6 +700,25 @@ extern "C" int dsoft_profile_read(double* ms_sum, int* counts, int n) {
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
+// Forward tile kernels run as CTA pairs (cluster of 2 consecutive row blocks, cta_group::2 MMAs).
+template <typename K>
+static int launch_fwd_pair(K kernel, int rbs, int nsplit, cudaStream_t st, const TileMaps& tm, const FwdParams& P) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((rbs + 1) / 2 * 2, nsplit, 1);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = FWD_SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, tm, P));
+  return 0;
+}
+
 // Backward tile kernel: the feature chunks of one (row block, column split) form a cluster along grid.x.
 // More than X_MAXC chunks are split into several launches (each recomputes the S tiles once).
 template <typename K>
@@ -809,7 +830,7 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
   const int b = p->sh.b;
   const int rbs = ceil_div(b, BM);
   TileMaps tm;
-  int rc = make_maps(p, gathered, &tm);
+  int rc = make_maps(p, gathered, &tm, 64);  // 64-row boxes: each CTA of a pair stages half a column tile
   if (rc) return rc;
 
   prep_scalars_kernel<<<1, 32, 0, st>>>(logit_scale, p->have_soft ? p->sh.teacher_temp : 0.f,
@@ -830,21 +851,21 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
     CUDA_TRY(cudaGetLastError());
   }
 
-  if ((rc = set_smem(dsoft_fwd_kernel<MODE_CLIP>, FWD_SMEM_BYTES))) return rc;
-  if ((rc = set_smem(dsoft_fwd_kernel<MODE_SOFT>, FWD_SMEM_BYTES))) return rc;
+  if ((rc = set_smem(dsoft_fwd_kernel<MODE_CLIP, 2>, FWD_SMEM_BYTES))) return rc;
+  if ((rc = set_smem(dsoft_fwd_kernel<MODE_SOFT, 2>, FWD_SMEM_BYTES))) return rc;
 
   FwdParams P;
   // image -> text (loss.py:266/272) and text -> image (loss.py:267/273)
   fill_clip_fwd(p, P, 0, 1, S + p->st_scal, X + p->sc_pc_it, S + p->st_diag);
   {
     ProfScope ps(PK_FWD_CLIP_IT, st);
-    dsoft_fwd_kernel<MODE_CLIP><<<dim3(rbs, p->f_clip.nsplit), NUM_THREADS, FWD_SMEM_BYTES, st>>>(tm, P);
+    if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_CLIP, 2>, rbs, p->f_clip.nsplit, st, tm, P))) return rc;
   }
   CUDA_TRY(cudaGetLastError());
   fill_clip_fwd(p, P, 1, 0, S + p->st_scal, X + p->sc_pc_ti, S + p->st_diag);
   {
     ProfScope ps(PK_FWD_CLIP_TI, st);
-    dsoft_fwd_kernel<MODE_CLIP><<<dim3(rbs, p->f_clip.nsplit), NUM_THREADS, FWD_SMEM_BYTES, st>>>(tm, P);
+    if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_CLIP, 2>, rbs, p->f_clip.nsplit, st, tm, P))) return rc;
   }
   CUDA_TRY(cudaGetLastError());
 
@@ -872,7 +893,7 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
     P.part = X + p->sc_ps;
     {
       ProfScope ps(PK_FWD_SOFT, st);
-      dsoft_fwd_kernel<MODE_SOFT><<<dim3(rbs, p->f_soft.nsplit), NUM_THREADS, FWD_SMEM_BYTES, st>>>(tm, P);
+      if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_SOFT, 2>, rbs, p->f_soft.nsplit, st, tm, P))) return rc;
     }
     CUDA_TRY(cudaGetLastError());
   }
@@ -1081,11 +1102,11 @@ extern "C" int dsoft_selftest_gemm(const void* a, const void* bmat, float* c, in
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TileMaps tm;
-  if ((rc = make_map(&tm.m[0], a, M, K, K))) return rc;
-  if ((rc = make_map(&tm.m[1], bmat, N, K, K))) return rc;
+  if ((rc = make_map(&tm.m[0], a, M, K, K, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 64))) return rc;
+  if ((rc = make_map(&tm.m[1], bmat, N, K, K, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 64))) return rc;
   tm.m[2] = tm.m[0];
   tm.m[3] = tm.m[1];
-  if ((rc = set_smem(dsoft_fwd_kernel<MODE_RAW>, FWD_SMEM_BYTES))) return rc;
+  if ((rc = set_smem(dsoft_fwd_kernel<MODE_RAW, 2>, FWD_SMEM_BYTES))) return rc;
   FwdParams P;
   memset(&P, 0, sizeof(P));
   P.nprod = 1;
@@ -1105,9 +1126,9 @@ extern "C" int dsoft_selftest_gemm(const void* a, const void* bmat, float* c, in
   P.tiles_per_split = ceil_div(P.ntiles, nsplit);
   P.npart = 0;
   P.part = c;
-  dsoft_fwd_kernel<MODE_RAW>
-      <<<dim3(ceil_div(M, BM), ceil_div(P.ntiles, P.tiles_per_split)), NUM_THREADS, FWD_SMEM_BYTES, st>>>(tm, P);
-  CUDA_TRY(cudaGetLastError());
+  if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_RAW, 2>, ceil_div(M, BM), ceil_div(P.ntiles, P.tiles_per_split), st,
+                            tm, P)))
+    return rc;
   return 0;
 }
 

@@ -133,24 +133,30 @@ __device__ __forceinline__ void issue_s_stage(uint32_t tmem_d, uint32_t a_smem, 
 //  MODE_CLIP partials (2): running max m (log2 units), sum 2^(x-m)        [+ diag dot product]
 //  MODE_SOFT partials (7): teacher m, Zt, Aq=sum w*q, Ap=sum w*p, Ar=sum w*r, student Zs, text Ztt
 //  (w = 2^(q-m); student/text use the fixed maximum log2(e)/tau, reached on the diagonal.)
-template <int MODE>
+// CG = 2: the kernel runs as clusters of two CTAs (consecutive row blocks) that drive cta_group::2 MMAs
+// (M = 256): each CTA loads its own 128 rows of the row-side operand and HALF of the column-side tile, the
+// leader issues one MMA for both.  Shared-memory operand reads per MMA drop from 8 KiB to 6 KiB (N = 128)
+// or 4 KiB per 64 cycles-equivalent (N = 256), which is what bounds the M=128 x N=128 form at ~40 %.
+template <int MODE, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ FwdParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_1024(smem_raw);
-  // streaming mode: F_STAGES stages of (A box | B box); resident mode: 8 A boxes, then 6 B-box stages
+  // streaming mode: stages of (A box | B boxes); resident mode: 8 A boxes, then B-only stages
   const bool resident = P.resident != 0;
   const int bn = P.bn;
-  const int nbox = bn / BN;  // 128-row boxes of the column operand per stage
-  const int stage_bytes = (resident ? 0 : TILE_BYTES) + nbox * TILE_BYTES;
+  const int brows = bn / CG;                 // column-operand rows this CTA stages per tile
+  const int boxr = (CG == 2) ? 64 : BM;      // rows per TMA box (maps are built accordingly)
+  const int box_bytes = boxr * 128;
+  const int stage_bytes = (resident ? 0 : TILE_BYTES) + brows * 128;
   const int nstages = min(8, (resident ? 6 : 14) * TILE_BYTES / stage_bytes);
   const int nslots = TMEM_COLS / bn;  // 4 x 128 or 2 x 256 columns
   uint8_t* ring = resident ? smem + 8 * TILE_BYTES : smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F_STAGES * 2 * TILE_BYTES + 2 * TILE_BYTES);
-  uint64_t* ring_full = bars;        // [8]
+  uint64_t* ring_full = bars;        // [8]  (CG = 2: the leader's copy collects both CTAs' bytes)
   uint64_t* ring_empty = bars + 8;   // [8]
   uint64_t* s_full = bars + 16;
-  uint64_t* s_empty = s_full + F_SLOTS;
+  uint64_t* s_empty = s_full + F_SLOTS;  // (CG = 2: the leader's copy collects both CTAs' epilogues)
   uint64_t* a_full = s_empty + F_SLOTS;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_full + 1);
 
@@ -160,6 +166,8 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   const int split = blockIdx.y;
   const int t0 = split * P.tiles_per_split;
   const int t1 = min(t0 + P.tiles_per_split, P.ntiles);
+  const int prank = (CG == 2) ? (rb & 1) : 0;  // rank in the pair (== cluster rank)
+  const bool leader = prank == 0;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) tma_prefetch_desc(&maps.m[i]);
@@ -169,14 +177,14 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     }
     for (int i = 0; i < F_SLOTS; ++i) {
       mbar_init(smem_u32(&s_full[i]), 1);
-      mbar_init(smem_u32(&s_empty[i]), NUM_EPI_THREADS);
+      mbar_init(smem_u32(&s_empty[i]), CG * NUM_EPI_THREADS);
     }
     mbar_init(smem_u32(a_full), 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(tmem_holder), TMEM_COLS);
+  if (warp == 2) tmem_alloc_cg<CG>(smem_u32(tmem_holder), TMEM_COLS);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
@@ -184,11 +192,17 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     // ------------------------------------------------------------------ TMA producer (warp-uniform loop)
     int stage = 0;
     uint32_t phase = 0;
+    auto load = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar_local, int c0, int c1) {
+      if constexpr (CG == 2) tma_load_2d_2sm(dst, m, mapa_shared(bar_local, 0), c0, c1);
+      else tma_load_2d(dst, m, bar_local, c0, c1);
+    };
     if (resident && elect_one()) {
       const uint32_t af = smem_u32(a_full);
-      mbar_arrive_expect_tx(af, P.kchunks[0] * TILE_BYTES);
+      if (leader) mbar_arrive_expect_tx(af, CG * P.kchunks[0] * TILE_BYTES);
       for (int kc = 0; kc < P.kchunks[0]; ++kc)
-        tma_load_2d(smem_u32(smem + kc * TILE_BYTES), &maps.m[P.a_map[0]], af, kc * BK, P.row0 + rb * BM);
+        for (int i = 0; i < BM / boxr; ++i)
+          load(smem_u32(smem + kc * TILE_BYTES + i * box_bytes), &maps.m[P.a_map[0]], af, kc * BK,
+               P.row0 + rb * BM + i * boxr);
     }
     __syncwarp();
     for (int t = t0; t < t1; ++t) {
@@ -200,14 +214,15 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
           if (elect_one()) {
             const uint32_t full = smem_u32(&ring_full[stage]);
             const uint32_t dst = smem_u32(ring + stage * stage_bytes);
-            mbar_arrive_expect_tx(full, stage_bytes);
+            if (leader) mbar_arrive_expect_tx(full, CG * stage_bytes);  // both CTAs' boxes land on this barrier
             uint32_t bdst = dst;
             if (!resident) {
-              tma_load_2d(dst, am, full, kc * BK, P.row0 + rb * BM);
+              for (int i = 0; i < BM / boxr; ++i)
+                load(dst + i * box_bytes, am, full, kc * BK, P.row0 + rb * BM + i * boxr);
               bdst += TILE_BYTES;
             }
-            for (int i = 0; i < nbox; ++i)
-              tma_load_2d(bdst + i * TILE_BYTES, bm, full, kc * BK, P.col0 + t * bn + i * BN);
+            for (int i = 0; i < brows / boxr; ++i)
+              load(bdst + i * box_bytes, bm, full, kc * BK, P.col0 + t * bn + prank * brows + i * boxr);
           }
           __syncwarp();
           if (++stage == nstages) { stage = 0; phase ^= 1; }
@@ -215,35 +230,41 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop)
-    int stage = 0;
-    uint32_t phase = 0;
-    int it = 0;
-    if (resident) {
-      mbar_wait(smem_u32(a_full), 0);
-      tc_fence_after();
-    }
-    for (int t = t0; t < t1; ++t) {
-      for (int p = 0; p < P.nprod; ++p, ++it) {
-        const int slot = it % nslots;
-        const uint32_t use = static_cast<uint32_t>(it / nslots);
-        mbar_wait(smem_u32(&s_empty[slot]), (use & 1) ^ 1);
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      const uint32_t idesc = make_idesc_bf16(BM * CG, bn, 0, 0);
+      if (resident) {
+        mbar_wait(smem_u32(a_full), 0);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + slot * bn;
-        for (int kc = 0; kc < P.kchunks[p]; ++kc) {
-          mbar_wait(smem_u32(&ring_full[stage]), phase);
+      }
+      for (int t = t0; t < t1; ++t) {
+        for (int p = 0; p < P.nprod; ++p, ++it) {
+          const int slot = it % nslots;
+          const uint32_t use = static_cast<uint32_t>(it / nslots);
+          mbar_wait(smem_u32(&s_empty[slot]), (use & 1) ^ 1);
           tc_fence_after();
-          if (elect_one()) {
-            const uint32_t st_smem = smem_u32(ring + stage * stage_bytes);
-            if (resident)
-              issue_s_stage(tmem_d, smem_u32(smem + kc * TILE_BYTES), st_smem, kc == 0, bn);
-            else
-              issue_s_stage(tmem_d, st_smem, st_smem + TILE_BYTES, kc == 0, bn);
-            umma_commit(smem_u32(&ring_empty[stage]));
-            if (kc == P.kchunks[p] - 1) umma_commit(smem_u32(&s_full[slot]));
+          const uint32_t tmem_d = tmem_base + slot * bn;
+          for (int kc = 0; kc < P.kchunks[p]; ++kc) {
+            mbar_wait(smem_u32(&ring_full[stage]), phase);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t st_smem = smem_u32(ring + stage * stage_bytes);
+              const uint32_t a_smem = resident ? smem_u32(smem + kc * TILE_BYTES) : st_smem;
+              const uint32_t b_smem = resident ? st_smem : st_smem + TILE_BYTES;
+              const uint64_t ad = make_smem_desc(a_smem, 16, 1024);
+              const uint64_t bd = make_smem_desc(b_smem, 16, 1024);
+#pragma unroll
+              for (int kk = 0; kk < BK / 16; ++kk)
+                umma_cg<CG>(tmem_d, ad + 2 * kk, bd + 2 * kk, idesc, (kc == 0 && kk == 0) ? 0u : 1u);
+              umma_commit_cg<CG>(smem_u32(&ring_empty[stage]));
+              if (kc == P.kchunks[p] - 1) umma_commit_cg<CG>(smem_u32(&s_full[slot]));
+            }
+            __syncwarp();
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
-          __syncwarp();
-          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -257,6 +278,10 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int sp = split * 2 + half;
     float v[32];
+    auto release_slot = [&](int slot) {  // the MMA issuer lives in the pair's leader
+      if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&s_empty[slot]), 0));
+      else mbar_arrive(smem_u32(&s_empty[slot]));
+    };
 
     if constexpr (MODE == MODE_RAW) {
       int it = 0;
@@ -276,7 +301,7 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
           }
         }
         tc_fence_before();
-        mbar_arrive(smem_u32(&s_empty[slot]));
+        release_slot(slot);
       }
     } else if constexpr (MODE == MODE_CLIP) {
       const float s2 = P.scal[SC_SCALE_L2];
@@ -318,7 +343,7 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
           m = mnew;
         }
         tc_fence_before();
-        mbar_arrive(smem_u32(&s_empty[slot]));
+        release_slot(slot);
       }
       if (li < P.b) {
         P.part[(0 * P.npart + sp) * P.b + li] = m;
@@ -429,7 +454,7 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
           }
         }
         tc_fence_before();
-        for (int p = 0; p < P.nprod; ++p) mbar_arrive(smem_u32(&s_empty[(it + p) % F_SLOTS]));
+        for (int p = 0; p < P.nprod; ++p) release_slot((it + p) % F_SLOTS);
       }
       if (li < P.b) {
         const int o = sp * P.b + li;
@@ -446,8 +471,8 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_dealloc_cg<CG>(tmem_base, TMEM_COLS);
 }
 
 // ================================================================================================

@@ -236,6 +236,77 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) 
       : "memory");
 }
 
+// ----------------------------------------------------------------------------------------------
+// cta_group::2 variants: a pair of CTAs (cluster ranks 2k, 2k+1) drives one M=256 MMA.  Each CTA holds its
+// own 128 rows of A and half of the N rows of B at the SAME shared-memory offsets; the leader (even rank)
+// issues; accumulator rows 0..127 land in the leader's TMEM, 128..255 in the peer's, same TMEM address.
+// Every tcgen05 instruction of a kernel must use one cta_group, hence the compile-time parameter.
+// ----------------------------------------------------------------------------------------------
+template <int CG>
+__device__ __forceinline__ void tmem_alloc_cg(uint32_t smem_holder, uint32_t ncols) {
+  if constexpr (CG == 1) {
+    tmem_alloc(smem_holder, ncols);
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_holder),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc_cg(uint32_t taddr, uint32_t ncols) {
+  if constexpr (CG == 1) {
+    tmem_dealloc(taddr, ncols);
+  } else {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void umma_cg(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  if constexpr (CG == 1) {
+    umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// commit: CG == 2 arrives on the barrier at this offset in BOTH CTAs of the pair (`pair_mask` = 0b11 << 2k)
+template <int CG>
+__device__ __forceinline__ void umma_commit_cg(uint32_t bar, uint16_t pair_mask = 3) {
+  if constexpr (CG == 1) {
+    umma_commit(bar);
+  } else {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            bar),
+        "h"(pair_mask)
+        : "memory");
+  }
+}
+// TMA load issued by either CTA of a pair; completion bytes are credited to `bar_cluster`, a shared::cluster
+// address (mapa_shared) of the mbarrier in the pair's leader.
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar_cluster,
+                                                int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+// arrive on an mbarrier of another CTA of the cluster (address from mapa_shared)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (one row per thread).
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
