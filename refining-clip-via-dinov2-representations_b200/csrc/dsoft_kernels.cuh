@@ -358,48 +358,48 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       const float cr = has_text ? P.rinv[2][gi] * P.scal[SC_ITX_L2] : 0.f;
       const float mx2 = P.scal[SC_ITX_L2];
       float m = M_FLOOR, zt = 0.f, aq = 0.f, ap = 0.f, ar = 0.f, zs = 0.f, zx = 0.f;
-      float w[32];
+      float w[64];  // teacher weights 2^(q - m) of this thread's 64 columns, kept across the three products
       int it = 0;
       for (int t = t0; t < t1; ++t, it += P.nprod) {
-        for (int p = 0; p < P.nprod; ++p) {
-          const int slot = (it + p) % F_SLOTS;
-          const uint32_t use = static_cast<uint32_t>((it + p) / F_SLOTS);
-          mbar_wait(smem_u32(&s_full[slot]), use & 1);
-        }
-        tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          const int jrel0 = t * BN + half * 64 + c * 32;
-          const int gj0 = P.col0 + jrel0;
-          const bool ragged = jrel0 + 32 > P.ncols;
-          const uint32_t coff = half * 64 + c * 32;
-          // ---- teacher: running max, w = 2^(q - m)
-          tmem_ld32(lane_addr + ((it + 0) % F_SLOTS) * BN + coff, v);
-          {
+        const int jt0 = t * BN + half * 64;  // first column (relative to col0) of this thread's 64 columns
+        const bool ragged = jt0 + 64 > P.ncols;
+        // ---- teacher: q (log2 units) for all 64 columns, then ONE running-max update for the tile; the
+        // TMEM slot goes back to the MMA issuer as soon as the values are in registers
+        {
+          const int slot = (it + 0) % F_SLOTS;
+          mbar_wait(smem_u32(&s_full[slot]), static_cast<uint32_t>((it + 0) / F_SLOTS) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int gj0 = P.col0 + jt0 + c * 32;
+            tmem_ld32(lane_addr + slot * BN + half * 64 + c * 32, v);
             const float4* rc = reinterpret_cast<const float4*>(P.rinv[0] + gj0);
 #pragma unroll
             for (int e4 = 0; e4 < 8; ++e4) {
               const float4 r = __ldg(rc + e4);
-              w[4 * e4 + 0] = v[4 * e4 + 0] * cq * r.x;
-              w[4 * e4 + 1] = v[4 * e4 + 1] * cq * r.y;
-              w[4 * e4 + 2] = v[4 * e4 + 2] * cq * r.z;
-              w[4 * e4 + 3] = v[4 * e4 + 3] * cq * r.w;
+              w[c * 32 + 4 * e4 + 0] = v[4 * e4 + 0] * cq * r.x;
+              w[c * 32 + 4 * e4 + 1] = v[4 * e4 + 1] * cq * r.y;
+              w[c * 32 + 4 * e4 + 2] = v[4 * e4 + 2] * cq * r.z;
+              w[c * 32 + 4 * e4 + 3] = v[4 * e4 + 3] * cq * r.w;
             }
           }
-          if (ragged || (gi >= gj0 && gi < gj0 + 32)) {
+          tc_fence_before();
+          release_slot(slot);
+          const int gj0 = P.col0 + jt0;
+          if (ragged || (gi >= gj0 && gi < gj0 + 64)) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (jrel0 + e >= P.ncols || gj0 + e == gi) w[e] = NEG_BIG;  // teacher diag masked: loss.py:376-377
+            for (int e = 0; e < 64; ++e)
+              if (jt0 + e >= P.ncols || gj0 + e == gi) w[e] = NEG_BIG;  // teacher diag masked: loss.py:376-377
           }
           float cm[4] = {w[0], w[1], w[2], w[3]};
 #pragma unroll
-          for (int e = 4; e < 32; ++e) cm[e & 3] = fmaxf(cm[e & 3], w[e]);
+          for (int e = 4; e < 64; ++e) cm[e & 3] = fmaxf(cm[e & 3], w[e]);
           const float mnew = fmaxf(m, fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])));
           const float alpha = fast_exp2(m - mnew);
           m = mnew;
           float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
+          for (int e = 0; e < 64; ++e) {
             const float q2 = w[e];
             const float we = fast_exp2(q2 - mnew);
             a0[e & 3] += we;
@@ -410,51 +410,43 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
           aq = aq * alpha + ((a1[0] + a1[1]) + (a1[2] + a1[3]));
           ap *= alpha;
           ar *= alpha;
-          // ---- student: sum w*p and fixed-max exp sum
-          tmem_ld32(lane_addr + ((it + 1) % F_SLOTS) * BN + coff, v);
-          {
-            const float4* rc = reinterpret_cast<const float4*>(P.rinv[1] + gj0);
-            float b0[4] = {0.f, 0.f, 0.f, 0.f}, b1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int e4 = 0; e4 < 8; ++e4) {
-              const float4 r = __ldg(rc + e4);
-              const float rr[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int e = 4 * e4 + k;
-                float p2 = v[e] * cp * rr[k];
-                if (ragged && jrel0 + e >= P.ncols) p2 = NEG_BIG;
-                b0[k] += fast_exp2(p2 - ms2);
-                b1[k] = fmaf(w[e], p2, b1[k]);
-              }
-            }
-            zs += (b0[0] + b0[1]) + (b0[2] + b0[3]);
-            ap += (b1[0] + b1[1]) + (b1[2] + b1[3]);
-          }
-          // ---- text (loss.py:387-397): same teacher weights
-          if (has_text) {
-            tmem_ld32(lane_addr + ((it + 2) % F_SLOTS) * BN + coff, v);
-            const float4* rc = reinterpret_cast<const float4*>(P.rinv[2] + gj0);
-            float b0[4] = {0.f, 0.f, 0.f, 0.f}, b1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int e4 = 0; e4 < 8; ++e4) {
-              const float4 r = __ldg(rc + e4);
-              const float rr[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int e = 4 * e4 + k;
-                float r2 = v[e] * cr * rr[k];
-                if (ragged && jrel0 + e >= P.ncols) r2 = NEG_BIG;
-                b0[k] += fast_exp2(r2 - mx2);
-                b1[k] = fmaf(w[e], r2, b1[k]);
-              }
-            }
-            zx += (b0[0] + b0[1]) + (b0[2] + b0[3]);
-            ar += (b1[0] + b1[1]) + (b1[2] + b1[3]);
-          }
         }
-        tc_fence_before();
-        for (int p = 0; p < P.nprod; ++p) release_slot((it + p) % F_SLOTS);
+        // ---- student (p = 1) and text (p = 2, loss.py:387-397): sum w*p and the fixed-max exp sum
+        for (int p = 1; p < P.nprod; ++p) {
+          const int slot = (it + p) % F_SLOTS;
+          mbar_wait(smem_u32(&s_full[slot]), static_cast<uint32_t>((it + p) / F_SLOTS) & 1);
+          tc_fence_after();
+          const float cs = (p == 1) ? cp : cr;
+          const float mfix = (p == 1) ? ms2 : mx2;
+          const float* rv = P.rinv[p];
+          float b0[4] = {0.f, 0.f, 0.f, 0.f}, b1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int jrel0 = jt0 + c * 32;
+            tmem_ld32(lane_addr + slot * BN + half * 64 + c * 32, v);
+            if (c == 1) {
+              tc_fence_before();
+              release_slot(slot);
+            }
+            const float4* rc = reinterpret_cast<const float4*>(rv + P.col0 + jrel0);
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const float4 r = __ldg(rc + e4);
+              const float rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int e = 4 * e4 + k;
+                float p2 = v[e] * cs * rr[k];
+                if (ragged && jrel0 + e >= P.ncols) p2 = NEG_BIG;
+                b0[k] += fast_exp2(p2 - mfix);
+                b1[k] = fmaf(w[c * 32 + e], p2, b1[k]);
+              }
+            }
+          }
+          const float zsum = (b0[0] + b0[1]) + (b0[2] + b0[3]);
+          const float asum = (b1[0] + b1[1]) + (b1[2] + b1[3]);
+          if (p == 1) { zs += zsum; ap += asum; } else { zx += zsum; ar += asum; }
+        }
       }
       if (li < P.b) {
         const int o = sp * P.b + li;
