@@ -275,19 +275,42 @@ def run_ours(args):
     h2d_bytes = (h_img.numel() + h_txt.numel() + h_dino.numel()) * 4
     host_out = torch.empty(3, dtype=torch.float32).pin_memory()
 
+    # double-buffered device staging: the H2D copy of step n+1 is issued on a side stream before step n runs
+    # (what train.py's `.to(device, non_blocking=True)` from the pinned DINO table achieves, train.py:280),
+    # so every step still pays its own 235 MB of host->device traffic inside the timed region
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage_bufs = [[torch.empty_like(t, device=dev) for t in (h_img, h_txt, h_dino)] for _ in range(2)]
+    stage_evt = [torch.cuda.Event() for _ in range(2)]
+
+    def issue_h2d(slot):
+        with torch.cuda.stream(copy_stream):
+            for d, h in zip(stage_bufs[slot], (h_img, h_txt, h_dino)):
+                d.copy_(h, non_blocking=True)
+            stage_evt[slot].record(copy_stream)
+
+    e2e_count = [0]
+
     def e2e_step():
+        n = e2e_count[0]
+        e2e_count[0] += 1
+        issue_h2d((n + 1) % 2)  # prefetch the next step's inputs
+        torch.cuda.current_stream().wait_event(stage_evt[n % 2])
         zero_grads()
-        im = h_img.to(dev, non_blocking=True).requires_grad_(True)
-        tx = h_txt.to(dev, non_blocking=True).requires_grad_(True)
-        dn = h_dino.to(dev, non_blocking=True)
+        im = stage_bufs[n % 2][0].requires_grad_(True)
+        tx = stage_bufs[n % 2][1].requires_grad_(True)
+        dn = stage_bufs[n % 2][2]
         o = step(im, tx, dn)
         host_out.copy_(torch.stack([o["total_loss"].detach(), o["classic_loss"].detach(), o["soft_loss"].detach()]),
                        non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the training loop reads the loss every step (train.py:354)
+        im.requires_grad_(False)
+        tx.requires_grad_(False)
+        im.grad = tx.grad = None
         return float(host_out[0])
 
     ms_e2e = float("nan")
     if not args.no_e2e:
+        issue_h2d(0)
         for _ in range(2):
             e2e_step()
         barrier()
