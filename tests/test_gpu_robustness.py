@@ -1,0 +1,107 @@
+"""Behaviour a training loop relies on beyond raw parity: dtypes, eval mode, CUDA-graph capture, repeat calls."""
+import pytest
+import torch
+
+from gpu_util import make_args, oracle_cfg, rel_err, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(B=256, D=128, Dd=192, seed=1):
+    img, txt, dino = synth(seed, B, D, Dd)
+    return img.cuda(), txt.cuda(), dino.cuda()
+
+
+def test_bf16_and_fp16_inputs_match_fp32_inputs(pkg):
+    """Inputs are bf16-representable, so feeding them as bf16 / fp32 must give identical results."""
+    img, txt, dino = _inputs()
+    args = make_args()
+    outs = []
+    for dt in (torch.float32, torch.bfloat16):
+        loss = pkg.ClipLossWithDINOEnhancements()
+        im = img.detach().clone().to(dt).requires_grad_(True)
+        tx = txt.detach().clone().to(dt).requires_grad_(True)
+        sc = torch.tensor(20.0, device="cuda", requires_grad=True)
+        o = loss(im, tx, sc, dino, args, output_dict=True)
+        o["total_loss"].backward()
+        assert im.grad.dtype == dt and tx.grad.dtype == dt
+        outs.append((float(o["classic_loss"]), im.grad.float(), float(sc.grad)))
+    # tau_t is rounded through the student dtype like the reference (loss.py:369): only the CLIP part is identical
+    assert outs[0][0] == outs[1][0]
+    linf, _ = rel_err(outs[1][1], outs[0][1])
+    assert linf < 2e-2  # bf16 gradient storage + bf16(0.15) teacher temperature
+
+
+def test_no_grad_eval_and_missing_dino(pkg):
+    img, txt, dino = _inputs()
+    loss = pkg.ClipLossWithDINOEnhancements()
+    with torch.no_grad():
+        o = loss(img, txt, torch.tensor(14.0, device="cuda"), dino, make_args(), output_dict=True)
+    assert not o["total_loss"].requires_grad and torch.isfinite(o["total_loss"])
+    # no DINO features for this batch (train.py zeroes lambda_soft, make_effective_args): classic only
+    o2 = loss(img, txt, torch.tensor(14.0, device="cuda"), None, make_args(lambda_soft=0.0), output_dict=True)
+    assert float(o2["soft_loss"]) == 0.0 and float(o2["total_loss"]) == float(o2["classic_loss"])
+    assert float(o2["classic_loss"]) == pytest.approx(float(o["classic_loss"]), rel=1e-6)
+
+
+def test_non_contiguous_and_repeated_calls(pkg):
+    img, txt, dino = _inputs()
+    wide = torch.zeros(img.shape[0], img.shape[1] * 2, device="cuda")
+    wide[:, ::2] = img
+    loss = pkg.ClipLossWithDINOEnhancements()
+    args = make_args()
+    a = loss(img, txt, torch.tensor(20.0, device="cuda"), dino, args, output_dict=True)["total_loss"]
+    b = loss(wide[:, ::2], txt, torch.tensor(20.0, device="cuda"), dino, args, output_dict=True)["total_loss"]
+    assert float(a) == float(b)
+    # two forwards before two backwards (e.g. gradient accumulation of two micro-batches): per-call buffers
+    i1 = img.clone().requires_grad_(True)
+    i2 = img.flip(0).clone().requires_grad_(True)
+    l1 = loss(i1, txt, torch.tensor(20.0, device="cuda"), dino, args, output_dict=True)["total_loss"]
+    l2 = loss(i2, txt.flip(0), torch.tensor(20.0, device="cuda"), dino.flip(0), args, output_dict=True)["total_loss"]
+    l1.backward()
+    l2.backward()
+    assert float(l1) == pytest.approx(float(l2), rel=1e-6)
+    linf, _ = rel_err(i2.grad.flip(0), i1.grad)
+    assert linf < 1e-4
+
+
+def test_cuda_graph_capture_and_replay(pkg):
+    """The whole loss fwd+bwd is stream-ordered with no host synchronisation, so it can be captured."""
+    img, txt, dino = _inputs(512, 128, 192, seed=4)
+    loss = pkg.ClipLossWithDINOEnhancements()
+    args = make_args(use_projection=True)
+    torch.manual_seed(0)
+    loss.init_proj(128, 192, "cuda", "mlp")
+    im = img.clone().requires_grad_(True)
+    tx = txt.clone().requires_grad_(True)
+    sc = torch.tensor(25.0, device="cuda", requires_grad=True)
+
+    def step():
+        out = loss(im, tx, sc, dino, args, output_dict=True)
+        gi, gt, gs = torch.autograd.grad(out["total_loss"], [im, tx, sc])
+        return out["total_loss"].detach(), gi, gt, gs
+
+    eager = [t.clone() for t in step()]
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            step()
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        static = step()
+    with torch.no_grad():
+        im.copy_(img.flip(0))  # new data in the captured input buffers
+        tx.copy_(txt.flip(0))
+    g.replay()
+    torch.cuda.synchronize()
+    replay_flipped = [t.clone() for t in static]
+    with torch.no_grad():
+        im.copy_(img)
+        tx.copy_(txt)
+    g.replay()
+    torch.cuda.synchronize()
+    for a, b in zip(eager, static):
+        assert torch.equal(a, b)
+    assert not torch.equal(replay_flipped[1], eager[1])
