@@ -97,21 +97,24 @@ int dsoft_pack(const dsoft_plan_t* plan, const void* image_dev, int image_dtype,
                int64_t ld_dino, void* gathered_dev, void* stream);
 
 /* Forward statistics pass.  logit_scale_dev: one fp32 (already exp'd, reference model.py:571).
+ * lambdas (HOST, 3 floats): {lambda_original, lambda_soft, text_lambda} (loss.py:387-388, 474).
  * Outputs: lse_local_dev [5][b] fp32 (log2-domain row log-sum-exps: clip i->t, clip t->i, teacher,
- * student, text) and losses_dev[3] = {classic_loss, soft_imgimg, soft_texttext} (loss.py:317-319,
- * 383, 396), each already divided by b. */
+ * student, text) and losses_dev[5] = {classic_loss, soft_imgimg, soft_texttext,
+ * soft = imgimg + text_lambda * texttext, total = lambda_original * classic + lambda_soft * soft}
+ * (loss.py:317-319, 383, 396-397, 473-477), the first three already divided by b. */
 int dsoft_forward(const dsoft_plan_t* plan, const void* gathered_dev, const float* logit_scale_dev,
-                  void* state_dev, void* scratch_dev, float* lse_local_dev, float* losses_dev,
-                  void* stream);
+                  const float* lambdas_host, void* state_dev, void* scratch_dev, float* lse_local_dev,
+                  float* losses_dev, void* stream);
 
 /* Backward pass.  lse_all_dev [world][5][b] = all ranks' lse_local (all-gathered by the caller when
- * world > 1).  gout_dev[3] = upstream gradients of the three forward outputs.  Outputs (fp32):
+ * world > 1).  gout_dev[5] = upstream gradients of the five forward outputs (the chain rule through
+ * `soft` and `total` is applied on the device with the same lambdas).  Outputs (fp32):
  * d_image [b][D], d_text [b][D], d_student [b][Dp] (ignored when Dp == 0), d_logit_scale [1].
  * Gradients follow the reference's per-rank convention (sum over ranks' losses == W x gradient of the
  * global mean loss; SURVEY.md "Gradient scaling"). */
 int dsoft_backward(const dsoft_plan_t* plan, const void* gathered_dev, const void* state_dev,
                    void* scratch_dev, const float* lse_all_dev, const float* gout_dev,
-                   float* d_image_dev, float* d_text_dev, float* d_student_dev,
+                   const float* lambdas_host, float* d_image_dev, float* d_text_dev, float* d_student_dev,
                    float* d_logit_scale_dev, void* stream);
 
 /* Optional timing of the tile kernels with CUDA events on the launching stream (bench.py roofline).

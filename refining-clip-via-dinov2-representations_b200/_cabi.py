@@ -46,8 +46,8 @@ PROTOTYPES = {
                              C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int64,
                              C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int64,
                              C.c_void_p, C.c_void_p]),
-    "dsoft_forward": (C.c_int, [C.c_void_p] * 8),
-    "dsoft_backward": (C.c_int, [C.c_void_p] * 11),
+    "dsoft_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)] + [C.c_void_p] * 5),
+    "dsoft_backward": (C.c_int, [C.c_void_p] * 6 + [C.POINTER(C.c_float)] + [C.c_void_p] * 5),
     "dsoft_selftest_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "dsoft_selftest_chain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -127,6 +127,7 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   if ((sh->flags & DSOFT_F_TEXT) && !(sh->text_temp > 0.f))
     return fail(DSOFT_EINVAL, "text_temp must be > 0");
   if (static_cast<long>(sh->b) * sh->world > (1L << 30)) return fail(DSOFT_EINVAL, "batch too large");
+  if (sh->D > 2048 || sh->Dp > 2048) return fail(DSOFT_EINVAL, "feature dims above 2048 are not supported");
 
   int sms = 0;
   int rc = query_num_sms(&sms);
@@ -245,13 +246,12 @@ extern "C" int dsoft_plan_kernel_flops(const dsoft_plan_t* p, double* algorithmi
 
 extern "C" int dsoft_plan_launches_forward(const dsoft_plan_t* p) {
   if (!p) return 0;
-  return 1 /*scalars*/ + (p->have_soft ? 3 : 1) /*norms*/ + 2 /*clip x2*/ + (p->have_soft ? 1 : 0) +
-         2 /*finalize, reduce*/;
+  return 1 /*pack*/ + 1 /*scalars*/ + 1 /*norms*/ + 2 /*clip x2*/ + (p->have_soft ? 1 : 0) + 1 /*finalize*/;
 }
 extern "C" int dsoft_plan_launches_backward(const dsoft_plan_t* p) {
   if (!p) return 0;
-  return 2 /*relayout, fp16 operands*/ + 2 /*clip x2*/ + (p->have_soft ? 1 : 0) + (p->have_text ? 1 : 0) +
-         2 /*finalize, ds reduce*/;
+  return 2 /*relayout, fp16 operands*/ + 2 * chunk_groups(p->nch_clip) + (p->have_soft ? chunk_groups(p->nch_stu) : 0) +
+         (p->have_text ? chunk_groups(p->nch_txt) : 0) + 1 /*finalize*/;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -321,34 +321,71 @@ __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 x) { return
 template <>
 __device__ __forceinline__ float to_f32<__half>(__half x) { return __half2float(x); }
 
-// src [rows][cols] (any float type, row stride ld) -> bf16 dst rows (row stride dst_ld)
-template <typename T>
-__global__ void pack_rows_kernel(const T* __restrict__ src, int64_t ld, __nv_bfloat16* __restrict__ dst,
-                                 int64_t dst_ld, int rows, int cols) {
-  const int64_t total = static_cast<int64_t>(rows) * (cols / 2);
+// All local matrices (image, text, student, dino; any float type, row stride ld) -> bf16 column slices of the
+// packed rows, in ONE launch.
+struct PackSrc {
+  const void* src;
+  int dtype;      // DSOFT_DT_*
+  int64_t ld;     // elements
+  int cols;
+  int dst_off;    // column offset in the packed row
+};
+struct PackArgs {
+  PackSrc m[4];
+  int nmat, rows;
+  int64_t dst_ld;
+  int64_t pairs_end[4];  // prefix sums of rows * cols / 2
+};
+
+__device__ __forceinline__ float2 load_pair(const void* src, int dtype, int64_t idx) {
+  if (dtype == DSOFT_DT_F32) {
+    const float2 v = *reinterpret_cast<const float2*>(static_cast<const float*>(src) + idx);
+    return v;
+  } else if (dtype == DSOFT_DT_BF16) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(static_cast<const __nv_bfloat16*>(src) + idx));
+  }
+  return __half22float2(*reinterpret_cast<const __half2*>(static_cast<const __half*>(src) + idx));
+}
+
+__global__ void pack_rows_kernel(PackArgs a, __nv_bfloat16* __restrict__ dst) {
+  const int64_t total = a.pairs_end[a.nmat - 1];
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(i / (cols / 2));
-    const int c = static_cast<int>(i % (cols / 2)) * 2;
-    const float x0 = to_f32<T>(src[r * ld + c]);
-    const float x1 = to_f32<T>(src[r * ld + c + 1]);
-    *reinterpret_cast<__nv_bfloat162*>(dst + r * dst_ld + c) = __floats2bfloat162_rn(x0, x1);
+    int k = 0;
+    while (i >= a.pairs_end[k]) ++k;
+    const int64_t j = i - (k ? a.pairs_end[k - 1] : 0);
+    const PackSrc& m = a.m[k];
+    const int half_cols = m.cols / 2;
+    const int r = static_cast<int>(j / half_cols);
+    const int c = static_cast<int>(j % half_cols) * 2;
+    const float2 x = load_pair(m.src, m.dtype, r * m.ld + c);
+    *reinterpret_cast<__nv_bfloat162*>(dst + r * a.dst_ld + m.dst_off + c) = __floats2bfloat162_rn(x.x, x.y);
   }
 }
 
-// one warp per row: out[r] = 1 / max(||row||, 1e-12)  (F.normalize eps, loss.py:345-359, 392)
-__global__ void rinv_kernel(const __nv_bfloat16* __restrict__ mat, int64_t ld, int rows, int cols,
-                            float* __restrict__ out, int out_len, float* __restrict__ rmin) {
+// one warp per row: out[r] = 1 / max(||row||, 1e-12)  (F.normalize eps, loss.py:345-359, 392); grid.y selects
+// the matrix (text / student / dino); the per-matrix minimum feeds the power-of-two operand scale sigma
+struct RinvArgs {
+  const __nv_bfloat16* mat[3];
+  int cols[3];
+  float* out[3];
+  float* rmin[3];
+  int64_t ld;
+  int rows, out_len;
+};
+__global__ void rinv_kernel(RinvArgs a) {
+  const int k = blockIdx.y;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (r >= out_len) return;
-  if (r >= rows) {
+  if (r >= a.out_len) return;
+  float* out = a.out[k];
+  if (r >= a.rows) {
     if (lane == 0) out[r] = 0.f;
     return;
   }
-  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(mat + r * ld);
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(a.mat[k] + r * a.ld);
   float acc = 0.f;
-  for (int c = lane; c < cols / 2; c += 32) {
+  for (int c = lane; c < a.cols[k] / 2; c += 32) {
     const float2 f = __bfloat1622float2(p[c]);
     acc = fmaf(f.x, f.x, acc);
     acc = fmaf(f.y, f.y, acc);
@@ -358,7 +395,7 @@ __global__ void rinv_kernel(const __nv_bfloat16* __restrict__ mat, int64_t ld, i
   if (lane == 0) {
     const float rv = 1.f / fmaxf(sqrtf(acc), 1e-12f);
     out[r] = rv;
-    atomicMin(reinterpret_cast<int*>(rmin), __float_as_int(rv));  // positive floats order like ints
+    atomicMin(reinterpret_cast<int*>(a.rmin[k]), __float_as_int(rv));  // positive floats order like ints
   }
 }
 
@@ -381,7 +418,11 @@ __global__ void prep_scalars_kernel(const float* __restrict__ logit_scale, float
   scal[SC_ITX] = text_temp > 0.f ? 1.f / text_temp : 0.f;
   scal[SC_ITX_L2] = text_temp > 0.f ? L2E / text_temp : 0.f;
   scal[SC_RMIN_T] = scal[SC_RMIN_Z] = scal[SC_RMIN_D] = __int_as_float(0x7f800000);  // +inf
+  scal[SC_TICKET_F] = scal[SC_TICKET_B] = 0.f;  // all-zero bits == integer 0
 }
+
+__device__ void block_reduce_rows(const float* __restrict__ in, int b, int nk, double* sums);
+__device__ bool last_block_done(int* ticket);
 
 struct FinFwdArgs {
   int b, np_c, np_s, have_soft, have_text;
@@ -392,6 +433,9 @@ struct FinFwdArgs {
   const float* scal;
   float* lse;      // [5][b]
   float* rowloss;  // [3][b]
+  int* ticket;     // zeroed by prep_scalars_kernel
+  float lam_orig, lam_soft, text_lambda;
+  float* losses;   // [5]: classic, soft_imgimg, soft_texttext, soft (= img + text_lambda * text), total
 };
 
 __device__ __forceinline__ float combine_lse2(const float* part, int np, int b, int i) {
@@ -403,7 +447,7 @@ __device__ __forceinline__ float combine_lse2(const float* part, int np, int b, 
 }
 
 // per-row combination of the column-split partial statistics -> LSEs (log2 domain) and row losses
-__global__ void finalize_fwd_kernel(FinFwdArgs a) {
+__device__ __forceinline__ void finalize_fwd_rows(const FinFwdArgs& a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.b) return;
   const float LN2 = 0.6931471805599453f;
@@ -445,9 +489,29 @@ __global__ void finalize_fwd_kernel(FinFwdArgs a) {
   a.rowloss[2 * a.b + i] = kl_x;
 }
 
-// deterministic single-block reduction: out[k] = scale[k] * sum_i in[k][i]
-__global__ void reduce_rows_kernel(const float* __restrict__ in, int b, int nk, float s0, float s1,
-                                   float s2, float* __restrict__ out) {
+__global__ void __launch_bounds__(128) finalize_fwd_kernel(FinFwdArgs a) {
+  finalize_fwd_rows(a);
+  if (last_block_done(a.ticket)) {
+    __shared__ double sums[3];
+    block_reduce_rows(a.rowloss, a.b, 3, sums);
+    if (threadIdx.x == 0) {
+      const double inv_b = 1.0 / a.b;
+      const float classic = static_cast<float>(0.5 * inv_b * sums[0]);   // loss.py:317-319
+      const float s_img = static_cast<float>(inv_b * sums[1]);           // loss.py:383 (batchmean)
+      const float s_txt = static_cast<float>(inv_b * sums[2]);           // loss.py:396
+      const float soft = s_img + a.text_lambda * s_txt;                  // loss.py:397
+      a.losses[0] = classic;
+      a.losses[1] = s_img;
+      a.losses[2] = s_txt;
+      a.losses[3] = soft;
+      a.losses[4] = a.lam_orig * classic + a.lam_soft * soft;            // loss.py:473-477
+    }
+  }
+}
+
+// Deterministic reduction by ONE block (fixed thread -> index mapping, fp64): sums[k] = sum_i in[k][i].
+// Called by the last block of a finalize kernel to finish (ticket pattern: no extra launch, no float atomics).
+__device__ void block_reduce_rows(const float* __restrict__ in, int b, int nk, double* sums) {
   __shared__ double sh[32];
   for (int k = 0; k < nk; ++k) {
     double acc = 0.0;
@@ -460,10 +524,25 @@ __global__ void reduce_rows_kernel(const float* __restrict__ in, int b, int nk, 
       double v = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (threadIdx.x == 0) out[k] = static_cast<float>(v * (k == 0 ? s0 : (k == 1 ? s1 : s2)));
+      if (threadIdx.x == 0) sums[k] = v;
     }
     __syncthreads();
   }
+}
+
+// true for every thread of exactly one block: the last one to get here (after its global writes are visible)
+__device__ bool last_block_done(int* ticket) {
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(ticket, 1);
+    is_last = (t == static_cast<int>(gridDim.x) - 1);
+    if (is_last) *ticket = 0;  // ready for the next call (e.g. a second backward through the same forward)
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last != 0;
 }
 
 // [W][5][b] (rank-major, as all-gathered) -> [5][Bcol] indexed by global column, zero padded
@@ -525,7 +604,10 @@ struct FinBwdArgs {
   const float* scal;
   const float* rinv_z;
   const float* rinv_t;
-  const float* gout;  // [3]
+  const float* gout;  // [5] upstream grads of {classic, soft_img, soft_txt, soft, total}
+  float lam_orig, lam_soft, text_lambda;
+  int* ticket;
+  float* d_scale;
   const float* lse_loc;  // [5][b] this rank's row LSEs (log2)
   float* d_image;
   float* d_text;
@@ -533,7 +615,7 @@ struct FinBwdArgs {
   float* dsrow;  // [b]
 };
 
-__device__ __forceinline__ float block_sum_128(float v, float* sh) {
+__device__ __forceinline__ float block_sum_128(float v, float* sh) {  // finalize_bwd_kernel: 4 warps
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   __syncthreads();
@@ -544,13 +626,38 @@ __device__ __forceinline__ float block_sum_128(float v, float* sh) {
 
 // One 128-thread block per local row: sum the column-split partial gradients, apply the fp32 one-hot
 // part of the CE gradient, the temperature / batch factors and the chain rule through F.normalize.
+// Every thread owns 4 consecutive features per pass (float4 traffic, sums stay in registers between the
+// dot-product pass and the output pass); FB_MAXIT passes cover feature widths up to 2048.
+constexpr int FB_MAXIT = 4;
+
+__device__ __forceinline__ float4 sum_splits4(const float* __restrict__ part, int nsplit, int b, int width, int i,
+                                               int f) {
+  float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < nsplit; ++s) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(part + (static_cast<size_t>(s) * b + i) * width + f));
+    u.x += v.x; u.y += v.y; u.z += v.z; u.w += v.w;
+  }
+  return u;
+}
+__device__ __forceinline__ float4 load_bf16x4(const __nv_bfloat16* p) {
+  const uint2 raw = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
 __global__ void __launch_bounds__(128) finalize_bwd_kernel(FinBwdArgs a) {
   __shared__ float sh[4];
   const int i = blockIdx.x;
+  const int tid = threadIdx.x;
   const size_t gi = static_cast<size_t>(a.row0) + i;
   const __nv_bfloat16* rowp = a.gathered + gi * a.row_elems;
   const float inv_b = 1.f / static_cast<float>(a.b);
-  const float gc = a.gout[0], gs = a.gout[1], gx = a.gout[2];
+  // chain rule through soft = img + tl * txt and total = lam_orig * classic + lam_soft * soft
+  const float g_soft = a.gout[3] + a.lam_soft * a.gout[4];
+  const float gc = a.gout[0] + a.lam_orig * a.gout[4];
+  const float gs = a.gout[1] + g_soft;
+  const float gx = a.gout[2] + a.text_lambda * g_soft;
   const float coefc = gc * a.scal[SC_SCALE] * 0.5f * inv_b;
   // diagonal entry of the CE logit gradient, (p_it_aa - 1) + (p_ti_aa - 1), in fp32 via expm1
   const float LN2 = 0.6931471805599453f;
@@ -560,86 +667,108 @@ __global__ void __launch_bounds__(128) finalize_bwd_kernel(FinBwdArgs a) {
   const float dg_img = a.row_only ? dm_it : dm_it + dm_ti;
   const float dg_txt = a.row_only ? dm_ti : dm_it + dm_ti;
 
+  float4 di[FB_MAXIT], dt[FB_MAXIT];  // d_image / d_text of this thread's features (D <= 2048)
+  float4 tfeat[FB_MAXIT];             // text features (reused by the text-text term)
+
   // ---- CLIP part (loss.py:317-319 backward)
-  for (int f = threadIdx.x; f < a.D; f += blockDim.x) {
-    float u1 = 0.f, u2 = 0.f;
-    for (int s = 0; s < a.ns_c; ++s) {
-      u1 += a.acc1[(static_cast<size_t>(s) * a.b + i) * a.D + f];
-      u2 += a.acc2[(static_cast<size_t>(s) * a.b + i) * a.D + f];
+#pragma unroll
+  for (int it = 0; it < FB_MAXIT; ++it) {
+    const int f = (it * 128 + tid) * 4;
+    if (f < a.D) {
+      const float4 u1 = sum_splits4(a.acc1, a.ns_c, a.b, a.D, i, f);
+      const float4 u2 = sum_splits4(a.acc2, a.ns_c, a.b, a.D, i, f);
+      const float4 tf = load_bf16x4(rowp + a.offT + f);
+      const float4 im = load_bf16x4(rowp + a.offI + f);
+      tfeat[it] = tf;
+      di[it] = make_float4(coefc * fmaf(dg_img, tf.x, u1.x), coefc * fmaf(dg_img, tf.y, u1.y),
+                           coefc * fmaf(dg_img, tf.z, u1.z), coefc * fmaf(dg_img, tf.w, u1.w));
+      dt[it] = make_float4(coefc * fmaf(dg_txt, im.x, u2.x), coefc * fmaf(dg_txt, im.y, u2.y),
+                           coefc * fmaf(dg_txt, im.z, u2.z), coefc * fmaf(dg_txt, im.w, u2.w));
     }
-    const float tf = __bfloat162float(rowp[a.offT + f]);
-    const float imf = __bfloat162float(rowp[a.offI + f]);
-    a.d_image[static_cast<size_t>(i) * a.D + f] = coefc * fmaf(dg_img, tf, u1);
-    a.d_text[static_cast<size_t>(i) * a.D + f] = coefc * fmaf(dg_txt, imf, u2);
   }
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     float d = 0.f;
     for (int s = 0; s < a.nds; ++s) d += a.ds1[s * a.b + i] + a.ds2[s * a.b + i];
     a.dsrow[i] = d - 2.f * a.diag[i];
   }
-  __syncthreads();
 
   // ---- student KL (loss.py:358-383 backward): d z~ = (g / (b tau_s)) * acc3 ; chain through normalize
   if (a.have_soft) {
     const float rz = a.rinv_z[gi];
     const float coefs = gs * a.scal[SC_ITS] * inv_b;
+    float4 dz[FB_MAXIT], zt[FB_MAXIT];
     float dot = 0.f;
-    for (int f = threadIdx.x; f < a.Dz; f += blockDim.x) {
-      float u = 0.f;
-      for (int s = 0; s < a.ns_s; ++s) u += a.acc3[(static_cast<size_t>(s) * a.b + i) * a.Dz + f];
-      const float zt = __bfloat162float(rowp[a.offZ + f]) * rz;
-      dot = fmaf(zt, coefs * u, dot);
+#pragma unroll
+    for (int it = 0; it < FB_MAXIT; ++it) {
+      const int f = (it * 128 + tid) * 4;
+      if (f < a.Dz) {
+        float4 u = sum_splits4(a.acc3, a.ns_s, a.b, a.Dz, i, f);
+        float4 z = load_bf16x4(rowp + a.offZ + f);
+        z.x *= rz; z.y *= rz; z.z *= rz; z.w *= rz;
+        u.x *= coefs; u.y *= coefs; u.z *= coefs; u.w *= coefs;
+        dot += z.x * u.x + z.y * u.y + z.z * u.z + z.w * u.w;
+        dz[it] = u;
+        zt[it] = z;
+      }
     }
     dot = block_sum_128(dot, sh);
-    float* dst = a.have_proj ? a.d_student : a.d_image;
-    for (int f = threadIdx.x; f < a.Dz; f += blockDim.x) {
-      float u = 0.f;
-      for (int s = 0; s < a.ns_s; ++s) u += a.acc3[(static_cast<size_t>(s) * a.b + i) * a.Dz + f];
-      const float zt = __bfloat162float(rowp[a.offZ + f]) * rz;
-      const float gval = rz * (coefs * u - zt * dot);
-      if (a.have_proj)
-        dst[static_cast<size_t>(i) * a.Dz + f] = gval;
-      else
-        dst[static_cast<size_t>(i) * a.Dz + f] += gval;
+#pragma unroll
+    for (int it = 0; it < FB_MAXIT; ++it) {
+      const int f = (it * 128 + tid) * 4;
+      if (f < a.Dz) {
+        const float4 g4 = make_float4(rz * (dz[it].x - zt[it].x * dot), rz * (dz[it].y - zt[it].y * dot),
+                                      rz * (dz[it].z - zt[it].z * dot), rz * (dz[it].w - zt[it].w * dot));
+        if (a.have_proj) {
+          *reinterpret_cast<float4*>(a.d_student + static_cast<size_t>(i) * a.Dz + f) = g4;
+        } else {  // student == image features: same thread owns the same features (Dz == D)
+          di[it].x += g4.x; di[it].y += g4.y; di[it].z += g4.z; di[it].w += g4.w;
+        }
+      }
     }
   }
   // ---- text-text KL (loss.py:387-397 backward)
   if (a.have_text) {
-    __syncthreads();
     const float rt = a.rinv_t[gi];
     const float coefx = gx * a.scal[SC_ITX] * inv_b;
+    float4 dx[FB_MAXIT];
     float dot = 0.f;
-    for (int f = threadIdx.x; f < a.D; f += blockDim.x) {
-      float u = 0.f;
-      for (int s = 0; s < a.ns_x; ++s) u += a.acc4[(static_cast<size_t>(s) * a.b + i) * a.D + f];
-      const float tt = __bfloat162float(rowp[a.offT + f]) * rt;
-      dot = fmaf(tt, coefx * u, dot);
+#pragma unroll
+    for (int it = 0; it < FB_MAXIT; ++it) {
+      const int f = (it * 128 + tid) * 4;
+      if (f < a.D) {
+        float4 u = sum_splits4(a.acc4, a.ns_x, a.b, a.D, i, f);
+        u.x *= coefx; u.y *= coefx; u.z *= coefx; u.w *= coefx;
+        const float4 t = tfeat[it];
+        dot += rt * (t.x * u.x + t.y * u.y + t.z * u.z + t.w * u.w);
+        dx[it] = u;
+      }
     }
     dot = block_sum_128(dot, sh);
-    for (int f = threadIdx.x; f < a.D; f += blockDim.x) {
-      float u = 0.f;
-      for (int s = 0; s < a.ns_x; ++s) u += a.acc4[(static_cast<size_t>(s) * a.b + i) * a.D + f];
-      const float tt = __bfloat162float(rowp[a.offT + f]) * rt;
-      a.d_text[static_cast<size_t>(i) * a.D + f] += rt * (coefx * u - tt * dot);
+#pragma unroll
+    for (int it = 0; it < FB_MAXIT; ++it) {
+      const int f = (it * 128 + tid) * 4;
+      if (f < a.D) {
+        const float4 t = tfeat[it];
+        dt[it].x += rt * (dx[it].x - rt * t.x * dot);
+        dt[it].y += rt * (dx[it].y - rt * t.y * dot);
+        dt[it].z += rt * (dx[it].z - rt * t.z * dot);
+        dt[it].w += rt * (dx[it].w - rt * t.w * dot);
+      }
     }
   }
-}
-
-// d logit_scale = g_classic / (2b) * sum_i dsrow[i]
-__global__ void reduce_ds_kernel(const float* __restrict__ dsrow, int b, const float* __restrict__ gout,
-                                 float* __restrict__ out) {
-  __shared__ double sh[32];
-  double acc = 0.0;
-  for (int i = threadIdx.x; i < b; i += blockDim.x) acc += static_cast<double>(dsrow[i]);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    double v = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (threadIdx.x == 0) out[0] = static_cast<float>(v * static_cast<double>(gout[0]) * 0.5 / b);
+  for (int it = 0; it < FB_MAXIT; ++it) {
+    const int f = (it * 128 + tid) * 4;
+    if (f < a.D) {
+      *reinterpret_cast<float4*>(a.d_image + static_cast<size_t>(i) * a.D + f) = di[it];
+      *reinterpret_cast<float4*>(a.d_text + static_cast<size_t>(i) * a.D + f) = dt[it];
+    }
+  }
+  // ---- d logit_scale = g_classic / (2b) * sum_i dsrow[i], finished by the last block
+  if (last_block_done(a.ticket)) {
+    __shared__ double sum1[1];
+    block_reduce_rows(a.dsrow, a.b, 1, sum1);
+    if (threadIdx.x == 0) a.d_scale[0] = static_cast<float>(sum1[0] * static_cast<double>(gc) * 0.5 / a.b);
   }
 }
 
@@ -745,34 +874,24 @@ static int launch_bwd(K kernel, int nch, int rbs, int nsplit, cudaStream_t st, c
   return 0;
 }
 
+// cudaFuncSetAttribute once per (kernel, device): K is only the function-pointer TYPE, so remember the
+// pointer values that were configured
 template <typename K>
 static int set_smem(K kernel, int bytes) {
+  static thread_local const void* done[16][2];
+  static thread_local int ndone = 0;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  const void* key = reinterpret_cast<const void*>(kernel);
+  const void* devkey = reinterpret_cast<const void*>(static_cast<uintptr_t>(dev) + 1);
+  for (int i = 0; i < ndone; ++i)
+    if (done[i][0] == key && done[i][1] == devkey) return 0;
   CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  return 0;
-}
-
-static int pack_one(const void* src, int dtype, int64_t ld, __nv_bfloat16* dst, int64_t dst_ld, int rows,
-                    int cols, cudaStream_t st) {
-  const int64_t total = static_cast<int64_t>(rows) * (cols / 2);
-  const int threads = 256;
-  const int blocks = static_cast<int>(std::min<int64_t>((total + threads - 1) / threads, 148 * 16));
-  switch (dtype) {
-    case DSOFT_DT_F32:
-      pack_rows_kernel<float><<<blocks, threads, 0, st>>>(static_cast<const float*>(src), ld, dst, dst_ld,
-                                                          rows, cols);
-      break;
-    case DSOFT_DT_BF16:
-      pack_rows_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(src),
-                                                                  ld, dst, dst_ld, rows, cols);
-      break;
-    case DSOFT_DT_F16:
-      pack_rows_kernel<__half><<<blocks, threads, 0, st>>>(static_cast<const __half*>(src), ld, dst,
-                                                           dst_ld, rows, cols);
-      break;
-    default:
-      return fail(DSOFT_EINVAL, "unknown dtype %d", dtype);
+  if (ndone < 16) {
+    done[ndone][0] = key;
+    done[ndone][1] = devkey;
+    ++ndone;
   }
-  CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
@@ -786,15 +905,30 @@ extern "C" int dsoft_pack(const dsoft_plan_t* p, const void* image, int image_dt
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* base =
       static_cast<__nv_bfloat16*>(gathered) + static_cast<size_t>(p->sh.rank) * p->sh.b * p->row_elems;
+  PackArgs a;
+  memset(&a, 0, sizeof(a));
+  a.rows = p->sh.b;
+  a.dst_ld = p->row_elems;
+  auto add = [&](const void* src, int dt, int64_t ld, int cols, int off) -> int {
+    if (dt < DSOFT_DT_F32 || dt > DSOFT_DT_F16) return fail(DSOFT_EINVAL, "unknown dtype %d", dt);
+    if (ld % 2 || reinterpret_cast<uintptr_t>(src) % 8)
+      return fail(DSOFT_EINVAL, "pack sources need even row strides and 8-byte aligned base pointers");
+    PackSrc& m = a.m[a.nmat];
+    m.src = src; m.dtype = dt; m.ld = ld; m.cols = cols; m.dst_off = off;
+    a.pairs_end[a.nmat] = (a.nmat ? a.pairs_end[a.nmat - 1] : 0) + static_cast<int64_t>(a.rows) * (cols / 2);
+    ++a.nmat;
+    return 0;
+  };
   int rc;
-  if ((rc = pack_one(image, image_dt, ld_image, base + p->offI, p->row_elems, p->sh.b, p->sh.D, st))) return rc;
-  if ((rc = pack_one(text, text_dt, ld_text, base + p->offT, p->row_elems, p->sh.b, p->sh.D, st))) return rc;
-  if (p->have_proj)
-    if ((rc = pack_one(student, student_dt, ld_student, base + p->offZ, p->row_elems, p->sh.b, p->sh.Dp, st)))
-      return rc;
-  if (p->have_soft)
-    if ((rc = pack_one(dino, dino_dt, ld_dino, base + p->offD, p->row_elems, p->sh.b, p->sh.Dd, st)))
-      return rc;
+  if ((rc = add(image, image_dt, ld_image, p->sh.D, p->offI))) return rc;
+  if ((rc = add(text, text_dt, ld_text, p->sh.D, p->offT))) return rc;
+  if (p->have_proj && (rc = add(student, student_dt, ld_student, p->sh.Dp, p->offZ))) return rc;
+  if (p->have_soft && (rc = add(dino, dino_dt, ld_dino, p->sh.Dd, p->offD))) return rc;
+  const int64_t total = a.pairs_end[a.nmat - 1];
+  const int threads = 256;
+  const int blocks = static_cast<int>(std::min<int64_t>((total + threads - 1) / threads, 148 * 16));
+  pack_rows_kernel<<<blocks, threads, 0, st>>>(a, base);
+  CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
@@ -820,8 +954,9 @@ static void fill_clip_fwd(const dsoft_plan* p, FwdParams& P, int amap, int bmap,
 }
 
 extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const float* logit_scale,
-                             void* state, void* scratch, float* lse_local, float* losses, void* stream) {
-  if (!p || !gathered || !logit_scale || !state || !scratch || !lse_local || !losses)
+                             const float* lambdas, void* state, void* scratch, float* lse_local,
+                             float* losses, void* stream) {
+  if (!p || !gathered || !logit_scale || !lambdas || !state || !scratch || !lse_local || !losses)
     return fail(DSOFT_EINVAL, "null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* S = static_cast<float*>(state);
@@ -837,17 +972,17 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
                                         p->have_text ? p->sh.text_temp : 0.f, S + p->st_scal);
   CUDA_TRY(cudaGetLastError());
 
-  {  // inverse norms of text / student / dino rows of all ranks (grid.y selects the matrix)
+  {  // inverse norms of text / student / dino rows of all ranks: one launch, grid.y = matrix
+    RinvArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    ra.ld = p->row_elems;
+    ra.rows = p->B;
+    ra.out_len = p->Bcol;
+    ra.mat[0] = g + p->offT; ra.cols[0] = p->sh.D;  ra.out[0] = S + p->st_rinv_t; ra.rmin[0] = S + p->st_scal + SC_RMIN_T;
+    ra.mat[1] = g + p->offZ; ra.cols[1] = p->Dz;    ra.out[1] = S + p->st_rinv_z; ra.rmin[1] = S + p->st_scal + SC_RMIN_Z;
+    ra.mat[2] = g + p->offD; ra.cols[2] = p->sh.Dd; ra.out[2] = S + p->st_rinv_d; ra.rmin[2] = S + p->st_scal + SC_RMIN_D;
     const int wpb = 8;
-    const int blocks = ceil_div(p->Bcol, wpb);
-    rinv_kernel<<<blocks, wpb * 32, 0, st>>>(g + p->offT, p->row_elems, p->B, p->sh.D, S + p->st_rinv_t,
-                                             p->Bcol, S + p->st_scal + SC_RMIN_T);
-    if (p->have_soft) {
-      rinv_kernel<<<blocks, wpb * 32, 0, st>>>(g + p->offZ, p->row_elems, p->B, p->Dz, S + p->st_rinv_z,
-                                               p->Bcol, S + p->st_scal + SC_RMIN_Z);
-      rinv_kernel<<<blocks, wpb * 32, 0, st>>>(g + p->offD, p->row_elems, p->B, p->sh.Dd,
-                                               S + p->st_rinv_d, p->Bcol, S + p->st_scal + SC_RMIN_D);
-    }
+    rinv_kernel<<<dim3(ceil_div(p->Bcol, wpb), p->have_soft ? 3 : 1), wpb * 32, 0, st>>>(ra);
     CUDA_TRY(cudaGetLastError());
   }
 
@@ -911,18 +1046,20 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
   fa.scal = S + p->st_scal;
   fa.lse = lse_local;
   fa.rowloss = X + p->sc_rowloss;
+  fa.ticket = reinterpret_cast<int*>(S + p->st_scal + SC_TICKET_F);
+  fa.lam_orig = lambdas[0];
+  fa.lam_soft = lambdas[1];
+  fa.text_lambda = lambdas[2];
+  fa.losses = losses;
   finalize_fwd_kernel<<<ceil_div(b, 128), 128, 0, st>>>(fa);
-  CUDA_TRY(cudaGetLastError());
-  const float inv_b = 1.f / static_cast<float>(b);
-  reduce_rows_kernel<<<1, 1024, 0, st>>>(X + p->sc_rowloss, b, 3, 0.5f * inv_b, inv_b, inv_b, losses);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
 extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const void* state, void* scratch,
-                              const float* lse_all, const float* gout, float* d_image, float* d_text,
-                              float* d_student, float* d_scale, void* stream) {
-  if (!p || !gathered || !state || !scratch || !lse_all || !gout || !d_image || !d_text || !d_scale)
+                              const float* lse_all, const float* gout, const float* lambdas, float* d_image,
+                              float* d_text, float* d_student, float* d_scale, void* stream) {
+  if (!p || !gathered || !state || !scratch || !lse_all || !gout || !lambdas || !d_image || !d_text || !d_scale)
     return fail(DSOFT_EINVAL, "null argument");
   if (p->have_proj && !d_student) return fail(DSOFT_EINVAL, "d_student is null but the plan has Dp > 0");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1083,9 +1220,12 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
   fa.d_text = d_text;
   fa.d_student = d_student;
   fa.dsrow = X + p->sc_dsrow;
+  fa.lam_orig = lambdas[0];
+  fa.lam_soft = lambdas[1];
+  fa.text_lambda = lambdas[2];
+  fa.ticket = reinterpret_cast<int*>(S + p->st_scal + SC_TICKET_B);
+  fa.d_scale = d_scale;
   finalize_bwd_kernel<<<b, 128, 0, st>>>(fa);
-  CUDA_TRY(cudaGetLastError());
-  reduce_ds_kernel<<<1, 1024, 0, st>>>(X + p->sc_dsrow, b, gout, d_scale);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

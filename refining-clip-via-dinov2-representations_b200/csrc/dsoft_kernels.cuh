@@ -51,7 +51,9 @@ enum {
   SC_RMIN_T = 8,    // min_j 1/||text_j||    (atomicMin by rinv_kernel; +inf until then)
   SC_RMIN_Z = 9,    // min_j 1/||student_j||
   SC_RMIN_D = 10,   // min_j 1/||dino_j||
-  SC_COUNT = 12
+  SC_TICKET_F = 12, // (int) blocks of finalize_fwd_kernel that are done: the last one reduces the row losses
+  SC_TICKET_B = 13, // (int) same for finalize_bwd_kernel
+  SC_COUNT = 16
 };
 
 // Power-of-two scale sigma <= min_j rinv_j: operand rows times sigma have norm <= 1, and the scaling is

@@ -159,18 +159,24 @@ class CudaBackend:
             "dsoft_pack",
         )
 
-    def forward(self, plan, gathered, logit_scale, state, scratch, lse_local, losses):
+    @staticmethod
+    def _lam(lambdas):
+        import ctypes as C
+
+        return (C.c_float * 3)(*[float(x) for x in lambdas])
+
+    def forward(self, plan, gathered, logit_scale, lambdas, state, scratch, lse_local, losses):
         _cabi.check(
-            self._lib.dsoft_forward(plan.handle, _ptr(gathered), _ptr(logit_scale), _ptr(state), _ptr(scratch),
-                                    _ptr(lse_local), _ptr(losses), self._stream(gathered)),
+            self._lib.dsoft_forward(plan.handle, _ptr(gathered), _ptr(logit_scale), self._lam(lambdas), _ptr(state),
+                                    _ptr(scratch), _ptr(lse_local), _ptr(losses), self._stream(gathered)),
             "dsoft_forward",
         )
 
-    def backward(self, plan, gathered, state, scratch, lse_all, gout, d_image, d_text, d_student, d_scale):
+    def backward(self, plan, gathered, state, scratch, lse_all, gout, lambdas, d_image, d_text, d_student, d_scale):
         _cabi.check(
             self._lib.dsoft_backward(plan.handle, _ptr(gathered), _ptr(state), _ptr(scratch), _ptr(lse_all),
-                                     _ptr(gout), _ptr(d_image), _ptr(d_text), _ptr(d_student), _ptr(d_scale),
-                                     self._stream(gathered)),
+                                     _ptr(gout), self._lam(lambdas), _ptr(d_image), _ptr(d_text), _ptr(d_student),
+                                     _ptr(d_scale), self._stream(gathered)),
             "dsoft_backward",
         )
 
@@ -191,11 +197,13 @@ def _default_backend(device: torch.device) -> CudaBackend:
 
 
 class _FnConfig:
-    __slots__ = ("backend", "world", "rank", "group", "flags", "teacher_temp", "text_temp")
+    __slots__ = ("backend", "world", "rank", "group", "flags", "teacher_temp", "text_temp", "lambdas")
 
 
 class _DinoSoftFn(torch.autograd.Function):
-    """(image, text, logit_scale, student_raw, dino) -> [classic_loss, soft_imgimg, soft_texttext]."""
+    """(image, text, logit_scale, student_raw, dino) ->
+    [classic_loss, soft_imgimg, soft_texttext, soft_loss, total_loss]  (loss composition loss.py:397, 473-477 is
+    done by the finalize kernel: ~12 tiny PyTorch kernels fewer per step)."""
 
     @staticmethod
     def forward(ctx, image, text, logit_scale, student, dino, cfg: _FnConfig):
@@ -220,9 +228,9 @@ class _DinoSoftFn(torch.autograd.Function):
         state = torch.empty(plan.state_numel, dtype=torch.float32, device=dev)
         scratch = torch.empty(plan.scratch_numel, dtype=torch.float32, device=dev)
         lse_all = torch.empty((W, 5, b), dtype=torch.float32, device=dev)
-        losses = torch.empty(3, dtype=torch.float32, device=dev)
+        losses = torch.empty(5, dtype=torch.float32, device=dev)
         ls = logit_scale.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
-        be.forward(plan, gathered, ls, state, scratch, lse_all[r], losses)
+        be.forward(plan, gathered, ls, cfg.lambdas, state, scratch, lse_all[r], losses)
         needs_grad = any(ctx.needs_input_grad[:4])
         if W > 1 and needs_grad:
             # column-side soft-max statistics of the other ranks' rows (5 floats per sample)
@@ -246,7 +254,7 @@ class _DinoSoftFn(torch.autograd.Function):
         d_student = torch.empty((b, Dp), dtype=torch.float32, device=dev) if Dp > 0 else None
         d_scale = torch.empty(1, dtype=torch.float32, device=dev)
         scratch = torch.empty(plan.scratch_numel, dtype=torch.float32, device=dev)
-        be.backward(plan, gathered, state, scratch, lse_all, gout, d_image, d_text, d_student, d_scale)
+        be.backward(plan, gathered, state, scratch, lse_all, gout, ctx.cfg.lambdas, d_image, d_text, d_student, d_scale)
         g_student = None
         if zdt is not None:
             g_student = d_student.to(zdt) if d_student is not None else None
@@ -414,28 +422,22 @@ class ClipLossWithDINOEnhancements(nn.Module):
         if self.world_size > 1 and not self.gather_with_grad:
             flags |= _cabi.DSOFT_F_ROW_ONLY
 
+        lambda_original = float(g(args, "lambda_original", 1.0))
+        text_lambda = float(g(args, "text_lambda", 0.2)) if text_on else 0.0
         cfg = _FnConfig()
         cfg.backend = self._backend if self._backend is not None else _default_backend(device)
         cfg.world, cfg.rank, cfg.group = self.world_size, self.rank, self.process_group
         cfg.flags, cfg.teacher_temp, cfg.text_temp = flags, teacher_temp, text_temp
+        cfg.lambdas = (lambda_original, lambda_soft if soft_on else 0.0, text_lambda)
 
         terms = _DinoSoftFn.apply(
             image_features, text_features, logit_scale, student, dino_features if soft_on else None, cfg
         )
         classic_loss = terms[0]
-
-        soft_loss = torch.zeros((), device=device)
-        if soft_on:
-            soft_loss = terms[1]
-            if text_on:
-                soft_loss = soft_loss + float(g(args, "text_lambda", 0.2)) * terms[2]
-
+        soft_loss = terms[3] if soft_on else torch.zeros((), device=device)
         weighted_loss = torch.zeros((), device=device, dtype=classic_loss.dtype)
-        total_loss = (
-            float(g(args, "lambda_original", 1.0)) * classic_loss
-            + lambda_soft * soft_loss
-            + lambda_weighted * weighted_loss
-        )
+        # lambda_weighted * weighted_loss is identically zero here (the branch raises above when enabled)
+        total_loss = terms[4]
         dbg = {}
         if output_dict:
             return {

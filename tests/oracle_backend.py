@@ -63,16 +63,20 @@ class OracleBackend:
             world_size=s.world, local_loss=True, gather_with_grad=not (s.flags & F_ROW_ONLY),
             soft_scope="local" if (s.flags & F_SOFT_LOCAL) else "global")
 
-    def forward(self, plan, gathered, logit_scale, state, scratch, lse_local, losses):
+    def forward(self, plan, gathered, logit_scale, lambdas, state, scratch, lse_local, losses):
         img, txt, stu, dino = self._decode(plan, gathered)
         out = self.oracle.rank_loss(img, txt, logit_scale.double()[0], dino, stu, self._cfg(plan), rank=plan.shape.rank)
-        losses[0], losses[1], losses[2] = float(out["classic_loss"]), float(out["soft_img"]), float(out["soft_txt"])
+        lo, ls, tl = lambdas
+        c, si, st = float(out["classic_loss"]), float(out["soft_img"]), float(out["soft_txt"])
+        losses[0], losses[1], losses[2] = c, si, st
+        losses[3] = si + tl * st
+        losses[4] = lo * c + ls * (si + tl * st)
         lse_local.zero_()
         state[0] = float(logit_scale[0])
         self.calls.append("forward")
 
     @torch.enable_grad()  # called from inside autograd.Function.backward, where grad mode is off
-    def backward(self, plan, gathered, state, scratch, lse_all, gout, d_image, d_text, d_student, d_scale):
+    def backward(self, plan, gathered, state, scratch, lse_all, gout, lambdas, d_image, d_text, d_student, d_scale):
         s = plan.shape
         cfg = self._cfg(plan)
         img, txt, stu, dino = (None if t is None else t.clone() for t in self._decode(plan, gathered))
@@ -81,7 +85,10 @@ class OracleBackend:
         if stu is not None:
             stu.requires_grad_(True)
         sc = torch.tensor(float(state[0]), dtype=torch.float64, requires_grad=True)
-        g = gout.double()
+        lo, ls, tl = lambdas
+        g5 = gout.double()
+        gsoft = g5[3] + ls * g5[4]
+        g = torch.stack([g5[0] + lo * g5[4], g5[1] + gsoft, g5[2] + tl * gsoft])
 
         def weighted(rank):
             o = self.oracle.rank_loss(img, txt, sc, dino, stu, cfg, rank=rank)
