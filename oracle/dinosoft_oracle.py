@@ -63,6 +63,9 @@ class OracleConfig:
     local_loss: bool = False
     gather_with_grad: bool = False
     soft_scope: str = "global"  # "global": soft terms over all B columns; "local": reference at W>1
+    # residual projection (loss.py:331-343): only active when the head keeps the width (Dd == D)
+    residual_projection: bool = False
+    residual_alpha: Optional[float] = None
     # operand rounding of the B200 path (the reference has none): student operand rounded to bf16
     round_student_bf16: bool = False
     extra: Dict[str, object] = field(default_factory=dict)
@@ -260,6 +263,11 @@ def loss_and_grads(
         student = None
         if pp is not None and dn is not None:
             student = mlp_head(im, pp, projection_type)
+            if cfg.residual_projection and student.shape == im.shape:  # loss.py:331-343
+                if cfg.residual_alpha is None:
+                    student = im + student
+                else:
+                    student = cfg.residual_alpha * im + (1 - cfg.residual_alpha) * student
             student.retain_grad()
         # this rank's own loss terms
         own = rank_loss(im, tx, sc, dn, student, cfg, rank=r)
@@ -281,7 +289,10 @@ def loss_and_grads(
         if student is not None and student.grad is not None:
             entry["d_student"] = student.grad[rows].detach().clone()
             # head parameters: this rank back-propagates d_student through its own head on its local rows
+            # (the residual mix scales the head's share by 1 or 1 - alpha)
             local_out = mlp_head(im.detach()[rows], pp, projection_type)
+            if cfg.residual_projection and local_out.shape[1] == im.shape[1] and cfg.residual_alpha is not None:
+                local_out = (1 - cfg.residual_alpha) * local_out
             g_pp = torch.autograd.grad(local_out, list(pp.values()), grad_outputs=entry["d_student"],
                                        allow_unused=True)
             entry["d_proj"] = {k: (None if g is None else g.detach().clone()) for k, g in zip(pp.keys(), g_pp)}

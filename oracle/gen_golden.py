@@ -130,6 +130,13 @@ CASES = [
          args=dict(use_projection=True, lambda_soft=0.0, soft_mode="none")),
     dict(name="w1_scale_below_10", B=40, D=32, Dd=32, scale=4.0, world=1, clustered=False,
          args=dict(use_projection=False, lambda_soft=0.5, soft_mode="kl_teacher", teacher_temp=0.15)),
+    dict(name="w1_residual", B=56, D=64, Dd=64, scale=25.0, world=1, clustered=True,
+         args=dict(use_projection=True, projection_type="mlp", residual_projection=True, lambda_soft=0.5,
+                   soft_mode="kl_teacher", soft_dino_to_text=True, text_lambda=0.3, text_student_temp=0.03,
+                   teacher_temp=0.15)),
+    dict(name="w1_residual_alpha", B=56, D=64, Dd=64, scale=25.0, world=1, clustered=True,
+         args=dict(use_projection=True, projection_type="linear", residual_projection=True, residual_alpha=0.3,
+                   lambda_soft=0.5, soft_mode="kl_teacher", teacher_temp=0.2)),
     dict(name="w2_gather_grad", B=64, D=64, Dd=96, scale=14.2857, world=2, clustered=True,
          local_loss=True, gather_with_grad=True,
          args=dict(use_projection=True, projection_type="mlp", lambda_soft=0.5, soft_mode="kl_teacher",

@@ -68,7 +68,8 @@ def test_labels_and_tau_helpers(pkg):
 
 
 @pytest.mark.parametrize("fname", ["w1_noproj_text.npz", "w1_classic_only.npz", "w1_scale_below_10.npz",
-                                   "w1_mlp_text_scale100.npz", "w1_linear_notext.npz", "w1_mlp_layernorm.npz"])
+                                   "w1_mlp_text_scale100.npz", "w1_linear_notext.npz", "w1_mlp_layernorm.npz",
+                                   "w1_residual.npz", "w1_residual_alpha.npz"])
 def test_module_wiring_reproduces_reference_fixture(pkg, oracle, fname):
     """Module (host logic) + oracle test double == the reference's own numbers at world_size 1.
     Checks knob decoding, projection-head handling, loss composition and the autograd plumbing."""

@@ -22,6 +22,8 @@ def _cfg_from(oracle, z, soft_scope="local"):
         local_loss=bool(z["local_loss"]),
         gather_with_grad=bool(z["gather_with_grad"]),
         soft_scope=soft_scope,  # the reference computes the soft terms on the local block
+        residual_projection=bool(a.get("residual_projection", False)),
+        residual_alpha=(None if a.get("residual_alpha") is None else float(a["residual_alpha"])),
     ), a
 
 
