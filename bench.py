@@ -351,6 +351,10 @@ def run_ours(args):
             avg_ms = ms_sum[k] / cnt[k]
             kern[name] = {"ms": round(avg_ms, 4), "alg_tflops": round(alg[k] / avg_ms / 1e9, 1),
                           "exec_tflops": round(exe[k] / avg_ms / 1e9, 1), "launches": cnt[k]}
+        # DRAM bytes (read + write) per launch from the ncu --set full capture of this exact workload
+        # (profiles/r01b_ncu_full_tile_kernels.csv); only meaningful for the default configuration
+        ncu_traffic = {"fwd_clip_i2t": 73.8e6, "fwd_clip_t2i": 73.7e6, "fwd_soft": 1009.5e6, "bwd_clip_image": 309.0e6,
+                       "bwd_clip_text": 310.1e6, "bwd_student": 1209.1e6, "bwd_text": 563.3e6}
         dom = max(kern, key=lambda n: kern[n]["ms"])
         dk = KERNEL_NAMES.index(dom)
         dom_ms = ms_sum[dk] / cnt[dk]
@@ -377,7 +381,8 @@ def run_ours(args):
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": round(achieved, 1), "peak": peak_sust,
-                         "unit": "TFLOP/s", "frac": round(achieved / peak_sust, 4), "traffic": None,
+                         "unit": "TFLOP/s", "frac": round(achieved / peak_sust, 4),
+                         "traffic": ncu_traffic.get(dom) if (GLOBAL_B == 32768 and world == 1) else None,
                          "peak_source": peak_src, "peak_burst": peak_burst,
                          "executed_tflops": kern[dom]["exec_tflops"],
                          "executed_frac": round(kern[dom]["exec_tflops"] / peak_sust, 4),
