@@ -122,7 +122,9 @@ class CudaBackend:
         self._lib = _cabi.lib()
         self._plans = {}
 
-    def plan(self, shape: "_cabi.Shape") -> _Plan:
+    def plan(self, shape: "_cabi.Shape", device: Optional[torch.device] = None) -> _Plan:
+        if device is not None and device.index is not None and torch.cuda.current_device() != device.index:
+            torch.cuda.set_device(device)
         key = (shape.key(), torch.cuda.current_device())
         p = self._plans.get(key)
         if p is None:
@@ -144,6 +146,10 @@ class CudaBackend:
 
     @staticmethod
     def _stream(t: torch.Tensor):
+        # the C side works on the CUDA runtime's current device: make it the tensors' device (a process that
+        # holds several GPUs may call the loss for a tensor that does not live on the current one)
+        if torch.cuda.current_device() != t.device.index:
+            torch.cuda.set_device(t.device)
         return torch.cuda.current_stream(t.device).cuda_stream
 
     def pack(self, plan, image, text, student, dino, gathered):
@@ -218,7 +224,7 @@ class _DinoSoftFn(torch.autograd.Function):
             Dd=(dino.shape[1] if (dino is not None and soft) else 0),
             flags=cfg.flags, teacher_temp=cfg.teacher_temp, text_temp=cfg.text_temp,
         )
-        plan = be.plan(shape)
+        plan = be.plan(shape, dev) if dev.type == "cuda" else be.plan(shape)
         gathered = torch.empty((b * W, plan.row_elems), dtype=torch.bfloat16, device=dev)
         be.pack(plan, image.detach(), text.detach(), None if student is None or not soft else student.detach(),
                 None if dino is None or not soft else dino.detach(), gathered)

@@ -20,7 +20,7 @@ class OracleBackend:
         self.oracle = oracle
         self.calls = []
 
-    def plan(self, shape):
+    def plan(self, shape, device=None):
         p = _Plan()
         p.shape = shape
         p.soft = bool(shape.flags & F_SOFT)
