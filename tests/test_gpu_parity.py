@@ -139,3 +139,16 @@ def test_config4_dims_vitl(pkg, oracle):
     """BASELINE config 4 feature dims (ViT-L/14: D=768, DINOv2-L: 1024, four 256-feature chunks with the head)."""
     check_against_oracle(pkg, oracle, 640, 768, 1024, 50.0, make_args(use_projection=False), seed=4)
     check_against_oracle(pkg, oracle, 384, 768, 1024, 50.0, make_args(use_projection=True), seed=4)
+
+
+@pytest.mark.parametrize("scale,teacher_temp,text_temp", [
+    (1.0, 0.15, 0.05),     # scale <= 10 is treated as a raw ln-scale by compute_student_tau (loss.py:172)
+    (200.0, 0.15, 0.02),   # beyond the model's clamp: CLIP logits use it as is, tau_s saturates at 0.01
+    (60.0, 0.03, 0.01),    # very sharp teacher / text student: exponent ranges of +-70 / +-290 in log2 units
+    (14.2857, 1.0, 0.5),   # nearly flat teacher
+])
+def test_temperature_and_scale_extremes(pkg, oracle, scale, teacher_temp, text_temp):
+    args = make_args(use_projection=True, teacher_temp=teacher_temp, text_student_temp=text_temp)
+    check_against_oracle(pkg, oracle, 384, 128, 192, scale, args, seed=13)
+    args = make_args(use_projection=False, teacher_temp=teacher_temp, text_student_temp=text_temp)
+    check_against_oracle(pkg, oracle, 384, 128, 192, scale, args, seed=14, clustered=False)
