@@ -251,7 +251,6 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    lib.dsoft_profile_enable(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -261,12 +260,28 @@ def run_ours(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    final_loss = float(out["total_loss"].detach())
+
+    # ---- per-kernel pass (same inputs, same loop, clocks still sampled): the product launches the independent
+    # tile kernels of a pass on forked streams so they fill each other's last wave; CUDA events around a kernel
+    # that shares the GPU do not give its own duration, so the recorder serialises the launches and this pass
+    # is timed separately from the headline above
+    prof_steps = max(1, min(args.steps, 10))
+    lib.dsoft_profile_enable(1)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    p0.record()
+    for _ in range(prof_steps):
+        zero_grads()
+        step(img, txt, dino)
+    p1.record()
+    barrier()
+    ms_serial = p0.elapsed_time(p1)
     clocks = sampler.stop() if rank == 0 else None
     ms_sum = (C.c_double * 7)()
     cnt = (C.c_int * 7)()
     _cabi.check(lib.dsoft_profile_read(ms_sum, cnt, 7), "dsoft_profile_read")
     lib.dsoft_profile_enable(0)
-    final_loss = float(out["total_loss"].detach())
 
     # ---- e2e: pinned host inputs -> H2D -> module -> loss scalars back to the host, every step
     h_img = img.detach().cpu().pin_memory()
@@ -359,7 +374,7 @@ def run_ours(args):
         dk = KERNEL_NAMES.index(dom)
         dom_ms = ms_sum[dk] / cnt[dk]
         achieved = alg[dk] / dom_ms / 1e9
-        tile_ms = sum(ms_sum[k] for k in range(7)) / args.steps
+        tile_ms = sum(ms_sum[k] for k in range(7)) / prof_steps
         step_ms = ms / args.steps
         step_alg_tflops = plan.flops / step_ms / 1e9  # this rank's algorithmic FLOPs / step time
         cpu_baseline = None
@@ -391,8 +406,12 @@ def run_ours(args):
             "step_roofline": {"algorithmic_tflops_per_gpu": round(step_alg_tflops, 1),
                               "frac_of_sustained_peak": round(step_alg_tflops / peak_sust, 4),
                               "frac_of_burst_peak": round(step_alg_tflops / peak_burst, 4) if peak_burst else None,
-                              "tile_kernel_ms_per_step": round(tile_ms, 4),
-                              "tile_kernel_share_of_step": round(tile_ms / step_ms, 4)},
+                              "serial_ms_per_step": round(ms_serial / prof_steps, 4),
+                              "tile_kernel_ms_per_serial_step": round(tile_ms, 4),
+                              "tile_kernel_share_of_serial_step": round(tile_ms / (ms_serial / prof_steps), 4),
+                              "note": "per-kernel durations come from a second pass of the same loop with the "
+                                      "tile kernels launched serially (dsoft_profile_enable); the headline "
+                                      "ms_per_step launches them on forked streams"},
             "kernels": kern,
             "cpu_baseline": cpu_baseline,
             "loss": final_loss,

@@ -123,6 +123,13 @@ int dsoft_backward(const dsoft_plan_t* plan, const void* gathered_dev, const voi
 int dsoft_profile_enable(int on);
 int dsoft_profile_read(double* ms_sum, int* counts, int n);
 
+/* The independent tile kernels of one pass (3 forward, 4 backward) are launched on internal side streams
+ * forked from / joined back into `stream`, so the next kernel's CTAs fill the partially empty last wave of
+ * the previous one; callers still see plain stream-ordered semantics, and stream capture records a
+ * fork/join graph.  on = 0 launches them serially on `stream` (also forced while dsoft_profile_enable(1) is
+ * active so that per-kernel durations are isolated).  Default: on, or the DSOFT_CONCURRENCY=0/1 variable. */
+int dsoft_set_concurrency(int on);
+
 /* Test / bring-up helper: C[M][N] (fp32) = A[M][K] . B[N][K]^T with bf16 operands through the same
  * TMA + tcgen05 tile path the loss kernels use (128 x 128 tiles). */
 int dsoft_selftest_gemm(const void* a_bf16_dev, const void* b_bf16_dev, float* c_dev, int M, int N,

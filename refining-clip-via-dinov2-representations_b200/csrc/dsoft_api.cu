@@ -827,6 +827,93 @@ extern "C" int dsoft_profile_read(double* ms_sum, int* counts, int n) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// fork/join of independent tile kernels
+//
+// The tile kernels of one pass are mutually independent (they read the gathered table / statistics and write
+// disjoint partial buffers), and every launch ends in a partially filled last wave. Launching them on forked
+// side streams lets the next kernel's CTAs fill that tail; one CTA per SM (smem + 512 TMEM columns) means
+// kernels never co-reside on an SM, so this is back-to-back execution without the idle tails. The side
+// streams are joined back into the caller's stream before the entry point returns, so the caller sees plain
+// stream-ordered semantics (and stream capture records a fork/join graph). Per-kernel timing
+// (dsoft_profile_enable) forces serial launches so that each duration is an isolated measurement.
+// ------------------------------------------------------------------------------------------------
+static const int NSIDE = 3;
+static int g_concurrency = -1;  // -1: read DSOFT_CONCURRENCY on first use (default on)
+
+extern "C" int dsoft_set_concurrency(int on) {
+  g_concurrency = on ? 1 : 0;
+  return 0;
+}
+
+static bool concurrency_on() {
+  if (g_concurrency < 0) {
+    const char* e = getenv("DSOFT_CONCURRENCY");
+    g_concurrency = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_concurrency == 1 && !g_prof.on;
+}
+
+struct SideStreams {
+  bool ready = false;
+  cudaStream_t s[NSIDE];
+  cudaEvent_t fork, join[NSIDE];
+};
+
+// one set per (host thread, device): events are re-recorded on every call
+static int side_streams(SideStreams** out) {
+  static thread_local SideStreams table[64];
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(DSOFT_EINVAL, "device ordinal %d out of range", dev);
+  SideStreams& ss = table[dev];
+  if (!ss.ready) {
+    for (int i = 0; i < NSIDE; ++i) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&ss.s[i], cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&ss.join[i], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+    ss.ready = true;
+  }
+  *out = &ss;
+  return 0;
+}
+
+struct Fork {
+  cudaStream_t main_st = nullptr;
+  SideStreams* ss = nullptr;
+  bool forked[NSIDE] = {false, false, false};
+  int begin(cudaStream_t st) {
+    main_st = st;
+    if (!concurrency_on()) return 0;
+    int rc = side_streams(&ss);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(ss->fork, main_st));
+    return 0;
+  }
+  // lane 0 is the caller's stream; lanes 1..NSIDE are side streams ordered after the fork point
+  int lane(int i, cudaStream_t* out) {
+    if (!ss || i <= 0) { *out = main_st; return 0; }
+    const int k = (i - 1) % NSIDE;
+    if (!forked[k]) {
+      CUDA_TRY(cudaStreamWaitEvent(ss->s[k], ss->fork, 0));
+      forked[k] = true;
+    }
+    *out = ss->s[k];
+    return 0;
+  }
+  int join() {
+    if (!ss) return 0;
+    for (int k = 0; k < NSIDE; ++k) {
+      if (!forked[k]) continue;
+      CUDA_TRY(cudaEventRecord(ss->join[k], ss->s[k]));
+      CUDA_TRY(cudaStreamWaitEvent(main_st, ss->join[k], 0));
+      forked[k] = false;
+    }
+    return 0;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
 // Forward tile kernels run as CTA pairs (cluster of 2 consecutive row blocks, cta_group::2 MMAs).
@@ -989,21 +1076,12 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
   if ((rc = set_smem(dsoft_fwd_kernel<MODE_CLIP, 2>, FWD_SMEM_BYTES))) return rc;
   if ((rc = set_smem(dsoft_fwd_kernel<MODE_SOFT, 2>, FWD_SMEM_BYTES))) return rc;
 
+  // the three tile kernels are independent: fork them (largest first), join before the finalize
+  Fork fk;
+  if ((rc = fk.begin(st))) return rc;
+  cudaStream_t ks = st;
+  int lane = 0;
   FwdParams P;
-  // image -> text (loss.py:266/272) and text -> image (loss.py:267/273)
-  fill_clip_fwd(p, P, 0, 1, S + p->st_scal, X + p->sc_pc_it, S + p->st_diag);
-  {
-    ProfScope ps(PK_FWD_CLIP_IT, st);
-    if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_CLIP, 2>, rbs, p->f_clip.nsplit, st, tm, P))) return rc;
-  }
-  CUDA_TRY(cudaGetLastError());
-  fill_clip_fwd(p, P, 1, 0, S + p->st_scal, X + p->sc_pc_ti, S + p->st_diag);
-  {
-    ProfScope ps(PK_FWD_CLIP_TI, st);
-    if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_CLIP, 2>, rbs, p->f_clip.nsplit, st, tm, P))) return rc;
-  }
-  CUDA_TRY(cudaGetLastError());
-
   if (p->have_soft) {
     memset(&P, 0, sizeof(P));
     P.nprod = p->have_text ? 3 : 2;
@@ -1026,12 +1104,30 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
     P.rinv[1] = S + p->st_rinv_z;
     P.rinv[2] = S + p->st_rinv_t;
     P.part = X + p->sc_ps;
+    if ((rc = fk.lane(lane++, &ks))) return rc;
     {
-      ProfScope ps(PK_FWD_SOFT, st);
-      if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_SOFT, 2>, rbs, p->f_soft.nsplit, st, tm, P))) return rc;
+      ProfScope ps(PK_FWD_SOFT, ks);
+      if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_SOFT, 2>, rbs, p->f_soft.nsplit, ks, tm, P))) return rc;
     }
     CUDA_TRY(cudaGetLastError());
   }
+  // image -> text (loss.py:266/272) and text -> image (loss.py:267/273)
+  fill_clip_fwd(p, P, 0, 1, S + p->st_scal, X + p->sc_pc_it, S + p->st_diag);
+  if ((rc = fk.lane(lane++, &ks))) return rc;
+  {
+    ProfScope ps(PK_FWD_CLIP_IT, ks);
+    if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_CLIP, 2>, rbs, p->f_clip.nsplit, ks, tm, P))) return rc;
+  }
+  CUDA_TRY(cudaGetLastError());
+  // same diagonal as the image -> text launch (which may run concurrently): only that one stores it
+  fill_clip_fwd(p, P, 1, 0, S + p->st_scal, X + p->sc_pc_ti, nullptr);
+  if ((rc = fk.lane(lane++, &ks))) return rc;
+  {
+    ProfScope ps(PK_FWD_CLIP_TI, ks);
+    if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_CLIP, 2>, rbs, p->f_clip.nsplit, ks, tm, P))) return rc;
+  }
+  CUDA_TRY(cudaGetLastError());
+  if ((rc = fk.join())) return rc;
 
   FinFwdArgs fa;
   fa.b = b;
@@ -1103,38 +1199,11 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
     P.row_only = p->row_only;
     P.scal = S + p->st_scal;
   };
-  // ---- CLIP, image rows: d image = s/(2b) sum_j (p_it[a,j] + p_ti[j,a]) T_j - ...
-  base(p->b_clip, 0, p->B, p->ntiles_g);
-  P.nprod = 1;
-  P.a_map[0] = 0;
-  P.b_map[0] = 1;
-  P.kchunks[0] = ceil_div(p->sh.D, BK);
-  P.dout = p->sh.D;
-  P.want_ds = 1;
-  if ((rc = vmap_for(p->v_offT, p->sh.D))) return rc;
-  P.lse_row = lse_loc + 0 * b;
-  P.lse_col = lsec + 1 * p->Bcol;
-  P.acc_part = X + p->sc_acc1;
-  P.ds_part = X + p->sc_ds1;
-  {
-    ProfScope ps(PK_BWD_CLIP_I, st);
-    if ((rc = launch_bwd(dsoft_bwd_kernel<MODE_CLIP>, p->nch_clip, rbs, p->b_clip.nsplit, st, tm, vmap, P))) return rc;
-  }
-  CUDA_TRY(cudaGetLastError());
-  // ---- CLIP, text rows
-  P.a_map[0] = 1;
-  P.b_map[0] = 0;
-  if ((rc = vmap_for(p->v_offI, p->sh.D))) return rc;
-  P.lse_row = lse_loc + 1 * b;
-  P.lse_col = lsec + 0 * p->Bcol;
-  P.acc_part = X + p->sc_acc2;
-  P.ds_part = X + p->sc_ds2;
-  {
-    ProfScope ps(PK_BWD_CLIP_T, st);
-    if ((rc = launch_bwd(dsoft_bwd_kernel<MODE_CLIP>, p->nch_clip, rbs, p->b_clip.nsplit, st, tm, vmap, P))) return rc;
-  }
-  CUDA_TRY(cudaGetLastError());
-
+  // the four tile kernels are independent: fork them (largest first), join before the finalize
+  Fork fk;
+  if ((rc = fk.begin(st))) return rc;
+  cudaStream_t ks = st;
+  int lane = 0;
   if (p->have_soft) {
     base(p->b_stu, p->s_col0, p->s_ncols, p->ntiles_s);
     P.nprod = 2;
@@ -1153,9 +1222,10 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
     P.rinv_d = S + p->st_rinv_d;
     P.rinv_y = S + p->st_rinv_z;
     P.acc_part = X + p->sc_acc3;
+    if ((rc = fk.lane(lane++, &ks))) return rc;
     {
-      ProfScope ps(PK_BWD_STU, st);
-      if ((rc = launch_bwd(dsoft_bwd_kernel<MODE_SOFT>, p->nch_stu, rbs, p->b_stu.nsplit, st, tm, vmap, P))) return rc;
+      ProfScope ps(PK_BWD_STU, ks);
+      if ((rc = launch_bwd(dsoft_bwd_kernel<MODE_SOFT>, p->nch_stu, rbs, p->b_stu.nsplit, ks, tm, vmap, P))) return rc;
     }
     CUDA_TRY(cudaGetLastError());
     if (p->have_text) {
@@ -1176,14 +1246,51 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
       P.rinv_d = S + p->st_rinv_d;
       P.rinv_y = S + p->st_rinv_t;
       P.acc_part = X + p->sc_acc4;
+      if ((rc = fk.lane(lane++, &ks))) return rc;
       {
-        ProfScope ps(PK_BWD_TXT, st);
-        if ((rc = launch_bwd(dsoft_bwd_kernel<MODE_SOFT>, p->nch_txt, rbs, p->b_txt.nsplit, st, tm, vmap, P)))
+        ProfScope ps(PK_BWD_TXT, ks);
+        if ((rc = launch_bwd(dsoft_bwd_kernel<MODE_SOFT>, p->nch_txt, rbs, p->b_txt.nsplit, ks, tm, vmap, P)))
           return rc;
       }
       CUDA_TRY(cudaGetLastError());
     }
   }
+
+  // ---- CLIP, image rows: d image = s/(2b) sum_j (p_it[a,j] + p_ti[j,a]) T_j - ...
+  base(p->b_clip, 0, p->B, p->ntiles_g);
+  P.nprod = 1;
+  P.a_map[0] = 0;
+  P.b_map[0] = 1;
+  P.kchunks[0] = ceil_div(p->sh.D, BK);
+  P.dout = p->sh.D;
+  P.want_ds = 1;
+  if ((rc = vmap_for(p->v_offT, p->sh.D))) return rc;
+  P.lse_row = lse_loc + 0 * b;
+  P.lse_col = lsec + 1 * p->Bcol;
+  P.acc_part = X + p->sc_acc1;
+  P.ds_part = X + p->sc_ds1;
+  if ((rc = fk.lane(lane++, &ks))) return rc;
+  {
+    ProfScope ps(PK_BWD_CLIP_I, ks);
+    if ((rc = launch_bwd(dsoft_bwd_kernel<MODE_CLIP>, p->nch_clip, rbs, p->b_clip.nsplit, ks, tm, vmap, P))) return rc;
+  }
+  CUDA_TRY(cudaGetLastError());
+  // ---- CLIP, text rows
+  P.a_map[0] = 1;
+  P.b_map[0] = 0;
+  if ((rc = vmap_for(p->v_offI, p->sh.D))) return rc;
+  P.lse_row = lse_loc + 1 * b;
+  P.lse_col = lsec + 0 * p->Bcol;
+  P.acc_part = X + p->sc_acc2;
+  P.ds_part = X + p->sc_ds2;
+  if ((rc = fk.lane(lane++, &ks))) return rc;
+  {
+    ProfScope ps(PK_BWD_CLIP_T, ks);
+    if ((rc = launch_bwd(dsoft_bwd_kernel<MODE_CLIP>, p->nch_clip, rbs, p->b_clip.nsplit, ks, tm, vmap, P))) return rc;
+  }
+  CUDA_TRY(cudaGetLastError());
+
+  if ((rc = fk.join())) return rc;
 
   FinBwdArgs fa;
   memset(&fa, 0, sizeof(fa));

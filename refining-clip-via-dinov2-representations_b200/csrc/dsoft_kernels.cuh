@@ -350,7 +350,7 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       if (li < P.b) {
         P.part[(0 * P.npart + sp) * P.b + li] = m;
         P.part[(1 * P.npart + sp) * P.b + li] = sum;
-        if (have_dg) P.diag[li] = dg;
+        if (have_dg && P.diag) P.diag[li] = dg;
       }
     } else {
       const float cq = P.rinv[0][gi] * P.scal[SC_ITT_L2];

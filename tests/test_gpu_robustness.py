@@ -105,3 +105,42 @@ def test_cuda_graph_capture_and_replay(pkg):
     for a, b in zip(eager, static):
         assert torch.equal(a, b)
     assert not torch.equal(replay_flipped[1], eager[1])
+
+
+def test_forked_and_serial_launches_agree_bitwise(pkg):
+    """The independent tile kernels run on forked streams by default (include/dsoft.h, dsoft_set_concurrency);
+    serial launches on the caller's stream must give bit-identical losses and gradients, also when the caller's
+    stream is not the default stream."""
+    from dinosoft_b200 import _cabi
+
+    lib = _cabi.lib()
+    img, txt, dino = _inputs(B=640, D=128, Dd=192, seed=5)
+    args = make_args(text_lambda=0.5, use_projection=True)
+    res = []
+    side = torch.cuda.Stream()
+    try:
+        for on, stream in ((1, None), (0, None), (1, side)):
+            lib.dsoft_set_concurrency(on)
+            loss = pkg.ClipLossWithDINOEnhancements()
+            torch.manual_seed(0)  # same lazily created MLP head in every variant
+            loss.init_proj(img.shape[1], dino.shape[1], img.device, projection_type="mlp")
+            im = img.clone().requires_grad_(True)
+            tx = txt.clone().requires_grad_(True)
+            sc = torch.tensor(25.0, device="cuda", requires_grad=True)
+            ctx = torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream())
+            if stream is not None:
+                stream.wait_stream(torch.cuda.current_stream())
+            with ctx:
+                o = loss(im, tx, sc, dino, args, output_dict=True)
+                o["total_loss"].backward()
+            torch.cuda.synchronize()
+            res.append((o["total_loss"].detach().clone(), im.grad.clone(), tx.grad.clone(), sc.grad.clone(),
+                        [prm.grad.clone() for prm in loss.parameters()]))
+    finally:
+        lib.dsoft_set_concurrency(1)
+    for other in res[1:]:
+        assert torch.equal(res[0][0], other[0])
+        assert torch.equal(res[0][1], other[1]) and torch.equal(res[0][2], other[2])
+        assert torch.equal(res[0][3], other[3])
+        for a, b in zip(res[0][4], other[4]):
+            assert torch.equal(a, b)
