@@ -37,7 +37,8 @@ sys.path.insert(0, ROOT)
 METRIC = "dino_soft_loss_fwd_bwd_samples_per_sec"
 GLOBAL_B, D_CLIP, D_DINO = 32768, 512, 768
 KERNEL_NAMES = ["fwd_clip_i2t", "fwd_clip_t2i", "fwd_soft", "bwd_clip_image", "bwd_clip_text",
-                "bwd_student", "bwd_text"]
+                "bwd_student", "bwd_text", "bwd_build_g_clip", "bwd_build_g_soft"]
+NK = len(KERNEL_NAMES)
 LOSS_ARGS = dict(use_projection=True, projection_type="mlp", lambda_soft=0.5, soft_mode="kl_teacher",
                  soft_dino_to_text=True, text_lambda=0.5, text_student_temp=0.02, teacher_temp=0.15,
                  lambda_original=1.0, lambda_weighted=0.0)
@@ -278,9 +279,9 @@ def run_ours(args):
     barrier()
     ms_serial = p0.elapsed_time(p1)
     clocks = sampler.stop() if rank == 0 else None
-    ms_sum = (C.c_double * 7)()
-    cnt = (C.c_int * 7)()
-    _cabi.check(lib.dsoft_profile_read(ms_sum, cnt, 7), "dsoft_profile_read")
+    ms_sum = (C.c_double * NK)()
+    cnt = (C.c_int * NK)()
+    _cabi.check(lib.dsoft_profile_read(ms_sum, cnt, NK), "dsoft_profile_read")
     lib.dsoft_profile_enable(0)
 
     # ---- e2e: pinned host inputs -> H2D -> module -> loss scalars back to the host, every step
@@ -346,9 +347,9 @@ def run_ours(args):
         from dinosoft_b200.loss import _cuda_backend
 
         plan = next(iter(_cuda_backend._plans.values()))
-        alg = (C.c_double * 7)()
-        exe = (C.c_double * 7)()
-        _cabi.check(lib.dsoft_plan_kernel_flops(plan.handle, alg, exe, 7), "dsoft_plan_kernel_flops")
+        alg = (C.c_double * NK)()
+        exe = (C.c_double * NK)()
+        _cabi.check(lib.dsoft_plan_kernel_flops(plan.handle, alg, exe, NK), "dsoft_plan_kernel_flops")
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -374,7 +375,7 @@ def run_ours(args):
         dk = KERNEL_NAMES.index(dom)
         dom_ms = ms_sum[dk] / cnt[dk]
         achieved = alg[dk] / dom_ms / 1e9
-        tile_ms = sum(ms_sum[k] for k in range(7)) / prof_steps
+        tile_ms = sum(ms_sum[k] for k in range(NK)) / prof_steps
         step_ms = ms / args.steps
         step_alg_tflops = plan.flops / step_ms / 1e9  # this rank's algorithmic FLOPs / step time
         cpu_baseline = None

@@ -37,6 +37,11 @@ extern "C" {
 #define DSOFT_F_TEXT 2u        /* text-text KL term enabled (loss.py:387-397)                      */
 #define DSOFT_F_SOFT_LOCAL 4u  /* soft terms over the local b x b block only (reference at W>1)    */
 #define DSOFT_F_ROW_ONLY 8u    /* gather_with_grad=False: gathered columns carry no gradient       */
+#define DSOFT_F_GMAT 16u       /* two-phase backward: the similarity tiles are recomputed by the forward
+                                  kernels' main loop, written out as fp16 logit-gradient matrices (scratch:
+                                  2 bytes per element of the local [b x columns] blocks), and the feature
+                                  gradients come from plain M=256 x N=256 gradient GEMMs.  Same results as
+                                  the fused backward, faster when the scratch memory can be spared.       */
 
 /* element types accepted by dsoft_pack */
 #define DSOFT_DT_F32 0
@@ -72,11 +77,14 @@ void dsoft_plan_destroy(dsoft_plan_t* plan);
  *              block (rows rank*b ..) is written by dsoft_pack, the rest by the caller's all-gather
  *              (this is the buffer `gather_features` loss.py:23-81 would have produced, in bf16);
  *   state    : small per-call state that must survive from forward to backward;
- *   scratch  : partial statistics / partial gradients, free to reuse after each call. */
+ *   scratch  : partial statistics / partial gradients (and, with DSOFT_F_GMAT, the fp16 logit-gradient
+ *              matrices), free to reuse after each call.  dsoft_forward only touches the first
+ *              dsoft_plan_forward_scratch_bytes of it. */
 size_t dsoft_plan_gathered_row_elems(const dsoft_plan_t* plan);
 size_t dsoft_plan_gathered_bytes(const dsoft_plan_t* plan);
 size_t dsoft_plan_state_bytes(const dsoft_plan_t* plan);
 size_t dsoft_plan_scratch_bytes(const dsoft_plan_t* plan);
+size_t dsoft_plan_forward_scratch_bytes(const dsoft_plan_t* plan);
 /* Algorithmic FLOPs of one fwd+bwd evaluation for this rank (SURVEY.md 8(d) formula / world). */
 double dsoft_plan_algorithmic_flops(const dsoft_plan_t* plan);
 /* FLOPs of the 7 tile-kernel launches of one fwd+bwd for this rank, in dsoft_profile_read order:
@@ -119,7 +127,8 @@ int dsoft_backward(const dsoft_plan_t* plan, const void* gathered_dev, const voi
 
 /* Optional timing of the tile kernels with CUDA events on the launching stream (bench.py roofline).
  * dsoft_profile_read synchronises the device, returns summed milliseconds and launch counts per kernel
- * kind (7 slots, order above) since the last read, and resets the recorder. */
+ * kind since the last read, and resets the recorder.  9 slots: the 7 kinds above (with DSOFT_F_GMAT slots
+ * 3..6 are the gradient GEMMs) followed by the CLIP (2 launches) and the soft logit-gradient kernels. */
 int dsoft_profile_enable(int on);
 int dsoft_profile_read(double* ms_sum, int* counts, int n);
 

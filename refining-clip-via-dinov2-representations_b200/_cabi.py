@@ -9,7 +9,7 @@ import threading
 
 from . import _build
 
-DSOFT_F_SOFT, DSOFT_F_TEXT, DSOFT_F_SOFT_LOCAL, DSOFT_F_ROW_ONLY = 1, 2, 4, 8
+DSOFT_F_SOFT, DSOFT_F_TEXT, DSOFT_F_SOFT_LOCAL, DSOFT_F_ROW_ONLY, DSOFT_F_GMAT = 1, 2, 4, 8, 16
 DT_F32, DT_BF16, DT_F16 = 0, 1, 2
 
 
@@ -36,6 +36,7 @@ PROTOTYPES = {
     "dsoft_plan_gathered_bytes": (C.c_size_t, [C.c_void_p]),
     "dsoft_plan_state_bytes": (C.c_size_t, [C.c_void_p]),
     "dsoft_plan_scratch_bytes": (C.c_size_t, [C.c_void_p]),
+    "dsoft_plan_forward_scratch_bytes": (C.c_size_t, [C.c_void_p]),
     "dsoft_plan_algorithmic_flops": (C.c_double, [C.c_void_p]),
     "dsoft_plan_kernel_flops": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]),
     "dsoft_profile_enable": (C.c_int, [C.c_int]),

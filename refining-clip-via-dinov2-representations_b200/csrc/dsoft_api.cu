@@ -12,6 +12,7 @@
 #include <new>
 
 #include "dsoft_kernels.cuh"
+#include "dsoft_gy.cuh"
 
 using namespace dsoft;
 
@@ -65,6 +66,11 @@ struct dsoft_plan {
       sc_dsrow, sc_v16, sc_total;
   // fp16 gradient-operand buffer [B][v_row]: text | image | normalised student | normalised text
   int v_offT, v_offI, v_offZn, v_offTn, v_row;
+  // DSOFT_F_GMAT: two-phase backward through fp16 logit-gradient matrices in scratch
+  int gmat;
+  int pitch_c, pitch_s;  // columns of the CLIP / soft G matrices: multiples of 64
+  size_t sc_Gci, sc_Gct, sc_Gs, sc_Gx, sc_fwd_total;
+  SplitPlan g_clip, g_stu, g_txt;  // K splits of the gradient GEMMs (tps = K steps per split)
 };
 
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -92,6 +98,19 @@ static SplitPlan choose_split(int row_blocks, int nchunk, int ntiles, int num_sm
     }
   }
   return best;
+}
+
+// K split of a gradient GEMM: `tiles` CTA pairs per split; fill ~2 waves of pair slots when there are few.
+static SplitPlan choose_gy_split(int tiles, int ksteps, int num_sms) {
+  const int slots = std::max(1, num_sms / 2);
+  int ns = 1;
+  if (tiles < 2 * slots) ns = std::max(1, (2 * slots) / std::max(1, tiles));
+  ns = std::min(ns, std::max(1, ksteps / 4));  // at least 4 K steps (256 columns) per split
+  ns = std::min(ns, 32);
+  SplitPlan sp;
+  sp.tps = ceil_div(ksteps, ns);
+  sp.nsplit = ceil_div(ksteps, sp.tps);
+  return sp;
 }
 
 extern "C" int dsoft_version(void) { return DSOFT_VERSION; }
@@ -165,6 +184,15 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   p->b_clip = choose_split(rbs, p->nch_clip, p->ntiles_g, sms);
   p->b_stu = choose_split(rbs, p->nch_stu, p->ntiles_s, sms);
   p->b_txt = choose_split(rbs, p->nch_txt, p->ntiles_s, sms);
+  p->gmat = (sh->flags & DSOFT_F_GMAT) != 0;
+  p->pitch_c = ceil_div(p->B, 64) * 64;
+  p->pitch_s = ceil_div(p->s_ncols, 64) * 64;
+  if (p->gmat) {
+    const int pairs = ceil_div(rbs, 2);
+    p->g_clip = choose_gy_split(pairs * ceil_div(sh->D, GY_N), p->pitch_c / 64, sms);
+    p->g_stu = choose_gy_split(pairs * ceil_div(p->Dz, GY_N), p->pitch_s / 64, sms);
+    p->g_txt = choose_gy_split(pairs * ceil_div(sh->D, GY_N), p->pitch_s / 64, sms);
+  }
 
   // ---- state (floats)
   size_t o = 0;
@@ -184,13 +212,24 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   p->sc_pc_ti = take(2 * 2 * p->f_clip.nsplit * b);
   p->sc_ps = take(soft ? 7 * 2 * p->f_soft.nsplit * b : 0);
   p->sc_rowloss = take(3 * b);
-  p->sc_acc1 = take(static_cast<size_t>(p->b_clip.nsplit) * b * sh->D);
-  p->sc_acc2 = take(static_cast<size_t>(p->b_clip.nsplit) * b * sh->D);
-  p->sc_acc3 = take(soft ? static_cast<size_t>(p->b_stu.nsplit) * b * p->Dz : 0);
-  p->sc_acc4 = take(p->have_text ? static_cast<size_t>(p->b_txt.nsplit) * b * sh->D : 0);
-  p->sc_ds1 = take(2 * X_MAXC * p->b_clip.nsplit * b);
-  p->sc_ds2 = take(2 * X_MAXC * p->b_clip.nsplit * b);
+  p->sc_fwd_total = o;  // the forward only needs the statistics partials above
+  const size_t ns_c = p->gmat ? p->g_clip.nsplit : p->b_clip.nsplit;
+  const size_t ns_s = p->gmat ? p->g_stu.nsplit : p->b_stu.nsplit;
+  const size_t ns_x = p->gmat ? p->g_txt.nsplit : p->b_txt.nsplit;
+  p->sc_acc1 = take(ns_c * b * sh->D);
+  p->sc_acc2 = take(ns_c * b * sh->D);
+  p->sc_acc3 = take(soft ? ns_s * b * p->Dz : 0);
+  p->sc_acc4 = take(p->have_text ? ns_x * b * sh->D : 0);
+  p->sc_ds1 = take(p->gmat ? 2 * p->f_clip.nsplit * b : 2 * X_MAXC * p->b_clip.nsplit * b);
+  p->sc_ds2 = take(p->gmat ? 2 * p->f_clip.nsplit * b : 2 * X_MAXC * p->b_clip.nsplit * b);
   p->sc_dsrow = take(b);
+  if (p->gmat) {
+    const size_t bpad = static_cast<size_t>(rbs) * BM;  // blocked layout holds whole 128-row blocks
+    p->sc_Gci = take(bpad * p->pitch_c / 2);
+    p->sc_Gct = take(bpad * p->pitch_c / 2);
+    p->sc_Gs = take(soft ? bpad * p->pitch_s / 2 : 0);
+    p->sc_Gx = take(p->have_text ? bpad * p->pitch_s / 2 : 0);
+  }
   p->v_offT = 0;
   p->v_offI = sh->D;
   p->v_offZn = 2 * sh->D;
@@ -211,6 +250,7 @@ extern "C" size_t dsoft_plan_gathered_bytes(const dsoft_plan_t* p) {
 }
 extern "C" size_t dsoft_plan_state_bytes(const dsoft_plan_t* p) { return p ? p->st_total * 4 : 0; }
 extern "C" size_t dsoft_plan_scratch_bytes(const dsoft_plan_t* p) { return p ? p->sc_total * 4 : 0; }
+extern "C" size_t dsoft_plan_forward_scratch_bytes(const dsoft_plan_t* p) { return p ? p->sc_fwd_total * 4 : 0; }
 
 extern "C" double dsoft_plan_algorithmic_flops(const dsoft_plan_t* p) {
   if (!p) return 0.0;
@@ -241,6 +281,13 @@ extern "C" int dsoft_plan_kernel_flops(const dsoft_plan_t* p, double* algorithmi
     algorithmic[6] = 2.0 * b * Bs * D;
     executed[6] = 2.0 * b * Bs * (chunk_groups(p->nch_txt) * (D + Dd) + D);
   }
+  if (p->gmat) {
+    // two-phase backward: slots 3..6 are the plain gradient GEMMs, slots 7 / 8 the logit-gradient kernels
+    // (every similarity product recomputed once; the teacher product once for student and text)
+    for (int k = 3; k < 7; ++k) executed[k] = algorithmic[k];
+    if (n > 7) executed[7] = 2.0 * (2.0 * b * Bc * D);
+    if (n > 8 && p->have_soft) executed[8] = 2.0 * b * Bs * (Dz + Dd + (p->have_text ? D : 0.0));
+  }
   return 0;
 }
 
@@ -250,6 +297,9 @@ extern "C" int dsoft_plan_launches_forward(const dsoft_plan_t* p) {
 }
 extern "C" int dsoft_plan_launches_backward(const dsoft_plan_t* p) {
   if (!p) return 0;
+  if (p->gmat)
+    return 2 /*relayout, fp16 operands*/ + 2 /*clip G*/ + 2 /*clip GEMMs*/ +
+           (p->have_soft ? 2 : 0) /*soft G, student GEMM*/ + (p->have_text ? 1 : 0) + 1 /*finalize*/;
   return 2 /*relayout, fp16 operands*/ + 2 * chunk_groups(p->nch_clip) + (p->have_soft ? chunk_groups(p->nch_stu) : 0) +
          (p->have_text ? chunk_groups(p->nch_txt) : 0) + 1 /*finalize*/;
 }
@@ -776,7 +826,7 @@ __global__ void __launch_bounds__(128) finalize_bwd_kernel(FinBwdArgs a) {
 // optional per-kernel timing (bench.py's roofline): CUDA events around each tile-kernel launch
 // ------------------------------------------------------------------------------------------------
 enum { PK_FWD_CLIP_IT = 0, PK_FWD_CLIP_TI, PK_FWD_SOFT, PK_BWD_CLIP_I, PK_BWD_CLIP_T, PK_BWD_STU, PK_BWD_TXT,
-       PK_COUNT };
+       PK_BWD_GCLIP, PK_BWD_GSOFT, PK_COUNT };
 static const int PROF_MAX = 4096;
 static struct {
   int on = 0;
@@ -1152,6 +1202,133 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
   return 0;
 }
 
+
+// Gradient GEMM launch: acc[split][b][dout] = G[b][pitch] . Y16[ycol0 + ..][voff .. voff + dout)
+static int launch_gy(const dsoft_plan* p, const __half* G, int pitch, const __half* v16, int voff, int dout,
+                     int ycol0, const SplitPlan& sp, float* acc, cudaStream_t st) {
+  CUtensorMap gmap, vmap;
+  int rc;
+  // blocked G: 64 columns x (row blocks * K tiles * 128) rows, one 16 KiB box per (row block, K tile)
+  const int g_rows = ceil_div(p->sh.b, BM) * (pitch / BK) * BM;
+  if ((rc = make_map(&gmap, G, g_rows, BK, BK, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, BM))) return rc;
+  if ((rc = make_map(&vmap, v16 + voff, p->B, dout, p->v_row, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 64))) return rc;
+  GyParams P;
+  P.b = p->sh.b;
+  P.dout = dout;
+  P.ksteps = pitch / BK;
+  P.steps_per_split = sp.tps;
+  P.nsplit = sp.nsplit;
+  P.ycol0 = ycol0;
+  P.acc_part = acc;
+  const int pairs = ceil_div(ceil_div(p->sh.b, BM), 2);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2, ceil_div(dout, GY_N), pairs * sp.nsplit);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = GY_SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, dsoft_gy_kernel, gmap, vmap, P));
+  return 0;
+}
+
+// DSOFT_F_GMAT backward.  Phase 1: the forward main loop again, its epilogue writing fp16 logit-gradient
+// tiles; phase 2: gradient GEMMs.  Three independent lanes on forked streams:
+//   soft (G kernel -> student GEMM -> text GEMM) | CLIP image rows (G -> GEMM) | CLIP text rows (G -> GEMM)
+static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* S, float* X, const float* lse_loc,
+                              const float* lsec, const __half* v16, cudaStream_t st) {
+  const int b = p->sh.b;
+  const int rbs = ceil_div(b, BM);
+  int rc;
+  TileMaps tm;
+  if ((rc = make_maps(p, gathered, &tm, 64))) return rc;
+  if ((rc = set_smem(dsoft_gy_kernel, GY_SMEM_BYTES))) return rc;
+  if ((rc = set_smem(dsoft_fwd_kernel<MODE_CLIP_G, 2>, FWD_SMEM_BYTES))) return rc;
+  if ((rc = set_smem(dsoft_fwd_kernel<MODE_SOFT_G, 2>, FWD_SMEM_BYTES))) return rc;
+  __half* Gci = reinterpret_cast<__half*>(X + p->sc_Gci);
+  __half* Gct = reinterpret_cast<__half*>(X + p->sc_Gct);
+  __half* Gs = reinterpret_cast<__half*>(X + p->sc_Gs);
+  __half* Gx = reinterpret_cast<__half*>(X + p->sc_Gx);
+  Fork fk;
+  if ((rc = fk.begin(st))) return rc;
+  cudaStream_t ks = st;
+  int lane = 0;
+  FwdParams P;
+  if (p->have_soft) {
+    if ((rc = fk.lane(lane++, &ks))) return rc;
+    memset(&P, 0, sizeof(P));
+    P.nprod = p->have_text ? 3 : 2;
+    P.bn = BN;
+    P.a_map[0] = P.b_map[0] = 3;
+    P.a_map[1] = P.b_map[1] = 2;
+    P.a_map[2] = P.b_map[2] = 1;
+    P.kchunks[0] = ceil_div(p->sh.Dd, BK);
+    P.kchunks[1] = ceil_div(p->Dz, BK);
+    P.kchunks[2] = ceil_div(p->sh.D, BK);
+    P.row0 = p->sh.rank * b;
+    P.b = b;
+    P.col0 = p->s_col0;
+    P.ncols = p->s_ncols;
+    P.ntiles = p->ntiles_s;
+    P.tiles_per_split = p->f_soft.tps;
+    P.npart = 2 * p->f_soft.nsplit;
+    P.scal = S + p->st_scal;
+    P.rinv[0] = S + p->st_rinv_d;
+    P.rinv[1] = S + p->st_rinv_z;
+    P.rinv[2] = S + p->st_rinv_t;
+    for (int k = 0; k < 3; ++k) {
+      P.lse_row[k] = lse_loc + (2 + k) * b;
+      P.lse_col[k] = lsec + static_cast<size_t>(2 + k) * p->Bcol;
+    }
+    P.gout[0] = Gs;
+    P.gout[1] = Gx;
+    P.g_pitch = p->pitch_s;
+    P.row_only = p->row_only;
+    P.rmin_idx[0] = SC_RMIN_Z;
+    P.rmin_idx[1] = SC_RMIN_T;
+    {
+      ProfScope ps(PK_BWD_GSOFT, ks);
+      if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_SOFT_G, 2>, rbs, p->f_soft.nsplit, ks, tm, P))) return rc;
+    }
+    {
+      ProfScope ps(PK_BWD_STU, ks);
+      if ((rc = launch_gy(p, Gs, p->pitch_s, v16, p->v_offZn, p->Dz, p->s_col0, p->g_stu, X + p->sc_acc3, ks)))
+        return rc;
+    }
+    if (p->have_text) {
+      ProfScope ps(PK_BWD_TXT, ks);
+      if ((rc = launch_gy(p, Gx, p->pitch_s, v16, p->v_offTn, p->sh.D, p->s_col0, p->g_txt, X + p->sc_acc4, ks)))
+        return rc;
+    }
+  }
+  for (int d = 0; d < 2; ++d) {  // d = 0: image rows (dI = G . T), d = 1: text rows (dT = G . I)
+    if ((rc = fk.lane(lane++, &ks))) return rc;
+    fill_clip_fwd(p, P, d == 0 ? 0 : 1, d == 0 ? 1 : 0, S + p->st_scal, nullptr, nullptr);
+    P.lse_row[0] = lse_loc + d * b;
+    P.lse_col[0] = lsec + static_cast<size_t>(1 - d) * p->Bcol;
+    P.gout[0] = d == 0 ? Gci : Gct;
+    P.g_pitch = p->pitch_c;
+    P.row_only = p->row_only;
+    P.ds_part = X + (d == 0 ? p->sc_ds1 : p->sc_ds2);
+    {
+      ProfScope ps(PK_BWD_GCLIP, ks);
+      if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_CLIP_G, 2>, rbs, p->f_clip.nsplit, ks, tm, P))) return rc;
+    }
+    {
+      ProfScope ps(d == 0 ? PK_BWD_CLIP_I : PK_BWD_CLIP_T, ks);
+      if ((rc = launch_gy(p, P.gout[0], p->pitch_c, v16, d == 0 ? p->v_offT : p->v_offI, p->sh.D, 0, p->g_clip,
+                          X + (d == 0 ? p->sc_acc1 : p->sc_acc2), ks)))
+        return rc;
+    }
+  }
+  return fk.join();
+}
+
 extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const void* state, void* scratch,
                               const float* lse_all, const float* gout, const float* lambdas, float* d_image,
                               float* d_text, float* d_student, float* d_scale, void* stream) {
@@ -1183,6 +1360,9 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
     return make_map(&vmap, v16 + voff, p->B, cols, p->v_row, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 64);
   };
 
+  if (p->gmat) {
+    if ((rc = backward_two_phase(p, gathered, S, X, lse_loc, lsec, v16, st))) return rc;
+  } else {
   if ((rc = set_smem(dsoft_bwd_kernel<MODE_CLIP>, BWD_SMEM_BYTES))) return rc;
   if ((rc = set_smem(dsoft_bwd_kernel<MODE_SOFT>, BWD_SMEM_BYTES))) return rc;
 
@@ -1291,6 +1471,7 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
   CUDA_TRY(cudaGetLastError());
 
   if ((rc = fk.join())) return rc;
+  }  // !p->gmat
 
   FinBwdArgs fa;
   memset(&fa, 0, sizeof(fa));
@@ -1306,10 +1487,10 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
   fa.have_text = p->have_text;
   fa.have_proj = p->have_proj;
   fa.row_only = p->row_only;
-  fa.ns_c = p->b_clip.nsplit;
-  fa.nds = 2 * p->b_clip.nsplit * chunk_cluster(p->nch_clip);
-  fa.ns_s = p->b_stu.nsplit;
-  fa.ns_x = p->b_txt.nsplit;
+  fa.ns_c = p->gmat ? p->g_clip.nsplit : p->b_clip.nsplit;
+  fa.nds = p->gmat ? 2 * p->f_clip.nsplit : 2 * p->b_clip.nsplit * chunk_cluster(p->nch_clip);
+  fa.ns_s = p->gmat ? p->g_stu.nsplit : p->b_stu.nsplit;
+  fa.ns_x = p->gmat ? p->g_txt.nsplit : p->b_txt.nsplit;
   fa.gathered = static_cast<const __nv_bfloat16*>(gathered);
   fa.acc1 = X + p->sc_acc1;
   fa.acc2 = X + p->sc_acc2;

@@ -37,6 +37,8 @@ constexpr float M_FLOOR = -1.0e4f;   // initial running max (log2 units); real l
 constexpr int MODE_CLIP = 0;
 constexpr int MODE_SOFT = 1;
 constexpr int MODE_RAW = 2;  // bring-up: forward stores the raw tile, backward uses G = raw dot products
+constexpr int MODE_CLIP_G = 3;  // forward main loop, epilogue writes the fp16 logit-gradient tile (two-phase bwd)
+constexpr int MODE_SOFT_G = 4;
 
 // scalar block computed on device by prep_scalars_kernel (no host sync on logit_scale)
 enum {
@@ -83,6 +85,15 @@ struct FwdParams {
   const float* rinv[3];  // per product: inverse L2 norms by global index (soft only)
   float* part;           // partial statistics [nstat][npart][b]
   float* diag;           // clip: raw dot product on the diagonal [b]
+  // ---- logit-gradient modes (MODE_CLIP_G / MODE_SOFT_G: first phase of the two-phase backward)
+  const float* lse_row[3];  // per product: LSE (log2) of this rank's rows (soft: 0 teacher, 1 student, 2 text)
+  const float* lse_col[3];  // per product: LSE by global column (clip: the OTHER direction's)
+  __half* gout[2];          // fp16 logit gradients, blocked [row block][64-col K tile][128 rows][64 cols]:
+                            // clip -> gout[0]; soft -> gout[0] student, gout[1] text
+  int g_pitch;              // columns of G (multiple of 64 >= ncols)
+  int row_only;             // gather_with_grad == False: drop the column-side terms
+  int rmin_idx[2];          // soft: SC_RMIN_Z, SC_RMIN_T (scale of the fp16 gradient operand)
+  float* ds_part;           // clip: d(logit_scale) row partials [npart][b]
 };
 
 struct BwdParams {
@@ -129,6 +140,26 @@ __device__ __forceinline__ void issue_s_stage(uint32_t tmem_d, uint32_t a_smem, 
   }
 }
 
+// element (local row li, column j) of a blocked fp16 logit-gradient matrix: K tiles of 64 columns, each
+// (row block, K tile) = one 16 KiB TMA box of the gradient GEMM's A operand
+__device__ __forceinline__ size_t g_index(int li, int j, int pitch) {
+  return ((static_cast<size_t>(li >> 7) * (pitch >> 6) + (j >> 6)) * BM + (li & 127)) * 64 + (j & 63);
+}
+
+// 32 consecutive logit gradients of one row -> fp16 -> global memory as two 32-byte stores (full sectors),
+// evict-first: read back once by the gradient GEMM, must not displace the operands in L2
+__device__ __forceinline__ void store_g32(__half* dst, const float (&g)[32]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    uint32_t w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = pack_f16x2(g[16 * i + 2 * k], g[16 * i + 2 * k + 1]);
+    asm volatile("st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 16 * i), "r"(w[0]),
+                 "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+  }
+}
+
 // ================================================================================================
 // Forward: per-row soft-max statistics
 // ================================================================================================
@@ -161,6 +192,17 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   uint64_t* s_empty = s_full + F_SLOTS;  // (CG = 2: the leader's copy collects both CTAs' epilogues)
   uint64_t* a_full = s_empty + F_SLOTS;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_full + 1);
+  // soft modes (streaming ring of 8 x 24 KiB = 192 KiB): the per-column vectors of a tile (inverse norms, and
+  // column LSEs in the G mode; 128 columns each) are staged by the producer with bulk copies into the 32 KiB
+  // the ring leaves free, COL_BUFS tiles deep.  The epilogue reads them as shared-memory broadcasts instead of
+  // ~16 dependent global loads per 32-column chunk (measured: those loads, not MUFU or the tensor pipe,
+  // bounded the epilogue).
+  constexpr bool kSoftMode = (MODE == MODE_SOFT || MODE == MODE_SOFT_G);
+  static_assert(!kSoftMode || CG == 2, "the column-vector buffers live in the hole the CG = 2 soft ring leaves");
+  constexpr int COL_VECS = 6, COL_BUFS = 4;
+  float* colbuf = reinterpret_cast<float*>(smem + 8 * 24576);            // [COL_BUFS][COL_VECS][128]
+  uint64_t* col_full = reinterpret_cast<uint64_t*>(colbuf + COL_BUFS * COL_VECS * BN);  // [COL_BUFS]
+  uint64_t* col_empty = col_full + COL_BUFS;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -182,6 +224,12 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       mbar_init(smem_u32(&s_empty[i]), CG * NUM_EPI_THREADS);
     }
     mbar_init(smem_u32(a_full), 1);
+    if constexpr (kSoftMode) {
+      for (int i = 0; i < COL_BUFS; ++i) {
+        mbar_init(smem_u32(&col_full[i]), 1);
+        mbar_init(smem_u32(&col_empty[i]), NUM_EPI_THREADS);
+      }
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_cg<CG>(smem_u32(tmem_holder), TMEM_COLS);
@@ -208,6 +256,24 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     }
     __syncwarp();
     for (int t = t0; t < t1; ++t) {
+      if constexpr (kSoftMode) {
+        const int n = t - t0;
+        const int cb = n % COL_BUFS;
+        mbar_wait(smem_u32(&col_empty[cb]), ((static_cast<uint32_t>(n / COL_BUFS)) & 1) ^ 1);
+        if (elect_one()) {
+          const uint32_t full = smem_u32(&col_full[cb]);
+          const int nvec = (MODE == MODE_SOFT_G ? 2 : 1) * P.nprod;
+          mbar_arrive_expect_tx(full, nvec * BN * 4);
+          float* dst = colbuf + cb * COL_VECS * BN;
+          const size_t c0 = static_cast<size_t>(P.col0) + static_cast<size_t>(t) * BN;
+          for (int p = 0; p < P.nprod; ++p) {
+            bulk_copy_g2s(smem_u32(dst + p * BN), P.rinv[p] + c0, BN * 4, full);
+            if constexpr (MODE == MODE_SOFT_G)
+              bulk_copy_g2s(smem_u32(dst + (3 + p) * BN), P.lse_col[p] + c0, BN * 4, full);
+          }
+        }
+        __syncwarp();
+      }
       for (int p = 0; p < P.nprod; ++p) {
         const CUtensorMap* am = &maps.m[P.a_map[p]];
         const CUtensorMap* bm = &maps.m[P.b_map[p]];
@@ -281,8 +347,15 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     const int sp = split * 2 + half;
     float v[32];
     auto release_slot = [&](int slot) {  // the MMA issuer lives in the pair's leader
-      if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&s_empty[slot]), 0));
-      else mbar_arrive(smem_u32(&s_empty[slot]));
+      if constexpr (CG == 2) {
+        // the G modes have global stores in flight: do not make the arrive wait for them
+        if constexpr (MODE == MODE_CLIP_G || MODE == MODE_SOFT_G)
+          mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&s_empty[slot]), 0));
+        else
+          mbar_arrive_cluster(mapa_shared(smem_u32(&s_empty[slot]), 0));
+      } else {
+        mbar_arrive(smem_u32(&s_empty[slot]));
+      }
     };
 
     if constexpr (MODE == MODE_RAW) {
@@ -352,6 +425,142 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
         P.part[(1 * P.npart + sp) * P.b + li] = sum;
         if (have_dg && P.diag) P.diag[li] = dg;
       }
+    } else if constexpr (MODE == MODE_CLIP_G) {
+      // G_aj = 2^(x - lse_row_a) + 2^(x - lse_col_j), j != a (the diagonal entry incl. its -2 one-hot part and
+      // the s/(2b) factor are applied in fp32 by finalize_bwd_kernel); ds_a = sum_j 2^(x - lse_row_a) dot_aj
+      const float s2 = P.scal[SC_SCALE_L2];
+      const float la = P.lse_row[0][min(li, P.b - 1)];
+      const bool row_only = P.row_only != 0;
+      const bool real_block = rb * BM < P.b;  // the odd pair member past the last row block owns no G rows
+      float dsacc = 0.f;
+      // column LSEs of the NEXT 32-column chunk are fetched while the current one is processed (two register
+      // buffers, loop fully unrolled so that they are addressed statically); launched with bn == 256 only
+      float4 lcA[8], lcB[8];
+      auto load_cols = [&](float4 (&d)[8], int gj0) {
+#pragma unroll
+        for (int e4 = 0; e4 < 8; ++e4) d[e4] = ldg_nc_v4_volatile(P.lse_col[0] + gj0 + 4 * e4);
+      };
+      if (t0 < t1) load_cols(lcA, P.col0 + t0 * 256 + half * 128);
+      int it = 0;
+      for (int t = t0; t < t1; ++t, ++it) {
+        const int slot = it % nslots;
+        const uint32_t use = static_cast<uint32_t>(it / nslots);
+        mbar_wait(smem_u32(&s_full[slot]), use & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int jrel0 = t * 256 + half * 128 + c * 32;
+          const int gj0 = P.col0 + jrel0;
+          tmem_ld32(lane_addr + slot * 256 + half * 128 + c * 32, v);
+          float4(&cur)[8] = (c & 1) ? lcB : lcA;
+          float4(&nxt)[8] = (c & 1) ? lcA : lcB;
+          if (c < 3) load_cols(nxt, gj0 + 32);
+          else if (t + 1 < t1) load_cols(nxt, P.col0 + (t + 1) * 256 + half * 128);
+          float g[32];
+#pragma unroll
+          for (int e4 = 0; e4 < 8; ++e4) {
+            const float ll[4] = {cur[e4].x, cur[e4].y, cur[e4].z, cur[e4].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int e = 4 * e4 + k;
+              const float x2 = v[e] * s2;
+              const float e1 = fast_exp2(x2 - la);
+              const float e2 = row_only ? 0.f : fast_exp2(x2 - ll[k]);
+              dsacc = fmaf(e1, v[e], dsacc);  // ragged columns carry dot = 0
+              g[e] = (gj0 + e == gi || jrel0 + e >= P.ncols) ? 0.f : e1 + e2;
+            }
+          }
+          if (real_block && jrel0 + 32 <= P.g_pitch) store_g32(P.gout[0] + g_index(li, jrel0, P.g_pitch), g);
+        }
+        tc_fence_before();
+        release_slot(slot);
+      }
+      if (li < P.b) P.ds_part[sp * P.b + li] = dsacc;
+    } else if constexpr (MODE == MODE_SOFT_G) {
+      // G_aj = [(2^(p-ls_a) + 2^(p-ls_j)) - (2^(q-lt_a) + 2^(q-lt_j))] / (||y_j|| sigma), j != a, for the
+      // student (-> gout[0]) and the text term (-> gout[1]) from ONE teacher tile
+      const int lic = min(li, P.b - 1);
+      const float cq = P.rinv[0][gi] * P.scal[SC_ITT_L2];
+      const float lt = P.lse_row[0][lic];
+      const bool row_only = P.row_only != 0;
+      const bool real_block = rb * BM < P.b;
+      float E[64];  // -(teacher terms) of this thread's 64 columns, kept across the student / text products
+      int it = 0;
+      for (int t = t0; t < t1; ++t, it += P.nprod) {
+        const int jt0 = t * BN + half * 64;
+        // this tile's column vectors (staged by the producer): [p] inverse norms, [3 + p] column LSEs
+        const int cb = (t - t0) % COL_BUFS;
+        mbar_wait(smem_u32(&col_full[cb]), static_cast<uint32_t>((t - t0) / COL_BUFS) & 1);
+        const float* cv = colbuf + cb * COL_VECS * BN + half * 64;
+        {
+          const int slot = (it + 0) % F_SLOTS;
+          mbar_wait(smem_u32(&s_full[slot]), static_cast<uint32_t>((it + 0) / F_SLOTS) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int gj0 = P.col0 + jt0 + c * 32;
+            tmem_ld32(lane_addr + slot * BN + half * 64 + c * 32, v);
+            const float4* rc = reinterpret_cast<const float4*>(cv + 0 * BN + c * 32);
+            const float4* lc = reinterpret_cast<const float4*>(cv + 3 * BN + c * 32);
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const float4 r4 = rc[e4];
+              const float4 l4 = lc[e4];
+              const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+              const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int e = 4 * e4 + k;
+                const float q2 = v[e] * cq * rr[k];
+                const float e1 = fast_exp2(q2 - lt);
+                const float e2 = row_only ? 0.f : fast_exp2(q2 - ll[k]);
+                E[c * 32 + e] = -(e1 + e2);
+              }
+            }
+          }
+          tc_fence_before();
+          release_slot(slot);
+        }
+        for (int p = 1; p < P.nprod; ++p) {
+          const int slot = (it + p) % F_SLOTS;
+          mbar_wait(smem_u32(&s_full[slot]), static_cast<uint32_t>((it + p) / F_SLOTS) & 1);
+          tc_fence_after();
+          const float cy = P.rinv[p][gi] * P.scal[(p == 1) ? SC_ITS_L2 : SC_ITX_L2];
+          const float ly = P.lse_row[p][lic];
+          const float isig = 1.f / pow2_floor(P.scal[P.rmin_idx[p - 1]]);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int jrel0 = jt0 + c * 32;
+            const int gj0 = P.col0 + jrel0;
+            tmem_ld32(lane_addr + slot * BN + half * 64 + c * 32, v);
+            if (c == 1) {
+              tc_fence_before();
+              release_slot(slot);
+            }
+            float g[32];
+            const float4* rc = reinterpret_cast<const float4*>(cv + p * BN + c * 32);
+            const float4* lc = reinterpret_cast<const float4*>(cv + (3 + p) * BN + c * 32);
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const float4 r4 = rc[e4];
+              const float4 l4 = lc[e4];
+              const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+              const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int e = 4 * e4 + k;
+                const float p2 = v[e] * cy * rr[k];
+                const float e1 = fast_exp2(p2 - ly);
+                const float e2 = row_only ? 0.f : fast_exp2(p2 - ll[k]);
+                const bool dead = (gj0 + e == gi) || (jrel0 + e >= P.ncols);
+                g[e] = dead ? 0.f : (E[c * 32 + e] + (e1 + e2)) * fminf(rr[k] * isig, 1.0e4f);
+              }
+            }
+            if (real_block && jrel0 + 32 <= P.g_pitch) store_g32(P.gout[p - 1] + g_index(li, jrel0, P.g_pitch), g);
+          }
+        }
+        mbar_arrive(smem_u32(&col_empty[cb]));
+      }
     } else {
       const float cq = P.rinv[0][gi] * P.scal[SC_ITT_L2];
       const float cp = P.rinv[1][gi] * P.scal[SC_ITS_L2];
@@ -365,6 +574,10 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       for (int t = t0; t < t1; ++t, it += P.nprod) {
         const int jt0 = t * BN + half * 64;  // first column (relative to col0) of this thread's 64 columns
         const bool ragged = jt0 + 64 > P.ncols;
+        // this tile's inverse column norms per product, staged by the producer
+        const int cb = (t - t0) % COL_BUFS;
+        mbar_wait(smem_u32(&col_full[cb]), static_cast<uint32_t>((t - t0) / COL_BUFS) & 1);
+        const float* cv = colbuf + cb * COL_VECS * BN + half * 64;
         // ---- teacher: q (log2 units) for all 64 columns, then ONE running-max update for the tile; the
         // TMEM slot goes back to the MMA issuer as soon as the values are in registers
         {
@@ -375,10 +588,10 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
           for (int c = 0; c < 2; ++c) {
             const int gj0 = P.col0 + jt0 + c * 32;
             tmem_ld32(lane_addr + slot * BN + half * 64 + c * 32, v);
-            const float4* rc = reinterpret_cast<const float4*>(P.rinv[0] + gj0);
+            const float4* rc = reinterpret_cast<const float4*>(cv + c * 32);
 #pragma unroll
             for (int e4 = 0; e4 < 8; ++e4) {
-              const float4 r = __ldg(rc + e4);
+              const float4 r = rc[e4];
               w[c * 32 + 4 * e4 + 0] = v[4 * e4 + 0] * cq * r.x;
               w[c * 32 + 4 * e4 + 1] = v[4 * e4 + 1] * cq * r.y;
               w[c * 32 + 4 * e4 + 2] = v[4 * e4 + 2] * cq * r.z;
@@ -420,7 +633,6 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
           tc_fence_after();
           const float cs = (p == 1) ? cp : cr;
           const float mfix = (p == 1) ? ms2 : mx2;
-          const float* rv = P.rinv[p];
           float b0[4] = {0.f, 0.f, 0.f, 0.f}, b1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -430,10 +642,10 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
               tc_fence_before();
               release_slot(slot);
             }
-            const float4* rc = reinterpret_cast<const float4*>(rv + P.col0 + jrel0);
+            const float4* rc = reinterpret_cast<const float4*>(cv + p * BN + c * 32);
 #pragma unroll
             for (int e4 = 0; e4 < 8; ++e4) {
-              const float4 r = __ldg(rc + e4);
+              const float4 r = rc[e4];
               const float rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
@@ -449,6 +661,7 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
           const float asum = (b1[0] + b1[1]) + (b1[2] + b1[3]);
           if (p == 1) { zs += zsum; ap += asum; } else { zx += zsum; ar += asum; }
         }
+        mbar_arrive(smem_u32(&col_empty[cb]));
       }
       if (li < P.b) {
         const int o = sp * P.b + li;

@@ -154,6 +154,14 @@ __device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster, uint32_t
       "r"(src_cta), "r"(bytes), "r"(mbar_cluster)
       : "memory");
 }
+// 1-D bulk copy global -> this CTA's shared memory (16-byte aligned, size multiple of 16), completion as tx
+// bytes on a local mbarrier
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+      "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+      : "memory");
+}
 // all threads of all CTAs in the cluster (a plain CTA barrier when the cluster has one CTA)
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -302,9 +310,39 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const CUtenso
       : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 eviction-priority policies for loads that must survive a concurrent stream of stores through L2
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_2d_2sm_hint(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar_cluster,
+                                                     int32_t c0, int32_t c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
 // arrive on an mbarrier of another CTA of the cluster (address from mapa_shared)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+
+// Same without release semantics: a .release arrive waits until every earlier global store of the thread has
+// been performed at cluster scope (MEMBAR), which stalls an epilogue that streams tiles to HBM.  Valid when the
+// barrier only hands back TMEM (reads completed by tcgen05.wait::ld + fence::before_thread_sync), not memory.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+
+// Read-only 16-byte global load that the compiler may not sink towards its first use (software prefetch of
+// per-column statistics ahead of the tile they belong to).
+__device__ __forceinline__ float4 ldg_nc_v4_volatile(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
 }
 
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (one row per thread).

@@ -23,6 +23,7 @@ Differences from the reference that are deliberate and documented in DESIGN.md:
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -97,8 +98,8 @@ _DTYPES = {torch.float32: _cabi.DT_F32, torch.bfloat16: _cabi.DT_BF16, torch.flo
 
 
 class _Plan:
-    __slots__ = ("handle", "row_elems", "state_numel", "scratch_numel", "flops", "launches_fwd",
-                 "launches_bwd", "shape")
+    __slots__ = ("handle", "row_elems", "state_numel", "scratch_numel", "fwd_scratch_numel", "flops",
+                 "launches_fwd", "launches_bwd", "shape")
 
 
 def _rowmajor(x: torch.Tensor) -> torch.Tensor:
@@ -137,6 +138,7 @@ class CudaBackend:
             p.row_elems = int(self._lib.dsoft_plan_gathered_row_elems(h))
             p.state_numel = int(self._lib.dsoft_plan_state_bytes(h)) // 4
             p.scratch_numel = int(self._lib.dsoft_plan_scratch_bytes(h)) // 4
+            p.fwd_scratch_numel = int(self._lib.dsoft_plan_forward_scratch_bytes(h)) // 4
             p.flops = float(self._lib.dsoft_plan_algorithmic_flops(h))
             p.launches_fwd = int(self._lib.dsoft_plan_launches_forward(h))
             p.launches_bwd = int(self._lib.dsoft_plan_launches_backward(h))
@@ -202,6 +204,29 @@ def _default_backend(device: torch.device) -> CudaBackend:
     return _cuda_backend
 
 
+# ---- two-phase backward (DSOFT_F_GMAT, include/dsoft.h) ------------------------------------------------
+# "auto": run the backward through fp16 logit-gradient matrices (2 B per element of up to four [b, B] blocks of
+# backward scratch) whenever they fit in GMAT_FRACTION of the device memory that is free right now; otherwise
+# use the fused backward, which never allocates anything of size b x B.  "always" / "never" force one path.
+GMAT = os.environ.get("DSOFT_GMAT", "auto")
+GMAT_FRACTION = 0.5
+
+
+def _gmat_fits(b, W, soft, text, soft_local, dev) -> bool:
+    if GMAT == "never":
+        return False
+    if GMAT == "always":
+        return True
+    if dev.type != "cuda":
+        return False
+    B = b * W
+    cols_s = b if soft_local else B
+    need = 2 * b * (2 * B + ((1 if soft else 0) + (1 if text else 0)) * cols_s)
+    free, _total = torch.cuda.mem_get_info(dev)
+    cached = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+    return need <= GMAT_FRACTION * (free + cached)
+
+
 class _FnConfig:
     __slots__ = ("backend", "world", "rank", "group", "flags", "teacher_temp", "text_temp", "lambdas")
 
@@ -218,11 +243,16 @@ class _DinoSoftFn(torch.autograd.Function):
         b, D = image.shape
         W, r = cfg.world, cfg.rank
         soft = bool(cfg.flags & _cabi.DSOFT_F_SOFT)
+        needs_grad = any(ctx.needs_input_grad[:4])
+        flags = cfg.flags
+        if needs_grad and _gmat_fits(b, W, soft, bool(flags & _cabi.DSOFT_F_TEXT),
+                                     bool(flags & _cabi.DSOFT_F_SOFT_LOCAL), dev):
+            flags |= _cabi.DSOFT_F_GMAT
         shape = _cabi.Shape(
             b=b, world=W, rank=r, D=D,
             Dp=(student.shape[1] if (student is not None and soft) else 0),
             Dd=(dino.shape[1] if (dino is not None and soft) else 0),
-            flags=cfg.flags, teacher_temp=cfg.teacher_temp, text_temp=cfg.text_temp,
+            flags=flags, teacher_temp=cfg.teacher_temp, text_temp=cfg.text_temp,
         )
         plan = be.plan(shape, dev) if dev.type == "cuda" else be.plan(shape)
         gathered = torch.empty((b * W, plan.row_elems), dtype=torch.bfloat16, device=dev)
@@ -232,12 +262,11 @@ class _DinoSoftFn(torch.autograd.Function):
             # the only feature exchange of the path: one all-gather of the packed bf16 rows (loss.py:23-81)
             dist.all_gather_into_tensor(gathered.view(-1), gathered[r * b:(r + 1) * b].view(-1), group=cfg.group)
         state = torch.empty(plan.state_numel, dtype=torch.float32, device=dev)
-        scratch = torch.empty(plan.scratch_numel, dtype=torch.float32, device=dev)
+        scratch = torch.empty(plan.fwd_scratch_numel, dtype=torch.float32, device=dev)
         lse_all = torch.empty((W, 5, b), dtype=torch.float32, device=dev)
         losses = torch.empty(5, dtype=torch.float32, device=dev)
         ls = logit_scale.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
         be.forward(plan, gathered, ls, cfg.lambdas, state, scratch, lse_all[r], losses)
-        needs_grad = any(ctx.needs_input_grad[:4])
         if W > 1 and needs_grad:
             # column-side soft-max statistics of the other ranks' rows (5 floats per sample)
             dist.all_gather_into_tensor(lse_all.view(-1), lse_all[r].view(-1), group=cfg.group)

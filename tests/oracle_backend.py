@@ -31,6 +31,7 @@ class OracleBackend:
         p.row_elems = p.offD + (shape.Dd if p.soft else 0)
         p.state_numel = 8
         p.scratch_numel = 8
+        p.fwd_scratch_numel = 8
         p.flops, p.launches_fwd, p.launches_bwd = 0.0, 0, 0
         return p
 

@@ -7,6 +7,18 @@ from gpu_util import make_args, synth
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["two_phase", "fused"])
+def backward_path(request, pkg):
+    """Both backward implementations must meet the same bar: the two-phase one (fp16 logit-gradient matrices +
+    gradient GEMMs, DSOFT_F_GMAT) and the fused one that keeps the logit gradients in shared memory."""
+    from dinosoft_b200 import loss as loss_mod
+
+    old = loss_mod.GMAT
+    loss_mod.GMAT = "always" if request.param == "two_phase" else "never"
+    yield request.param
+    loss_mod.GMAT = old
+
 B, D, DD = 32768, 512, 768
 
 
