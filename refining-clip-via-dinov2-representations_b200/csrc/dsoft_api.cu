@@ -71,6 +71,8 @@ struct dsoft_plan {
   int pitch_c, pitch_s;  // columns of the CLIP / soft G matrices: multiples of 64
   size_t sc_Gci, sc_Gct, sc_Gs, sc_Gx, sc_fwd_total;
   SplitPlan g_clip, g_stu, g_txt;  // K splits of the gradient GEMMs (tps = K steps per split)
+  SplitPlan g_clip_t;              // world == 1: dT = G^T . I, K runs over G's rows
+  int clip_tr;                     // world == 1 two-phase: one CLIP logit-gradient matrix serves both directions
 };
 
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -192,6 +194,8 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
     p->g_clip = choose_gy_split(pairs * ceil_div(sh->D, GY_N), p->pitch_c / 64, sms);
     p->g_stu = choose_gy_split(pairs * ceil_div(p->Dz, GY_N), p->pitch_s / 64, sms);
     p->g_txt = choose_gy_split(pairs * ceil_div(sh->D, GY_N), p->pitch_s / 64, sms);
+    p->clip_tr = sh->world == 1;
+    p->g_clip_t = choose_gy_split(pairs * ceil_div(sh->D, GY_N), rbs * 2, sms);
   }
 
   // ---- state (floats)
@@ -213,7 +217,7 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   p->sc_ps = take(soft ? 7 * 2 * p->f_soft.nsplit * b : 0);
   p->sc_rowloss = take(3 * b);
   p->sc_fwd_total = o;  // the forward only needs the statistics partials above
-  const size_t ns_c = p->gmat ? p->g_clip.nsplit : p->b_clip.nsplit;
+  const size_t ns_c = p->gmat ? std::max(p->g_clip.nsplit, p->g_clip_t.nsplit) : p->b_clip.nsplit;
   const size_t ns_s = p->gmat ? p->g_stu.nsplit : p->b_stu.nsplit;
   const size_t ns_x = p->gmat ? p->g_txt.nsplit : p->b_txt.nsplit;
   p->sc_acc1 = take(ns_c * b * sh->D);
@@ -226,7 +230,7 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   if (p->gmat) {
     const size_t bpad = static_cast<size_t>(rbs) * BM;  // blocked layout holds whole 128-row blocks
     p->sc_Gci = take(bpad * p->pitch_c / 2);
-    p->sc_Gct = take(bpad * p->pitch_c / 2);
+    p->sc_Gct = take(p->clip_tr ? 0 : bpad * p->pitch_c / 2);
     p->sc_Gs = take(soft ? bpad * p->pitch_s / 2 : 0);
     p->sc_Gx = take(p->have_text ? bpad * p->pitch_s / 2 : 0);
   }
@@ -285,7 +289,7 @@ extern "C" int dsoft_plan_kernel_flops(const dsoft_plan_t* p, double* algorithmi
     // two-phase backward: slots 3..6 are the plain gradient GEMMs, slots 7 / 8 the logit-gradient kernels
     // (every similarity product recomputed once; the teacher product once for student and text)
     for (int k = 3; k < 7; ++k) executed[k] = algorithmic[k];
-    if (n > 7) executed[7] = 2.0 * (2.0 * b * Bc * D);
+    if (n > 7) executed[7] = (p->clip_tr ? 1.0 : 2.0) * (2.0 * b * Bc * D);
     if (n > 8 && p->have_soft) executed[8] = 2.0 * b * Bs * (Dz + Dd + (p->have_text ? D : 0.0));
   }
   return 0;
@@ -298,7 +302,7 @@ extern "C" int dsoft_plan_launches_forward(const dsoft_plan_t* p) {
 extern "C" int dsoft_plan_launches_backward(const dsoft_plan_t* p) {
   if (!p) return 0;
   if (p->gmat)
-    return 2 /*relayout, fp16 operands*/ + 2 /*clip G*/ + 2 /*clip GEMMs*/ +
+    return 2 /*relayout, fp16 operands*/ + (p->clip_tr ? 1 : 2) /*clip G*/ + 2 /*clip GEMMs*/ +
            (p->have_soft ? 2 : 0) /*soft G, student GEMM*/ + (p->have_text ? 1 : 0) + 1 /*finalize*/;
   return 2 /*relayout, fp16 operands*/ + 2 * chunk_groups(p->nch_clip) + (p->have_soft ? chunk_groups(p->nch_stu) : 0) +
          (p->have_text ? chunk_groups(p->nch_txt) : 0) + 1 /*finalize*/;
@@ -641,11 +645,11 @@ __global__ void make_v16_kernel(const __nv_bfloat16* __restrict__ gathered, int 
 struct FinBwdArgs {
   int b, D, Dz, row0, row_elems, offI, offT, offZ;
   int have_soft, have_text, have_proj, row_only;
-  int ns_c, ns_s, ns_x;
+  int ns_c, ns_c2, ns_s, ns_x;  // split counts of acc1, acc2, acc3, acc4
   int nds;  // d(logit_scale) partials per row: nsplit x cluster size x 2 halves
   const __nv_bfloat16* gathered;
   const float* acc1;  // [ns_c][b][D]   sum_j G_clip . T_j   (image rows)
-  const float* acc2;  // [ns_c][b][D]   sum_j G_clip' . I_j  (text rows)
+  const float* acc2;  // [ns_c2][b][D]  sum_j G_clip' . I_j  (text rows)
   const float* acc3;  // [ns_s][b][Dz]  sum_j G_stu . Z_j / ||Z_j||
   const float* acc4;  // [ns_x][b][D]   sum_j G_txt . T_j / ||T_j||
   const float* ds1;   // [2 ns_c][b]
@@ -726,7 +730,7 @@ __global__ void __launch_bounds__(128) finalize_bwd_kernel(FinBwdArgs a) {
     const int f = (it * 128 + tid) * 4;
     if (f < a.D) {
       const float4 u1 = sum_splits4(a.acc1, a.ns_c, a.b, a.D, i, f);
-      const float4 u2 = sum_splits4(a.acc2, a.ns_c, a.b, a.D, i, f);
+      const float4 u2 = sum_splits4(a.acc2, a.ns_c2, a.b, a.D, i, f);
       const float4 tf = load_bf16x4(rowp + a.offT + f);
       const float4 im = load_bf16x4(rowp + a.offI + f);
       tfeat[it] = tf;
@@ -1204,23 +1208,26 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
 
 
 // Gradient GEMM launch: acc[split][b][dout] = G[b][pitch] . Y16[ycol0 + ..][voff .. voff + dout)
+// transposed = true (world == 1 only): acc[split][col][dout] = G^T . Y16, K runs over G's rows
 static int launch_gy(const dsoft_plan* p, const __half* G, int pitch, const __half* v16, int voff, int dout,
-                     int ycol0, const SplitPlan& sp, float* acc, cudaStream_t st) {
+                     int ycol0, const SplitPlan& sp, float* acc, cudaStream_t st, bool transposed = false) {
   CUtensorMap gmap, vmap;
   int rc;
   // blocked G: 64 columns x (row blocks * K tiles * 128) rows, one 16 KiB box per (row block, K tile)
-  const int g_rows = ceil_div(p->sh.b, BM) * (pitch / BK) * BM;
-  if ((rc = make_map(&gmap, G, g_rows, BK, BK, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, BM))) return rc;
+  const int rbs = ceil_div(p->sh.b, BM);
+  const int g_rows = rbs * (pitch / BK) * BM;
+  if ((rc = make_map(&gmap, G, g_rows, BK, BK, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, transposed ? 64 : BM))) return rc;
   if ((rc = make_map(&vmap, v16 + voff, p->B, dout, p->v_row, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 64))) return rc;
   GyParams P;
   P.b = p->sh.b;
   P.dout = dout;
-  P.ksteps = pitch / BK;
+  P.ksteps = transposed ? rbs * 2 : pitch / BK;
   P.steps_per_split = sp.tps;
   P.nsplit = sp.nsplit;
   P.ycol0 = ycol0;
+  P.g_ktiles = pitch / BK;
   P.acc_part = acc;
-  const int pairs = ceil_div(ceil_div(p->sh.b, BM), 2);
+  const int pairs = ceil_div(rbs, 2);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2, ceil_div(dout, GY_N), pairs * sp.nsplit);
   cfg.blockDim = dim3(NUM_THREADS);
@@ -1233,7 +1240,8 @@ static int launch_gy(const dsoft_plan* p, const __half* G, int pitch, const __ha
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, dsoft_gy_kernel, gmap, vmap, P));
+  if (transposed) CUDA_TRY(cudaLaunchKernelEx(&cfg, dsoft_gy_kernel<true>, gmap, vmap, P));
+  else CUDA_TRY(cudaLaunchKernelEx(&cfg, dsoft_gy_kernel<false>, gmap, vmap, P));
   return 0;
 }
 
@@ -1247,7 +1255,8 @@ static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* 
   int rc;
   TileMaps tm;
   if ((rc = make_maps(p, gathered, &tm, 64))) return rc;
-  if ((rc = set_smem(dsoft_gy_kernel, GY_SMEM_BYTES))) return rc;
+  if ((rc = set_smem(dsoft_gy_kernel<false>, GY_SMEM_BYTES))) return rc;
+  if ((rc = set_smem(dsoft_gy_kernel<true>, GY_SMEM_BYTES))) return rc;
   if ((rc = set_smem(dsoft_fwd_kernel<MODE_CLIP_G, 2>, FWD_SMEM_BYTES))) return rc;
   if ((rc = set_smem(dsoft_fwd_kernel<MODE_SOFT_G, 2>, FWD_SMEM_BYTES))) return rc;
   __half* Gci = reinterpret_cast<__half*>(X + p->sc_Gci);
@@ -1306,7 +1315,7 @@ static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* 
         return rc;
     }
   }
-  for (int d = 0; d < 2; ++d) {  // d = 0: image rows (dI = G . T), d = 1: text rows (dT = G . I)
+  for (int d = 0; d < (p->clip_tr ? 1 : 2); ++d) {  // d = 0: image rows (dI = G . T), d = 1: text rows (dT = G . I)
     if ((rc = fk.lane(lane++, &ks))) return rc;
     fill_clip_fwd(p, P, d == 0 ? 0 : 1, d == 0 ? 1 : 0, S + p->st_scal, nullptr, nullptr);
     P.lse_row[0] = lse_loc + d * b;
@@ -1315,6 +1324,7 @@ static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* 
     P.g_pitch = p->pitch_c;
     P.row_only = p->row_only;
     P.ds_part = X + (d == 0 ? p->sc_ds1 : p->sc_ds2);
+    P.ds_both = p->clip_tr;
     {
       ProfScope ps(PK_BWD_GCLIP, ks);
       if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_CLIP_G, 2>, rbs, p->f_clip.nsplit, ks, tm, P))) return rc;
@@ -1325,6 +1335,14 @@ static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* 
                           X + (d == 0 ? p->sc_acc1 : p->sc_acc2), ks)))
         return rc;
     }
+  }
+  if (p->clip_tr) {
+    // world == 1: G_text[j][i] = p_ti[j,i] + p_it[i,j] = G_image[i][j]: dT = G_image^T . I, no second G matrix;
+    // the text rows' d(logit_scale) partials were folded into the image rows' (ds_both)
+    CUDA_TRY(cudaMemsetAsync(X + p->sc_ds2, 0, sizeof(float) * 2 * p->f_clip.nsplit * b, ks));
+    ProfScope ps(PK_BWD_CLIP_T, ks);
+    if ((rc = launch_gy(p, Gci, p->pitch_c, v16, p->v_offI, p->sh.D, 0, p->g_clip_t, X + p->sc_acc2, ks, true)))
+      return rc;
   }
   return fk.join();
 }
@@ -1488,6 +1506,7 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
   fa.have_proj = p->have_proj;
   fa.row_only = p->row_only;
   fa.ns_c = p->gmat ? p->g_clip.nsplit : p->b_clip.nsplit;
+  fa.ns_c2 = (p->gmat && p->clip_tr) ? p->g_clip_t.nsplit : fa.ns_c;
   fa.nds = p->gmat ? 2 * p->f_clip.nsplit : 2 * p->b_clip.nsplit * chunk_cluster(p->nch_clip);
   fa.ns_s = p->gmat ? p->g_stu.nsplit : p->b_stu.nsplit;
   fa.ns_x = p->gmat ? p->g_txt.nsplit : p->b_txt.nsplit;

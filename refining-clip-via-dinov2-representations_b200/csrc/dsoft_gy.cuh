@@ -21,6 +21,9 @@ namespace dsoft {
 //  A = G   blocked [row block][64-column K tile][128 rows][64 cols]: one TMA box (SW128, K-major) = 16 KiB of
 //          contiguous memory; addressed as a 2-D tensor of 64 columns x (row blocks * K tiles * 128) rows
 //  B = Y16 [cols][Dout], MN-major (features contiguous), box 64 features x 64 rows, SW128
+//  AT = true multiplies with G^T instead (dT = G^T . I16 for the CLIP text rows when world == 1, where the text
+//  rows' logit-gradient matrix is exactly the transpose of the image rows' one): M runs over G's columns, K over
+//  its rows; the A tile of a CTA is two boxes of 64 G-columns x 64 G-rows, MN-major like the B operand.
 //  grid (2, n tiles, row pairs * k splits), cluster (2,1,1): CTA `prank` holds 128 of the pair's 256 rows
 //  and 128 of the tile's 256 features; the leader issues the MMAs for both.
 //  ring: 6 stages x (A 16 KiB | B 2 x 8 KiB); TMEM: 256 fp32 accumulator columns per CTA.
@@ -30,15 +33,17 @@ constexpr int GY_N = 256;
 constexpr int GY_SMEM_BYTES = GY_STAGES * SLAB + 1024 + 256;
 
 struct GyParams {
-  int b;                // rows of G and of the output
+  int b;                // rows of the output (AT: columns of G in scope)
   int dout;             // gradient features
   int ksteps;           // K steps of 64 columns over the whole (padded) column range
   int steps_per_split;  // K steps per split
   int nsplit;
-  int ycol0;            // row of Y16 that matches G column 0 (first global column in scope)
+  int ycol0;            // row of Y16 that matches K index 0
+  int g_ktiles;         // 64-column tiles per row block of the blocked G (its pitch / 64)
   float* acc_part;      // [nsplit][b][dout] fp32
 };
 
+template <bool AT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dsoft_gy_kernel(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUtensorMap vmap,
                 const __grid_constant__ GyParams P) {
@@ -88,7 +93,14 @@ dsoft_gy_kernel(const __grid_constant__ CUtensorMap gmap, const __grid_constant_
         const uint32_t full_leader = mapa_shared(full, 0);
         const uint32_t dst = smem_u32(smem + stage * SLAB);
         if (leader) mbar_arrive_expect_tx(full, 2 * SLAB);
-        tma_load_2d_2sm(dst, &gmap, full_leader, 0, (rb * P.ksteps + k) * BM);
+        if constexpr (AT) {
+          // K step k = G rows [64k, 64k + 64) = half `k & 1` of row block `k >> 1`; M = G columns 128 rb ..
+          const int grow = ((k >> 1) * P.g_ktiles + 2 * rb) * BM + (k & 1) * 64;
+          tma_load_2d_2sm(dst, &gmap, full_leader, 0, grow);
+          tma_load_2d_2sm(dst + TILE_BYTES / 2, &gmap, full_leader, 0, grow + BM);
+        } else {
+          tma_load_2d_2sm(dst, &gmap, full_leader, 0, (rb * P.g_ktiles + k) * BM);
+        }
         tma_load_2d_2sm(dst + TILE_BYTES, &vmap, full_leader, f0, P.ycol0 + k * BK);
         tma_load_2d_2sm(dst + TILE_BYTES + TILE_BYTES / 2, &vmap, full_leader, f0 + BK, P.ycol0 + k * BK);
       }
@@ -99,7 +111,7 @@ dsoft_gy_kernel(const __grid_constant__ CUtensorMap gmap, const __grid_constant_
     if (leader) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t idesc = make_idesc_bf16(2 * BM, GY_N, 0, 1, 1);  // fp16, A K-major, B MN-major
+      const uint32_t idesc = make_idesc_bf16(2 * BM, GY_N, AT ? 1 : 0, 1, 1);  // fp16, B MN-major
       for (int k = k0; k < k1; ++k) {
         mbar_wait(smem_u32(&ring_full[stage]), phase);
         tc_fence_after();
@@ -108,7 +120,8 @@ dsoft_gy_kernel(const __grid_constant__ CUtensorMap gmap, const __grid_constant_
           const uint32_t v_addr = a_addr + TILE_BYTES;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t ad = make_smem_desc(a_addr + kk * 32, 16, 1024);
+            const uint64_t ad = AT ? make_smem_desc(a_addr + kk * 2048, TILE_BYTES / 2, 1024)
+                                   : make_smem_desc(a_addr + kk * 32, 16, 1024);
             const uint64_t bd = make_smem_desc(v_addr + kk * 2048, TILE_BYTES / 2, 1024);
             umma_cg<2>(tmem_base, ad, bd, idesc, (k == k0 && kk == 0) ? 0u : 1u);
           }

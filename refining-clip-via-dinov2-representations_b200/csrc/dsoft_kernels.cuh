@@ -94,6 +94,8 @@ struct FwdParams {
   int row_only;             // gather_with_grad == False: drop the column-side terms
   int rmin_idx[2];          // soft: SC_RMIN_Z, SC_RMIN_T (scale of the fp16 gradient operand)
   float* ds_part;           // clip: d(logit_scale) row partials [npart][b]
+  int ds_both;              // clip, world == 1: one launch serves both directions (the text rows' matrix is the
+                            // transpose), so the row partial also takes the column-side term
 };
 
 struct BwdParams {
@@ -432,6 +434,8 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       const float la = P.lse_row[0][min(li, P.b - 1)];
       const bool row_only = P.row_only != 0;
       const bool real_block = rb * BM < P.b;  // the odd pair member past the last row block owns no G rows
+      const bool live_row = li < P.b;         // rows past b are K entries of the transposed GEMM: keep them zero
+      const bool ds_both = P.ds_both != 0;
       float dsacc = 0.f;
       // column LSEs of the NEXT 32-column chunk are fetched while the current one is processed (two register
       // buffers, loop fully unrolled so that they are addressed statically); launched with bn == 256 only
@@ -466,8 +470,8 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
               const float x2 = v[e] * s2;
               const float e1 = fast_exp2(x2 - la);
               const float e2 = row_only ? 0.f : fast_exp2(x2 - ll[k]);
-              dsacc = fmaf(e1, v[e], dsacc);  // ragged columns carry dot = 0
-              g[e] = (gj0 + e == gi || jrel0 + e >= P.ncols) ? 0.f : e1 + e2;
+              dsacc = fmaf(ds_both ? e1 + e2 : e1, v[e], dsacc);  // ragged columns carry dot = 0
+              g[e] = (gj0 + e == gi || jrel0 + e >= P.ncols || !live_row) ? 0.f : e1 + e2;
             }
           }
           if (real_block && jrel0 + 32 <= P.g_pitch) store_g32(P.gout[0] + g_index(li, jrel0, P.g_pitch), g);
