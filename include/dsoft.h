@@ -136,7 +136,8 @@ int dsoft_profile_read(double* ms_sum, int* counts, int n);
  * forked from / joined back into `stream`, so the next kernel's CTAs fill the partially empty last wave of
  * the previous one; callers still see plain stream-ordered semantics, and stream capture records a
  * fork/join graph.  on = 0 launches them serially on `stream` (also forced while dsoft_profile_enable(1) is
- * active so that per-kernel durations are isolated).  Default: on, or the DSOFT_CONCURRENCY=0/1 variable. */
+ * active so that per-kernel durations are isolated), on = 1 always forks, on < 0 (default, or the
+ * DSOFT_CONCURRENCY=0/1 variable unset) forks only for small per-rank blocks, where it pays. */
 int dsoft_set_concurrency(int on);
 
 /* Test / bring-up helper: C[M][N] (fp32) = A[M][K] . B[N][K]^T with bf16 operands through the same

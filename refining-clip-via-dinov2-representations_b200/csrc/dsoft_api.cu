@@ -892,19 +892,24 @@ extern "C" int dsoft_profile_read(double* ms_sum, int* counts, int n) {
 // (dsoft_profile_enable) forces serial launches so that each duration is an isolated measurement.
 // ------------------------------------------------------------------------------------------------
 static const int NSIDE = 3;
-static int g_concurrency = -1;  // -1: read DSOFT_CONCURRENCY on first use (default on)
+static int g_concurrency = -2;  // -2: read DSOFT_CONCURRENCY on first use; -1 auto, 0 off, 1 on
 
 extern "C" int dsoft_set_concurrency(int on) {
-  g_concurrency = on ? 1 : 0;
+  g_concurrency = on < 0 ? -1 : (on ? 1 : 0);
   return 0;
 }
 
-static bool concurrency_on() {
-  if (g_concurrency < 0) {
+// auto: fork only when this rank's block of the similarity matrices is small (<= 2^28 elements).  Measured on
+// B200: +7 % at B = 8192 and +3.7 % at b x B = 8192 x 32768 (tails of 1-3 wave kernels filled), but nothing
+// at b x B >= 16384 x 32768, where the step is power capped and the extra activity only lowers the SM clock.
+static bool concurrency_on(const dsoft_plan* p) {
+  if (g_concurrency == -2) {
     const char* e = getenv("DSOFT_CONCURRENCY");
-    g_concurrency = (e && e[0] == '0') ? 0 : 1;
+    g_concurrency = !e ? -1 : (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : -1));
   }
-  return g_concurrency == 1 && !g_prof.on;
+  if (g_prof.on || g_concurrency == 0) return false;
+  if (g_concurrency == 1) return true;
+  return static_cast<double>(p->sh.b) * p->B <= 268435456.0;
 }
 
 struct SideStreams {
@@ -936,9 +941,9 @@ struct Fork {
   cudaStream_t main_st = nullptr;
   SideStreams* ss = nullptr;
   bool forked[NSIDE] = {false, false, false};
-  int begin(cudaStream_t st) {
+  int begin(const dsoft_plan* p, cudaStream_t st) {
     main_st = st;
-    if (!concurrency_on()) return 0;
+    if (!concurrency_on(p)) return 0;
     int rc = side_streams(&ss);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(ss->fork, main_st));
@@ -1132,7 +1137,7 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
 
   // the three tile kernels are independent: fork them (largest first), join before the finalize
   Fork fk;
-  if ((rc = fk.begin(st))) return rc;
+  if ((rc = fk.begin(p, st))) return rc;
   cudaStream_t ks = st;
   int lane = 0;
   FwdParams P;
@@ -1264,7 +1269,7 @@ static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* 
   __half* Gs = reinterpret_cast<__half*>(X + p->sc_Gs);
   __half* Gx = reinterpret_cast<__half*>(X + p->sc_Gx);
   Fork fk;
-  if ((rc = fk.begin(st))) return rc;
+  if ((rc = fk.begin(p, st))) return rc;
   cudaStream_t ks = st;
   int lane = 0;
   FwdParams P;
@@ -1399,7 +1404,7 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
   };
   // the four tile kernels are independent: fork them (largest first), join before the finalize
   Fork fk;
-  if ((rc = fk.begin(st))) return rc;
+  if ((rc = fk.begin(p, st))) return rc;
   cudaStream_t ks = st;
   int lane = 0;
   if (p->have_soft) {

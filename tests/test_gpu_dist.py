@@ -20,9 +20,10 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, B, D, Dd, scale, argd, ctor, ret):
+def _worker(rank, world, port, B, D, Dd, scale, argd, ctor, ret, gmat):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["DSOFT_GMAT"] = gmat  # backward implementation (read when the package is imported)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -61,13 +62,14 @@ def _worker(rank, world, port, B, D, Dd, scale, argd, ctor, ret):
     (dict(local_loss=True, gather_with_grad=True, soft_scope="local"), dict(use_projection=False)),
     (dict(local_loss=True, gather_with_grad=False, soft_scope="global"), dict(use_projection=False)),
 ])
-def test_two_gpu_parity(oracle, ctor, argd):
+@pytest.mark.parametrize("gmat", ["always", "never"], ids=["two_phase", "fused"])
+def test_two_gpu_parity(oracle, ctor, argd, gmat):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     B, D, Dd, scale, world = 512, 128, 192, 30.0, 2
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), B, D, Dd, scale, argd, ctor, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), B, D, Dd, scale, argd, ctor, ret, gmat), nprocs=world, join=True)
     args = make_args(**argd)
     img, txt, dino = synth(21, B, D, Dd)
     cfg = oracle_cfg(oracle, args, world_size=world, local_loss=True, gather_with_grad=ctor["gather_with_grad"],

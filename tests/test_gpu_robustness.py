@@ -137,7 +137,7 @@ def test_forked_and_serial_launches_agree_bitwise(pkg):
             res.append((o["total_loss"].detach().clone(), im.grad.clone(), tx.grad.clone(), sc.grad.clone(),
                         [prm.grad.clone() for prm in loss.parameters()]))
     finally:
-        lib.dsoft_set_concurrency(1)
+        lib.dsoft_set_concurrency(-1)  # back to the automatic choice
     for other in res[1:]:
         assert torch.equal(res[0][0], other[0])
         assert torch.equal(res[0][1], other[1]) and torch.equal(res[0][2], other[2])
