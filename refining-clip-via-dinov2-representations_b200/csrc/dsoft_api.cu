@@ -401,6 +401,43 @@ __device__ __forceinline__ float2 load_pair(const void* src, int dtype, int64_t 
   return __half22float2(*reinterpret_cast<const __half2*>(static_cast<const __half*>(src) + idx));
 }
 
+// fast path: every source has 16-byte aligned rows -> 8 elements per thread and iteration (two 16-byte loads of
+// fp32, or one of bf16 / fp16; one 16-byte store).  pairs_end counts pairs, so an octet index is a quarter of it.
+__global__ void __launch_bounds__(256) pack_rows8_kernel(PackArgs a, __nv_bfloat16* __restrict__ dst) {
+  const int64_t total = a.pairs_end[a.nmat - 1] / 4;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int k = 0;
+    while (i >= a.pairs_end[k] / 4) ++k;
+    const int64_t j = i - (k ? a.pairs_end[k - 1] / 4 : 0);
+    const PackSrc& m = a.m[k];
+    const int oct_cols = m.cols / 8;
+    const int r = static_cast<int>(j / oct_cols);
+    const int c = static_cast<int>(j % oct_cols) * 8;
+    const int64_t idx = r * m.ld + c;
+    uint4 o;
+    if (m.dtype == DSOFT_DT_F32) {
+      const float4 x0 = __ldcs(reinterpret_cast<const float4*>(static_cast<const float*>(m.src) + idx));
+      const float4 x1 = __ldcs(reinterpret_cast<const float4*>(static_cast<const float*>(m.src) + idx + 4));
+      o = make_uint4(pack_bf16x2(x0.x, x0.y), pack_bf16x2(x0.z, x0.w), pack_bf16x2(x1.x, x1.y),
+                     pack_bf16x2(x1.z, x1.w));
+    } else if (m.dtype == DSOFT_DT_BF16) {
+      o = __ldcs(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(m.src) + idx));
+    } else {
+      const uint4 raw = __ldcs(reinterpret_cast<const uint4*>(static_cast<const __half*>(m.src) + idx));
+      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+      uint32_t ow[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+        ow[q] = pack_bf16x2(f.x, f.y);
+      }
+      o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+    *reinterpret_cast<uint4*>(dst + r * a.dst_ld + m.dst_off + c) = o;
+  }
+}
+
 __global__ void pack_rows_kernel(PackArgs a, __nv_bfloat16* __restrict__ dst) {
   const int64_t total = a.pairs_end[a.nmat - 1];
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -427,29 +464,46 @@ struct RinvArgs {
   int64_t ld;
   int rows, out_len;
 };
-__global__ void rinv_kernel(RinvArgs a) {
+constexpr int RINV_ROWS_PER_WARP = 4;
+__global__ void __launch_bounds__(256) rinv_kernel(RinvArgs a) {
+  __shared__ float wmin[8];
   const int k = blockIdx.y;
-  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (r >= a.out_len) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* out = a.out[k];
-  if (r >= a.rows) {
-    if (lane == 0) out[r] = 0.f;
-    return;
-  }
-  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(a.mat[k] + r * a.ld);
-  float acc = 0.f;
-  for (int c = lane; c < a.cols[k] / 2; c += 32) {
-    const float2 f = __bfloat1622float2(p[c]);
-    acc = fmaf(f.x, f.x, acc);
-    acc = fmaf(f.y, f.y, acc);
-  }
+  const int ncol8 = a.cols[k] / 8;  // feature widths are multiples of 8: 16-byte loads
+  float mn = __int_as_float(0x7f800000);
+  for (int q = 0; q < RINV_ROWS_PER_WARP; ++q) {
+    const int r = (blockIdx.x * 8 + warp) * RINV_ROWS_PER_WARP + q;
+    if (r >= a.out_len) break;
+    if (r >= a.rows) {
+      if (lane == 0) out[r] = 0.f;
+      continue;
+    }
+    const uint4* p = reinterpret_cast<const uint4*>(a.mat[k] + r * a.ld);
+    float acc = 0.f;
+    for (int c = lane; c < ncol8; c += 32) {
+      const uint4 raw = __ldg(p + c);
+      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) {
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+        acc = fmaf(f.x, f.x, acc);
+        acc = fmaf(f.y, f.y, acc);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     const float rv = 1.f / fmaxf(sqrtf(acc), 1e-12f);
-    out[r] = rv;
-    atomicMin(reinterpret_cast<int*>(a.rmin[k]), __float_as_int(rv));  // positive floats order like ints
+    if (lane == 0) out[r] = rv;
+    mn = fminf(mn, rv);
+  }
+  // one atomic per block (per row they serialise on a single address)
+  if (lane == 0) wmin[warp] = mn;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) mn = fminf(mn, wmin[w]);
+    if (mn < __int_as_float(0x7f800000))
+      atomicMin(reinterpret_cast<int*>(a.rmin[k]), __float_as_int(mn));  // positive floats order like ints
   }
 }
 
@@ -486,7 +540,7 @@ struct FinFwdArgs {
   const float* diag;
   const float* scal;
   float* lse;      // [5][b]
-  float* rowloss;  // [3][b]
+  float* rowloss;  // [3][gridDim.x] per-block sums of the row losses
   int* ticket;     // zeroed by prep_scalars_kernel
   float lam_orig, lam_soft, text_lambda;
   float* losses;   // [5]: classic, soft_imgimg, soft_texttext, soft (= img + text_lambda * text), total
@@ -501,8 +555,9 @@ __device__ __forceinline__ float combine_lse2(const float* part, int np, int b, 
 }
 
 // per-row combination of the column-split partial statistics -> LSEs (log2 domain) and row losses
-__device__ __forceinline__ void finalize_fwd_rows(const FinFwdArgs& a) {
+__device__ __forceinline__ void finalize_fwd_rows(const FinFwdArgs& a, float (&rl)[3]) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  rl[0] = rl[1] = rl[2] = 0.f;
   if (i >= a.b) return;
   const float LN2 = 0.6931471805599453f;
   const float l_it = combine_lse2(a.pc_it, a.np_c, a.b, i);
@@ -510,7 +565,7 @@ __device__ __forceinline__ void finalize_fwd_rows(const FinFwdArgs& a) {
   a.lse[0 * a.b + i] = l_it;
   a.lse[1 * a.b + i] = l_ti;
   // classic CE row term (loss.py:317-319): lse_it - L_ii + lse_ti - L_ii
-  a.rowloss[0 * a.b + i] = LN2 * (l_it + l_ti) - 2.f * a.scal[SC_SCALE] * a.diag[i];
+  rl[0] = LN2 * (l_it + l_ti) - 2.f * a.scal[SC_SCALE] * a.diag[i];
   float l_t = 0.f, l_s = 0.f, l_x = 0.f, kl_s = 0.f, kl_x = 0.f;
   if (a.have_soft) {
     const int st = a.np_s * a.b;
@@ -539,15 +594,30 @@ __device__ __forceinline__ void finalize_fwd_rows(const FinFwdArgs& a) {
   a.lse[2 * a.b + i] = l_t;
   a.lse[3 * a.b + i] = l_s;
   a.lse[4 * a.b + i] = l_x;
-  a.rowloss[1 * a.b + i] = kl_s;
-  a.rowloss[2 * a.b + i] = kl_x;
+  rl[1] = kl_s;
+  rl[2] = kl_x;
 }
 
 __global__ void __launch_bounds__(128) finalize_fwd_kernel(FinFwdArgs a) {
-  finalize_fwd_rows(a);
+  float rl[3];
+  finalize_fwd_rows(a, rl);
+  {  // this block's 128 row losses -> one partial per term (fixed order: deterministic)
+    __shared__ float shp[3][4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float v = rl[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0) shp[k][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3)
+      a.rowloss[threadIdx.x * gridDim.x + blockIdx.x] =
+          (shp[threadIdx.x][0] + shp[threadIdx.x][1]) + (shp[threadIdx.x][2] + shp[threadIdx.x][3]);
+  }
   if (last_block_done(a.ticket)) {
     __shared__ double sums[3];
-    block_reduce_rows(a.rowloss, a.b, 3, sums);
+    block_reduce_rows(a.rowloss, gridDim.x, 3, sums);
     if (threadIdx.x == 0) {
       const double inv_b = 1.0 / a.b;
       const float classic = static_cast<float>(0.5 * inv_b * sums[0]);   // loss.py:317-319
@@ -666,7 +736,7 @@ struct FinBwdArgs {
   float* d_image;
   float* d_text;
   float* d_student;
-  float* dsrow;  // [b]
+  float* dsrow;  // [gridDim.x] per-block sums of the d(logit_scale) row terms
 };
 
 __device__ __forceinline__ float block_sum_128(float v, float* sh) {  // finalize_bwd_kernel: 4 warps
@@ -681,8 +751,8 @@ __device__ __forceinline__ float block_sum_128(float v, float* sh) {  // finaliz
 // One 128-thread block per local row: sum the column-split partial gradients, apply the fp32 one-hot
 // part of the CE gradient, the temperature / batch factors and the chain rule through F.normalize.
 // Every thread owns 4 consecutive features per pass (float4 traffic, sums stay in registers between the
-// dot-product pass and the output pass); FB_MAXIT passes cover feature widths up to 2048.
-constexpr int FB_MAXIT = 4;
+// dot-product pass and the output pass); FB_MAXIT passes cover feature widths up to 512 * FB_MAXIT (template
+// parameter: the per-thread arrays cost registers, and this kernel lives on occupancy).
 
 __device__ __forceinline__ float4 sum_splits4(const float* __restrict__ part, int nsplit, int b, int width, int i,
                                                int f) {
@@ -700,10 +770,14 @@ __device__ __forceinline__ float4 load_bf16x4(const __nv_bfloat16* p) {
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
+template <int FB_MAXIT>
 __global__ void __launch_bounds__(128) finalize_bwd_kernel(FinBwdArgs a) {
   __shared__ float sh[4];
-  const int i = blockIdx.x;
   const int tid = threadIdx.x;
+  float ds_block = 0.f;  // thread 0: this block's share of sum_i dsrow[i]
+  // a few thousand blocks stride over the rows: one ticket atomic per BLOCK (per row they serialise on one
+  // address and cost more than the gradient traffic)
+  for (int i = blockIdx.x; i < a.b; i += gridDim.x) {
   const size_t gi = static_cast<size_t>(a.row0) + i;
   const __nv_bfloat16* rowp = a.gathered + gi * a.row_elems;
   const float inv_b = 1.f / static_cast<float>(a.b);
@@ -743,7 +817,7 @@ __global__ void __launch_bounds__(128) finalize_bwd_kernel(FinBwdArgs a) {
   if (tid == 0) {
     float d = 0.f;
     for (int s = 0; s < a.nds; ++s) d += a.ds1[s * a.b + i] + a.ds2[s * a.b + i];
-    a.dsrow[i] = d - 2.f * a.diag[i];
+    ds_block += d - 2.f * a.diag[i];
   }
 
   // ---- student KL (loss.py:358-383 backward): d z~ = (g / (b tau_s)) * acc3 ; chain through normalize
@@ -818,10 +892,14 @@ __global__ void __launch_bounds__(128) finalize_bwd_kernel(FinBwdArgs a) {
       *reinterpret_cast<float4*>(a.d_text + static_cast<size_t>(i) * a.D + f) = dt[it];
     }
   }
+  __syncthreads();  // sh is reused by the next row
+  }
   // ---- d logit_scale = g_classic / (2b) * sum_i dsrow[i], finished by the last block
+  if (tid == 0) a.dsrow[blockIdx.x] = ds_block;
   if (last_block_done(a.ticket)) {
     __shared__ double sum1[1];
-    block_reduce_rows(a.dsrow, a.b, 1, sum1);
+    block_reduce_rows(a.dsrow, gridDim.x, 1, sum1);
+    const float gc = a.gout[0] + a.lam_orig * a.gout[4];
     if (threadIdx.x == 0) a.d_scale[0] = static_cast<float>(sum1[0] * static_cast<double>(gc) * 0.5 / a.b);
   }
 }
@@ -1070,10 +1148,18 @@ extern "C" int dsoft_pack(const dsoft_plan_t* p, const void* image, int image_dt
   if ((rc = add(text, text_dt, ld_text, p->sh.D, p->offT))) return rc;
   if (p->have_proj && (rc = add(student, student_dt, ld_student, p->sh.Dp, p->offZ))) return rc;
   if (p->have_soft && (rc = add(dino, dino_dt, ld_dino, p->sh.Dd, p->offD))) return rc;
-  const int64_t total = a.pairs_end[a.nmat - 1];
+  bool vec8 = reinterpret_cast<uintptr_t>(base) % 16 == 0 && a.dst_ld % 8 == 0;
+  for (int k = 0; k < a.nmat; ++k) {
+    const PackSrc& m = a.m[k];
+    const int64_t per16 = m.dtype == DSOFT_DT_F32 ? 4 : 8;  // elements per 16 bytes
+    vec8 = vec8 && reinterpret_cast<uintptr_t>(m.src) % 16 == 0 && m.ld % per16 == 0 && m.cols % 8 == 0 &&
+           m.dst_off % 8 == 0;
+  }
   const int threads = 256;
+  const int64_t total = vec8 ? a.pairs_end[a.nmat - 1] / 4 : a.pairs_end[a.nmat - 1];
   const int blocks = static_cast<int>(std::min<int64_t>((total + threads - 1) / threads, 148 * 16));
-  pack_rows_kernel<<<blocks, threads, 0, st>>>(a, base);
+  if (vec8) pack_rows8_kernel<<<blocks, threads, 0, st>>>(a, base);
+  else pack_rows_kernel<<<blocks, threads, 0, st>>>(a, base);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -1127,8 +1213,7 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
     ra.mat[0] = g + p->offT; ra.cols[0] = p->sh.D;  ra.out[0] = S + p->st_rinv_t; ra.rmin[0] = S + p->st_scal + SC_RMIN_T;
     ra.mat[1] = g + p->offZ; ra.cols[1] = p->Dz;    ra.out[1] = S + p->st_rinv_z; ra.rmin[1] = S + p->st_scal + SC_RMIN_Z;
     ra.mat[2] = g + p->offD; ra.cols[2] = p->sh.Dd; ra.out[2] = S + p->st_rinv_d; ra.rmin[2] = S + p->st_scal + SC_RMIN_D;
-    const int wpb = 8;
-    rinv_kernel<<<dim3(ceil_div(p->Bcol, wpb), p->have_soft ? 3 : 1), wpb * 32, 0, st>>>(ra);
+    rinv_kernel<<<dim3(ceil_div(p->Bcol, 8 * RINV_ROWS_PER_WARP), p->have_soft ? 3 : 1), 256, 0, st>>>(ra);
     CUDA_TRY(cudaGetLastError());
   }
 
@@ -1537,7 +1622,13 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
   fa.text_lambda = lambdas[2];
   fa.ticket = reinterpret_cast<int*>(S + p->st_scal + SC_TICKET_B);
   fa.d_scale = d_scale;
-  finalize_bwd_kernel<<<b, 128, 0, st>>>(fa);
+  {
+    const int width = std::max(p->sh.D, p->Dz);
+    const dim3 grid(std::min(b, p->num_sms * 16));
+    if (width <= 512) finalize_bwd_kernel<1><<<grid, 128, 0, st>>>(fa);
+    else if (width <= 1024) finalize_bwd_kernel<2><<<grid, 128, 0, st>>>(fa);
+    else finalize_bwd_kernel<4><<<grid, 128, 0, st>>>(fa);
+  }
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
