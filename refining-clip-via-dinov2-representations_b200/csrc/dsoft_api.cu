@@ -69,7 +69,7 @@ struct dsoft_plan {
   // DSOFT_F_GMAT: two-phase backward through fp16 logit-gradient matrices in scratch
   int gmat;
   int pitch_c, pitch_s;  // columns of the CLIP / soft G matrices: multiples of 64
-  size_t sc_Gci, sc_Gct, sc_Gs, sc_Gx, sc_fwd_total;
+  size_t sc_Gci, sc_Gct, sc_Gs, sc_Gx, sc_Gs2, sc_Gx2, sc_fwd_total;
   SplitPlan g_clip, g_stu, g_txt;  // K splits of the gradient GEMMs (tps = K steps per split)
   SplitPlan g_clip_t;              // world == 1: dT = G^T . I, K runs over G's rows
   int clip_tr;                     // world == 1 two-phase: one CLIP logit-gradient matrix serves both directions
@@ -233,6 +233,9 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
     p->sc_Gct = take(p->clip_tr ? 0 : bpad * p->pitch_c / 2);
     p->sc_Gs = take(soft ? bpad * p->pitch_s / 2 : 0);
     p->sc_Gx = take(p->have_text ? bpad * p->pitch_s / 2 : 0);
+    // world == 1: row-scaled copies of the upper block triangle for the transposed reads of the soft GEMMs
+    p->sc_Gs2 = take(soft && p->clip_tr ? bpad * p->pitch_s / 2 : 0);
+    p->sc_Gx2 = take(p->have_text && p->clip_tr ? bpad * p->pitch_s / 2 : 0);
   }
   p->v_offT = 0;
   p->v_offI = sh->D;
@@ -290,7 +293,9 @@ extern "C" int dsoft_plan_kernel_flops(const dsoft_plan_t* p, double* algorithmi
     // (every similarity product recomputed once; the teacher product once for student and text)
     for (int k = 3; k < 7; ++k) executed[k] = algorithmic[k];
     if (n > 7) executed[7] = (p->clip_tr ? 1.0 : 2.0) * (2.0 * b * Bc * D);
-    if (n > 8 && p->have_soft) executed[8] = 2.0 * b * Bs * (Dz + Dd + (p->have_text ? D : 0.0));
+    if (n > 8 && p->have_soft)  // world == 1: only the upper block triangle (plus the 256-wide diagonal blocks)
+      executed[8] = (p->clip_tr ? 0.5 * (1.0 + 256.0 / std::max(256.0, Bs)) : 1.0) * 2.0 * b * Bs *
+                    (Dz + Dd + (p->have_text ? D : 0.0));
   }
   return 0;
 }
@@ -1299,14 +1304,19 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
 
 // Gradient GEMM launch: acc[split][b][dout] = G[b][pitch] . Y16[ycol0 + ..][voff .. voff + dout)
 // transposed = true (world == 1 only): acc[split][col][dout] = G^T . Y16, K runs over G's rows
+// G2 != null (world == 1, symmetric soft G): blocks left of each row pair's diagonal block are read transposed
+// from G2, the row-scaled copy of the upper block triangle
 static int launch_gy(const dsoft_plan* p, const __half* G, int pitch, const __half* v16, int voff, int dout,
-                     int ycol0, const SplitPlan& sp, float* acc, cudaStream_t st, bool transposed = false) {
-  CUtensorMap gmap, vmap;
+                     int ycol0, const SplitPlan& sp, float* acc, cudaStream_t st, bool transposed = false,
+                     const __half* G2 = nullptr) {
+  const bool tri = G2 != nullptr;
+  CUtensorMap gmap, gmap64, vmap;
   int rc;
   // blocked G: 64 columns x (row blocks * K tiles * 128) rows, one 16 KiB box per (row block, K tile)
   const int rbs = ceil_div(p->sh.b, BM);
   const int g_rows = rbs * (pitch / BK) * BM;
-  if ((rc = make_map(&gmap, G, g_rows, BK, BK, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, transposed ? 64 : BM))) return rc;
+  if ((rc = make_map(&gmap, G, g_rows, BK, BK, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, BM))) return rc;
+  if ((rc = make_map(&gmap64, tri ? G2 : G, g_rows, BK, BK, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 64))) return rc;
   if ((rc = make_map(&vmap, v16 + voff, p->B, dout, p->v_row, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 64))) return rc;
   GyParams P;
   P.b = p->sh.b;
@@ -1316,6 +1326,7 @@ static int launch_gy(const dsoft_plan* p, const __half* G, int pitch, const __ha
   P.nsplit = sp.nsplit;
   P.ycol0 = ycol0;
   P.g_ktiles = pitch / BK;
+  P.tri = tri ? 1 : 0;
   P.acc_part = acc;
   const int pairs = ceil_div(rbs, 2);
   cudaLaunchConfig_t cfg{};
@@ -1330,8 +1341,8 @@ static int launch_gy(const dsoft_plan* p, const __half* G, int pitch, const __ha
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (transposed) CUDA_TRY(cudaLaunchKernelEx(&cfg, dsoft_gy_kernel<true>, gmap, vmap, P));
-  else CUDA_TRY(cudaLaunchKernelEx(&cfg, dsoft_gy_kernel<false>, gmap, vmap, P));
+  if (transposed) CUDA_TRY(cudaLaunchKernelEx(&cfg, dsoft_gy_kernel<true>, gmap, gmap64, vmap, P));
+  else CUDA_TRY(cudaLaunchKernelEx(&cfg, dsoft_gy_kernel<false>, gmap, gmap64, vmap, P));
   return 0;
 }
 
@@ -1390,18 +1401,32 @@ static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* 
     P.row_only = p->row_only;
     P.rmin_idx[0] = SC_RMIN_Z;
     P.rmin_idx[1] = SC_RMIN_T;
+    // world == 1: the student / text / teacher matrices are symmetric, so G is: only the tiles from each row
+    // pair's diagonal block onwards are computed (half the work), in column chunks small enough to balance the
+    // triangular load; the gradient GEMMs read the other half through the transposed blocks
+    const bool tri = p->clip_tr;
+    int nsplit = p->f_soft.nsplit;
+    if (tri) {
+      P.tri = 1;
+      P.gout2[0] = reinterpret_cast<__half*>(X + p->sc_Gs2);
+      P.gout2[1] = reinterpret_cast<__half*>(X + p->sc_Gx2);
+      P.tiles_per_split = std::max(8, ceil_div(p->ntiles_s, 8));
+      nsplit = ceil_div(p->ntiles_s, P.tiles_per_split);
+    }
     {
       ProfScope ps(PK_BWD_GSOFT, ks);
-      if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_SOFT_G, 2>, rbs, p->f_soft.nsplit, ks, tm, P))) return rc;
+      if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_SOFT_G, 2>, rbs, nsplit, ks, tm, P))) return rc;
     }
     {
       ProfScope ps(PK_BWD_STU, ks);
-      if ((rc = launch_gy(p, Gs, p->pitch_s, v16, p->v_offZn, p->Dz, p->s_col0, p->g_stu, X + p->sc_acc3, ks)))
+      if ((rc = launch_gy(p, Gs, p->pitch_s, v16, p->v_offZn, p->Dz, p->s_col0, p->g_stu, X + p->sc_acc3, ks, false,
+                          tri ? P.gout2[0] : nullptr)))
         return rc;
     }
     if (p->have_text) {
       ProfScope ps(PK_BWD_TXT, ks);
-      if ((rc = launch_gy(p, Gx, p->pitch_s, v16, p->v_offTn, p->sh.D, p->s_col0, p->g_txt, X + p->sc_acc4, ks)))
+      if ((rc = launch_gy(p, Gx, p->pitch_s, v16, p->v_offTn, p->sh.D, p->s_col0, p->g_txt, X + p->sc_acc4, ks, false,
+                          tri ? P.gout2[1] : nullptr)))
         return rc;
     }
   }

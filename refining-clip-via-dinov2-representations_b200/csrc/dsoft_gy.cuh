@@ -40,13 +40,16 @@ struct GyParams {
   int nsplit;
   int ycol0;            // row of Y16 that matches K index 0
   int g_ktiles;         // 64-column tiles per row block of the blocked G (its pitch / 64)
+  int tri;              // symmetric G of which only the blocks from each row pair's 256-column diagonal block
+                        // onwards exist: K steps below 4 * pair read the transposed blocks instead (AT-style)
   float* acc_part;      // [nsplit][b][dout] fp32
 };
 
 template <bool AT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-dsoft_gy_kernel(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUtensorMap vmap,
-                const __grid_constant__ GyParams P) {
+dsoft_gy_kernel(const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUtensorMap gmap64,
+                const __grid_constant__ CUtensorMap vmap, const __grid_constant__ GyParams P) {
+  // gmap: 128-row boxes (K-major A tiles); gmap64: 64-row boxes of the same matrix (transposed, MN-major A tiles)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GY_STAGES * SLAB);
@@ -69,6 +72,7 @@ dsoft_gy_kernel(const __grid_constant__ CUtensorMap gmap, const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&gmap);
+    tma_prefetch_desc(&gmap64);
     tma_prefetch_desc(&vmap);
     for (int i = 0; i < GY_STAGES; ++i) {
       mbar_init(smem_u32(&ring_full[i]), 1);
@@ -93,11 +97,11 @@ dsoft_gy_kernel(const __grid_constant__ CUtensorMap gmap, const __grid_constant_
         const uint32_t full_leader = mapa_shared(full, 0);
         const uint32_t dst = smem_u32(smem + stage * SLAB);
         if (leader) mbar_arrive_expect_tx(full, 2 * SLAB);
-        if constexpr (AT) {
+        if (AT || (P.tri && k < 4 * pair)) {
           // K step k = G rows [64k, 64k + 64) = half `k & 1` of row block `k >> 1`; M = G columns 128 rb ..
           const int grow = ((k >> 1) * P.g_ktiles + 2 * rb) * BM + (k & 1) * 64;
-          tma_load_2d_2sm(dst, &gmap, full_leader, 0, grow);
-          tma_load_2d_2sm(dst + TILE_BYTES / 2, &gmap, full_leader, 0, grow + BM);
+          tma_load_2d_2sm(dst, &gmap64, full_leader, 0, grow);
+          tma_load_2d_2sm(dst + TILE_BYTES / 2, &gmap64, full_leader, 0, grow + BM);
         } else {
           tma_load_2d_2sm(dst, &gmap, full_leader, 0, (rb * P.g_ktiles + k) * BM);
         }
@@ -111,19 +115,21 @@ dsoft_gy_kernel(const __grid_constant__ CUtensorMap gmap, const __grid_constant_
     if (leader) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t idesc = make_idesc_bf16(2 * BM, GY_N, AT ? 1 : 0, 1, 1);  // fp16, B MN-major
+      const uint32_t idesc_n = make_idesc_bf16(2 * BM, GY_N, 0, 1, 1);  // fp16, A K-major, B MN-major
+      const uint32_t idesc_t = make_idesc_bf16(2 * BM, GY_N, 1, 1, 1);  // fp16, A MN-major (transposed blocks)
       for (int k = k0; k < k1; ++k) {
         mbar_wait(smem_u32(&ring_full[stage]), phase);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + stage * SLAB);
           const uint32_t v_addr = a_addr + TILE_BYTES;
+          const bool tr = AT || (P.tri && k < 4 * pair);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t ad = AT ? make_smem_desc(a_addr + kk * 2048, TILE_BYTES / 2, 1024)
+            const uint64_t ad = tr ? make_smem_desc(a_addr + kk * 2048, TILE_BYTES / 2, 1024)
                                    : make_smem_desc(a_addr + kk * 32, 16, 1024);
             const uint64_t bd = make_smem_desc(v_addr + kk * 2048, TILE_BYTES / 2, 1024);
-            umma_cg<2>(tmem_base, ad, bd, idesc, (k == k0 && kk == 0) ? 0u : 1u);
+            umma_cg<2>(tmem_base, ad, bd, tr ? idesc_t : idesc_n, (k == k0 && kk == 0) ? 0u : 1u);
           }
           umma_commit_cg<2>(smem_u32(&ring_empty[stage]));
           if (k == k1 - 1) umma_commit_cg<2>(smem_u32(acc_full));

@@ -90,10 +90,14 @@ struct FwdParams {
   const float* lse_col[3];  // per product: LSE by global column (clip: the OTHER direction's)
   __half* gout[2];          // fp16 logit gradients, blocked [row block][64-col K tile][128 rows][64 cols]:
                             // clip -> gout[0]; soft -> gout[0] student, gout[1] text
+  __half* gout2[2];         // soft, tri: same tiles scaled for the transposed read (see the epilogue)
   int g_pitch;              // columns of G (multiple of 64 >= ncols)
   int row_only;             // gather_with_grad == False: drop the column-side terms
   int rmin_idx[2];          // soft: SC_RMIN_Z, SC_RMIN_T (scale of the fp16 gradient operand)
   float* ds_part;           // clip: d(logit_scale) row partials [npart][b]
+  int tri;                  // soft G, world == 1: the matrices are symmetric -> only the column tiles from the row
+                            // pair's own 256-column diagonal block onwards are computed (tile 2 * (rb / 2) ..);
+                            // the gradient GEMM takes the missing part from the transposed blocks
   int ds_both;              // clip, world == 1: one launch serves both directions (the text rows' matrix is the
                             // transpose), so the row partial also takes the column-side term
 };
@@ -142,6 +146,13 @@ __device__ __forceinline__ void issue_s_stage(uint32_t tmem_d, uint32_t a_smem, 
   }
 }
 
+// 8 packed fp16 pairs -> one 32-byte evict-first store
+__device__ __forceinline__ void st_cs_v8(void* dst, const uint32_t (&w)[8]) {
+  asm volatile("st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(w[0]), "r"(w[1]),
+               "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+
 // element (local row li, column j) of a blocked fp16 logit-gradient matrix: K tiles of 64 columns, each
 // (row block, K tile) = one 16 KiB TMA box of the gradient GEMM's A operand
 __device__ __forceinline__ size_t g_index(int li, int j, int pitch) {
@@ -156,9 +167,32 @@ __device__ __forceinline__ void store_g32(__half* dst, const float (&g)[32]) {
     uint32_t w[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) w[k] = pack_f16x2(g[16 * i + 2 * k], g[16 * i + 2 * k + 1]);
-    asm volatile("st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 16 * i), "r"(w[0]),
-                 "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
-                 : "memory");
+    st_cs_v8(dst + 16 * i, w);
+  }
+}
+// same with one factor for the whole row chunk
+__device__ __forceinline__ void store_g32_scaled(__half* dst, const float (&g)[32], float f) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    uint32_t w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = pack_f16x2(g[16 * i + 2 * k] * f, g[16 * i + 2 * k + 1] * f);
+    st_cs_v8(dst + 16 * i, w);
+  }
+}
+// same with per-column factors min(rinv[e] * isig, 1e4) (rinv: 32 floats in shared memory)
+__device__ __forceinline__ void store_g32_colscaled(__half* dst, const float (&g)[32], const float4* rinv, float isig) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    uint32_t w[8];
+#pragma unroll
+    for (int k4 = 0; k4 < 4; ++k4) {
+      const float4 r = rinv[4 * i + k4];
+      const int e = 16 * i + 4 * k4;
+      w[2 * k4 + 0] = pack_f16x2(g[e + 0] * fminf(r.x * isig, 1.0e4f), g[e + 1] * fminf(r.y * isig, 1.0e4f));
+      w[2 * k4 + 1] = pack_f16x2(g[e + 2] * fminf(r.z * isig, 1.0e4f), g[e + 3] * fminf(r.w * isig, 1.0e4f));
+    }
+    st_cs_v8(dst + 16 * i, w);
   }
 }
 
@@ -210,8 +244,8 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
   const int rb = blockIdx.x;
   const int split = blockIdx.y;
-  const int t0 = split * P.tiles_per_split;
-  const int t1 = min(t0 + P.tiles_per_split, P.ntiles);
+  const int t0 = (P.tri ? 2 * (rb >> 1) : 0) + split * P.tiles_per_split;
+  const int t1 = min(t0 + P.tiles_per_split, P.ntiles);  // may be <= t0 (triangular mode): nothing to do
   const int prank = (CG == 2) ? (rb & 1) : 0;  // rank in the pair (== cluster rank)
   const bool leader = prank == 0;
 
@@ -488,6 +522,7 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       const float lt = P.lse_row[0][lic];
       const bool row_only = P.row_only != 0;
       const bool real_block = rb * BM < P.b;
+      const bool live_row = li < P.b;  // rows past b are K entries of the transposed gradient GEMM: keep them zero
       float E[64];  // -(teacher terms) of this thread's 64 columns, kept across the student / text products
       int it = 0;
       for (int t = t0; t < t1; ++t, it += P.nprod) {
@@ -556,11 +591,17 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
                 const float p2 = v[e] * cy * rr[k];
                 const float e1 = fast_exp2(p2 - ly);
                 const float e2 = row_only ? 0.f : fast_exp2(p2 - ll[k]);
-                const bool dead = (gj0 + e == gi) || (jrel0 + e >= P.ncols);
-                g[e] = dead ? 0.f : (E[c * 32 + e] + (e1 + e2)) * fminf(rr[k] * isig, 1.0e4f);
+                const bool dead = (gj0 + e == gi) || (jrel0 + e >= P.ncols) || !live_row;
+                g[e] = dead ? 0.f : E[c * 32 + e] + (e1 + e2);  // symmetric in (a, j) when world == 1
               }
             }
-            if (real_block && jrel0 + 32 <= P.g_pitch) store_g32(P.gout[p - 1] + g_index(li, jrel0, P.g_pitch), g);
+            if (real_block && jrel0 + 32 <= P.g_pitch) {
+              // the fp16 operand row is y_j * sigma (exact), so G carries 1 / (||y_j|| sigma) of its COLUMN ...
+              const size_t go = g_index(li, jrel0, P.g_pitch);
+              store_g32_colscaled(P.gout[p - 1] + go, g, rc, isig);
+              // ... and the copy the triangular GEMM reads transposed (K index = this row) that of its ROW
+              if (P.tri) store_g32_scaled(P.gout2[p - 1] + go, g, fminf(P.rinv[p][gi] * isig, 1.0e4f));
+            }
           }
         }
         mbar_arrive(smem_u32(&col_empty[cb]));
