@@ -173,7 +173,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
@@ -183,11 +183,15 @@ class ClockSampler:
                 sm.append(float(f[0])); mx.append(float(f[1]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[2]))
+            except ValueError:
+                pass
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w": statistics.median(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -393,7 +397,11 @@ def run_ours(args):
             "metric": METRIC, "value": GLOBAL_B * args.steps / (ms / 1e3), "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": workload_config(world),
+            "config": dict(workload_config(world),
+                           backward=("two-phase: fp16 logit-gradient matrices + M=256xN=256 gradient GEMMs"
+                                     + (", symmetric shortcuts (world 1)" if world == 1 else "")
+                                     if plan.shape.flags & _cabi.DSOFT_F_GMAT else
+                                     "fused: logit gradients stay in shared memory")),
             "clocks": clocks,
             "e2e": None if args.no_e2e else {
                 "value": GLOBAL_B * args.steps / (ms_e2e / 1e3), "unit": "samples/s",

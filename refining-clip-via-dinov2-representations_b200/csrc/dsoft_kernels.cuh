@@ -244,8 +244,15 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
   const int rb = blockIdx.x;
   const int split = blockIdx.y;
-  const int t0 = (P.tri ? 2 * (rb >> 1) : 0) + split * P.tiles_per_split;
-  const int t1 = min(t0 + P.tiles_per_split, P.ntiles);  // may be <= t0 (triangular mode): nothing to do
+  // triangular mode: column chunks are aligned from the END of the row for every row pair, so that the CTAs of
+  // one chunk index (launched next to each other) stream the same column tiles at the same time and share them
+  // in L2; a pair's lowest chunk is cut at its diagonal block and the chunks left of it are empty
+  int t0 = split * P.tiles_per_split;
+  int t1 = min(t0 + P.tiles_per_split, P.ntiles);
+  if (P.tri) {
+    t1 = P.ntiles - split * P.tiles_per_split;
+    t0 = max(t1 - P.tiles_per_split, 2 * (rb >> 1));  // may be >= t1: nothing to do
+  }
   const int prank = (CG == 2) ? (rb & 1) : 0;  // rank in the pair (== cluster rank)
   const bool leader = prank == 0;
 

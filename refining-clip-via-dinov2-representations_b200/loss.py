@@ -212,6 +212,9 @@ GMAT = os.environ.get("DSOFT_GMAT", "auto")
 GMAT_FRACTION = 0.5
 
 
+_gmat_decisions = {}
+
+
 def _gmat_fits(b, W, soft, text, soft_local, dev) -> bool:
     if GMAT == "never":
         return False
@@ -219,9 +222,22 @@ def _gmat_fits(b, W, soft, text, soft_local, dev) -> bool:
         return True
     if dev.type != "cuda":
         return False
+    key = (b, W, soft, text, soft_local, dev.index)
+    hit = _gmat_decisions.get(key)
+    if hit is not None:  # decided when this shape was first seen: no driver query on the step path
+        return hit
+    _gmat_decisions[key] = _gmat_fits_now(b, W, soft, text, soft_local, dev)
+    return _gmat_decisions[key]
+
+
+def _gmat_fits_now(b, W, soft, text, soft_local, dev) -> bool:
     B = b * W
     cols_s = b if soft_local else B
-    need = 2 * b * (2 * B + ((1 if soft else 0) + (1 if text else 0)) * cols_s)
+    n_soft = (1 if soft else 0) + (1 if text else 0)
+    if W == 1:  # one CLIP matrix, but a row-scaled second copy of each soft matrix (triangular backward)
+        need = 2 * b * (B + 2 * n_soft * cols_s)
+    else:
+        need = 2 * b * (2 * B + n_soft * cols_s)
     free, _total = torch.cuda.mem_get_info(dev)
     cached = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
     return need <= GMAT_FRACTION * (free + cached)
