@@ -372,9 +372,10 @@ def run_ours(args):
             kern[name] = {"ms": round(avg_ms, 4), "alg_tflops": round(alg[k] / avg_ms / 1e9, 1),
                           "exec_tflops": round(exe[k] / avg_ms / 1e9, 1), "launches": cnt[k]}
         # DRAM bytes (read + write) per launch from the ncu --set full capture of this exact workload
-        # (profiles/r01b_ncu_full_tile_kernels.csv); only meaningful for the default configuration
-        ncu_traffic = {"fwd_clip_i2t": 73.8e6, "fwd_clip_t2i": 73.7e6, "fwd_soft": 1009.5e6, "bwd_clip_image": 309.0e6,
-                       "bwd_clip_text": 310.1e6, "bwd_student": 1209.1e6, "bwd_text": 563.3e6}
+        # (profiles/r01c_ncu_full_tile_kernels.csv); only meaningful for the default configuration
+        ncu_traffic = {"fwd_clip_i2t": 74.3e6, "fwd_clip_t2i": 74.3e6, "fwd_soft": 1702.8e6,
+                       "bwd_clip_image": 2345.1e6, "bwd_clip_text": 2347.1e6, "bwd_student": 2622.9e6,
+                       "bwd_text": 2346.0e6, "bwd_build_g_clip": 2321.0e6, "bwd_build_g_soft": 13604.2e6}
         # dominant kernel = the longest launch that carries algorithmic FLOPs (the logit-gradient kernels of
         # the two-phase backward only recompute similarity tiles: SURVEY 8(d) counts those products once, in
         # the forward; their executed FLOPs are in `kernels`)
