@@ -391,11 +391,11 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     float v[32];
     auto release_slot = [&](int slot) {  // the MMA issuer lives in the pair's leader
       if constexpr (CG == 2) {
-        // the G modes have global stores in flight: do not make the arrive wait for them
-        if constexpr (MODE == MODE_CLIP_G || MODE == MODE_SOFT_G)
-          mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&s_empty[slot]), 0));
-        else
-          mbar_arrive_cluster(mapa_shared(smem_u32(&s_empty[slot]), 0));
+        // relaxed: a .release arrive is a MEMBAR that waits for every earlier memory operation of the thread
+        // (ncu: "membar" was the top stall of the soft epilogue, and with the G stores in flight it serialised
+        // the G kernels).  The barrier only hands back TMEM, whose reads are complete (tcgen05.wait::ld) and
+        // ordered by fence::before_thread_sync.
+        mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&s_empty[slot]), 0));
       } else {
         mbar_arrive(smem_u32(&s_empty[slot]));
       }

@@ -1,4 +1,4 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_robustness.py -m gpu -x -q 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_selftest.py -m gpu -x -q 2>&1 | tail -2
 timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/tri.log 2>&1
 python - <<PY
 import json
