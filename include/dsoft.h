@@ -87,10 +87,12 @@ size_t dsoft_plan_scratch_bytes(const dsoft_plan_t* plan);
 size_t dsoft_plan_forward_scratch_bytes(const dsoft_plan_t* plan);
 /* Algorithmic FLOPs of one fwd+bwd evaluation for this rank (SURVEY.md 8(d) formula / world). */
 double dsoft_plan_algorithmic_flops(const dsoft_plan_t* plan);
-/* FLOPs of the 7 tile-kernel launches of one fwd+bwd for this rank, in dsoft_profile_read order:
- * fwd clip i->t, fwd clip t->i, fwd soft, bwd clip (image rows), bwd clip (text rows), bwd student,
- * bwd text.  `algorithmic` follows SURVEY.md 8(d) (each distinct product once, no recompute);
- * `executed` is what the tensor cores really do (tile recompute per 256-feature chunk included). */
+/* FLOPs of the tile-kernel launches of one fwd+bwd for this rank, in dsoft_profile_read order (n >= 7;
+ * 9 slots are filled when available): fwd clip i->t, fwd clip t->i, fwd soft, bwd clip (image rows), bwd
+ * clip (text rows), bwd student, bwd text, [7] CLIP logit-gradient kernel(s), [8] soft logit-gradient kernel
+ * (the last two only with DSOFT_F_GMAT, where slots 3..6 are the gradient GEMMs).  `algorithmic` follows
+ * SURVEY.md 8(d) (each distinct product once, no recompute); `executed` is what the tensor cores really do
+ * (tile recompute included). */
 int dsoft_plan_kernel_flops(const dsoft_plan_t* plan, double* algorithmic, double* executed, int n);
 /* Number of CUDA kernels dsoft_forward / dsoft_backward launch (for bench.py's gpu_launches). */
 int dsoft_plan_launches_forward(const dsoft_plan_t* plan);

@@ -310,21 +310,6 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const CUtenso
       : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1)
       : "memory");
 }
-// L2 eviction-priority policies for loads that must survive a concurrent stream of stores through L2
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ void tma_load_2d_2sm_hint(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar_cluster,
-                                                     int32_t c0, int32_t c1, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      :
-      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "l"(policy)
-      : "memory");
-}
 // arrive on an mbarrier of another CTA of the cluster (address from mapa_shared)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
