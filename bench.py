@@ -159,7 +159,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -168,14 +168,23 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
-    def stop(self):
+    def mark(self):
+        """Index of the next sample: brackets the timed region inside a sampler that is already running (the
+        nvidia-smi process needs ~0.1 s to start, longer than a whole timed region on 8 GPUs)."""
+        return len(self.lines)
+
+    def stop(self, first=0, last=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
+        last = len(self.lines) if last is None else last
+        window = self.lines[first:last]
+        if not window:  # region shorter than one sampling period: the samples around it
+            window = self.lines[max(0, first - 1):last + 1]
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in window:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -217,6 +226,11 @@ def run_ours(args):
     assert GLOBAL_B % world == 0
     b = GLOBAL_B // world
     lib = _cabi.lib()
+    # started before the inputs are generated: nvidia-smi needs ~0.1 s to come up, longer than a whole timed
+    # region on 8 GPUs; mark() brackets the timed region in its sample stream
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
 
     img, txt, dino = synth(1234 + rank, b, D_CLIP, D_DINO, dev)
     larg = types.SimpleNamespace(**LOSS_ARGS)
@@ -253,9 +267,7 @@ def run_ours(args):
     barrier()
 
     # ---- timed region: resident inputs
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    clk_first = sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -282,7 +294,7 @@ def run_ours(args):
     p1.record()
     barrier()
     ms_serial = p0.elapsed_time(p1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(clk_first, sampler.mark()) if rank == 0 else None
     ms_sum = (C.c_double * NK)()
     cnt = (C.c_int * NK)()
     _cabi.check(lib.dsoft_profile_read(ms_sum, cnt, NK), "dsoft_profile_read")
