@@ -43,6 +43,7 @@ __all__ = [
     "round_bf16",
     "mlp_head",
     "rank_loss",
+    "weighted_ce",
     "loss_and_grads",
 ]
 
@@ -66,6 +67,11 @@ class OracleConfig:
     # residual projection (loss.py:331-343): only active when the head keeps the width (Dd == D)
     residual_projection: bool = False
     residual_alpha: Optional[float] = None
+    # denominator-modulated ("weighted") CE branch (loss.py:416-471); single-rank only in the reference
+    lambda_weighted: float = 0.0
+    rho: float = 0.1
+    c_clip: float = 1.0
+    weight_text_symmetry: bool = False
     # operand rounding of the B200 path (the reference has none): student operand rounded to bf16
     round_student_bf16: bool = False
     extra: Dict[str, object] = field(default_factory=dict)
@@ -129,6 +135,52 @@ def _kl_batchmean(student_logits: torch.Tensor, q: torch.Tensor) -> torch.Tensor
     log_p = student_logits - _row_lse(student_logits).unsqueeze(1)
     qlogq = torch.where(q > 0, q * q.clamp_min(torch.finfo(q.dtype).tiny).log(), torch.zeros_like(q))
     return (qlogq - q * log_p).sum() / student_logits.shape[0]
+
+
+def _modulated_logits(logits: torch.Tensor, r: torch.Tensor, rho: float, c_clip: float) -> torch.Tensor:
+    """One direction of the DINO-guided logit modulation (loss.py:432-446 / 450-463).
+
+    ``r`` is the DINO dissimilarity in the orientation of ``logits`` with a zero diagonal.  The offsets are
+    p-centred with the UNMODIFIED row soft-max (gradient flows through it), clamped to +-c_clip and scaled by
+    beta = rho * median_row(std_row(logits)) / c_clip, a host float (``.item()``: no gradient)."""
+    p_base = torch.softmax(logits, dim=1)
+    centred = (r - (p_base * r).sum(dim=1, keepdim=True)).clamp(min=-c_clip, max=c_clip)
+    with torch.no_grad():
+        # torch.std: unbiased; torch.median: the lower of the two middle values for an even row count
+        sigma = torch.median(logits.float().std(dim=1)).clamp(min=1e-6)
+    beta = float(rho * sigma / c_clip)
+    n = logits.shape[0]
+    idx = torch.arange(n)
+    delta = beta * centred
+    delta = delta.clone()
+    delta[idx, idx] = 0.0  # masked_fill(eye, 0): the positive pair's logit is never shifted
+    return logits + delta, beta
+
+
+def weighted_ce(logits_it: torch.Tensor, logits_ti: torch.Tensor, dino: torch.Tensor, labels: torch.Tensor,
+                cfg: "OracleConfig") -> Dict[str, object]:
+    """Denominator-modulated CLIP CE (loss.py:416-471): 0.5 * (CE(L_it + Delta_it) + CE(L_ti [+ Delta_ti])).
+
+    Needs square [b, b] logits: the reference builds ``r`` and the diagonal mask from the LOCAL batch
+    (loss.py:423-429), so the branch only runs with one rank."""
+    b = dino.shape[0]
+    if logits_it.shape != (b, b):
+        raise RuntimeError(
+            f"The size of tensor a ({logits_it.shape[1]}) must match the size of tensor b ({b}) at non-singleton "
+            "dimension 1")
+    with torch.no_grad():
+        dn = _l2_normalize(dino)
+        r = 1.0 - (dn @ dn.T).clamp(-1, 1)
+        idx = torch.arange(b)
+        r[idx, idx] = 0.0
+    it_tilde, beta_img = _modulated_logits(logits_it, r, float(cfg.rho), float(cfg.c_clip))
+    beta_txt = 0.0
+    if cfg.weight_text_symmetry:
+        ti_tilde, beta_txt = _modulated_logits(logits_ti, r.T, float(cfg.rho), float(cfg.c_clip))
+    else:
+        ti_tilde = logits_ti
+    loss = 0.5 * (_cross_entropy_mean(it_tilde, labels) + _cross_entropy_mean(ti_tilde, labels))
+    return {"loss": loss, "beta_img": beta_img, "beta_txt": beta_txt}
 
 
 def mlp_head(x: torch.Tensor, params: Dict[str, torch.Tensor], projection_type: str = "mlp") -> torch.Tensor:
@@ -222,8 +274,14 @@ def rank_loss(
             s_tt = (t_all[rows] @ t_cols.T) / float(cfg.text_student_temp)
             soft_txt = _kl_batchmean(s_tt, q)
     soft = soft_img + (float(cfg.text_lambda) * soft_txt if cfg.text_enabled else 0.0)
-    total = float(cfg.lambda_original) * classic + float(cfg.lambda_soft) * soft  # loss.py:473-477
-    out.update(soft_img=soft_img, soft_txt=soft_txt, soft_loss=soft, total_loss=total)
+    weighted = torch.zeros((), dtype=image_all.dtype)
+    if float(cfg.lambda_weighted) > 0.0 and dino_all is not None and b > 1:  # loss.py:422
+        wres = weighted_ce(logits_it, logits_ti, dino_all[rows], labels, cfg)
+        weighted = wres["loss"]
+        out.update(beta_img=wres["beta_img"], beta_txt=wres["beta_txt"])
+    total = (float(cfg.lambda_original) * classic + float(cfg.lambda_soft) * soft
+             + float(cfg.lambda_weighted) * weighted)  # loss.py:473-477
+    out.update(soft_img=soft_img, soft_txt=soft_txt, soft_loss=soft, weighted_loss=weighted, total_loss=total)
     return out
 
 
@@ -282,7 +340,7 @@ def loss_and_grads(
             own["total_loss"].backward()
             g_sc = sc.grad
         rows = slice(r * b, (r + 1) * b)
-        entry = {k: float(v.detach()) for k, v in own.items()}
+        entry = {k: float(v.detach()) if torch.is_tensor(v) else float(v) for k, v in own.items()}
         entry["d_image"] = im.grad[rows].detach().clone()
         entry["d_text"] = tx.grad[rows].detach().clone()
         entry["d_logit_scale"] = float(g_sc)

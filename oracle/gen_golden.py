@@ -137,6 +137,14 @@ CASES = [
     dict(name="w1_residual_alpha", B=56, D=64, Dd=64, scale=25.0, world=1, clustered=True,
          args=dict(use_projection=True, projection_type="linear", residual_projection=True, residual_alpha=0.3,
                    lambda_soft=0.5, soft_mode="kl_teacher", teacher_temp=0.2)),
+    # denominator-modulated CE branch (loss.py:416-471): alone, and with every other term switched on
+    dict(name="w1_weighted", B=64, D=64, Dd=96, scale=14.2857, world=1, clustered=True,
+         args=dict(use_projection=False, lambda_soft=0.0, soft_mode="none", lambda_weighted=0.5, rho=0.1,
+                   c_clip=1.0, weight_text_symmetry=False)),
+    dict(name="w1_weighted_sym_all_terms", B=80, D=64, Dd=96, scale=40.0, world=1, clustered=True,
+         args=dict(use_projection=True, projection_type="mlp", lambda_soft=0.5, soft_mode="kl_teacher",
+                   soft_dino_to_text=True, text_lambda=0.5, text_student_temp=0.02, teacher_temp=0.15,
+                   lambda_weighted=0.7, rho=0.2, c_clip=0.5, weight_text_symmetry=True)),
     dict(name="w2_gather_grad", B=64, D=64, Dd=96, scale=14.2857, world=2, clustered=True,
          local_loss=True, gather_with_grad=True,
          args=dict(use_projection=True, projection_type="mlp", lambda_soft=0.5, soft_mode="kl_teacher",
@@ -148,11 +156,21 @@ CASES = [
 ]
 
 
+# input / head seeds per fixture: the position the case had when its fixture was first generated
+SEED_INDEX = {"w1_noproj_text": 0, "w1_mlp_text_scale100": 1, "w1_linear_notext": 2, "w1_mlp_layernorm": 3,
+              "w1_classic_only": 4, "w1_scale_below_10": 5, "w1_residual": 6, "w1_residual_alpha": 7,
+              "w2_gather_grad": 8, "w2_no_gather_grad": 9, "w1_weighted": 10, "w1_weighted_sym_all_terms": 11}
+
+
 def main():
     os.makedirs(OUT_DIR, exist_ok=True)
     ref = load_reference()
     port = 29611
-    for ci, case in enumerate(CASES):
+    only = set(sys.argv[1:])  # optional: fixture names to (re)generate; seeds depend on the case NAME, not order
+    for case in CASES:
+        if only and case["name"] not in only:
+            continue
+        ci = SEED_INDEX[case["name"]]
         img, txt, dino = synth_inputs(1234 + ci, case["B"], case["D"], case["Dd"], case["clustered"])
         args = types.SimpleNamespace(**case["args"])
         world = case["world"]

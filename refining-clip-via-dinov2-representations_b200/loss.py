@@ -18,7 +18,8 @@ Differences from the reference that are deliberate and documented in DESIGN.md:
     is rounded with a straight-through gradient); all soft-max / KL arithmetic is fp32;
   * at world_size > 1 the soft terms default to the *global* row block (``soft_scope="global"``);
     ``soft_scope="local"`` reproduces the reference's local b x b block;
-  * the weighted-CE branch (loss.py:416-471, lambda_weighted > 0) is not implemented yet and raises;
+  * the weighted-CE branch (loss.py:416-471, lambda_weighted > 0; one rank only, off by default) runs as
+    fp32 PyTorch tensor ops next to the fused terms (fused kernels for it are the next step);
   * Horovod is not supported (``use_horovod=True`` raises).
 """
 from __future__ import annotations
@@ -313,6 +314,91 @@ class _DinoSoftFn(torch.autograd.Function):
 
 
 # --------------------------------------------------------------------------------------------------
+# denominator-modulated ("weighted") CE branch, loss.py:416-471 + diagnostics loss.py:479-595
+# --------------------------------------------------------------------------------------------------
+# Optional (lambda_weighted defaults to 0), single-rank only in the reference, and next in line for fused
+# kernels.  Until then it runs as plain fp32 PyTorch tensor ops on the inputs' device
+# (cuBLAS + element-wise kernels, [B, B] intermediates like the reference) next to the fused classic / soft
+# terms; autograd provides its backward.  Differences from the reference: fp32 logits also under autocast, and
+# beta stays a detached device scalar instead of `.item()` (no host synchronisation; same value).
+def _shift_logits(logits: torch.Tensor, dissim: torch.Tensor, rho: float, c_clip: float):
+    """logits + beta * clamp(r - E_p[r]) with a zero diagonal; p = soft-max of the UNMODIFIED rows (carries
+    gradient), beta = rho * median(row std) / c_clip (no gradient)."""
+    p_rows = torch.softmax(logits, dim=1)
+    r_hat = (dissim - (p_rows * dissim).sum(dim=1, keepdim=True)).clamp(min=-c_clip, max=c_clip)
+    with torch.no_grad():
+        beta = rho * torch.median(logits.float().std(dim=1)).clamp(min=1e-6) / c_clip
+    delta = (beta * r_hat).clone()
+    delta.diagonal().zero_()
+    return logits + delta, delta, r_hat, p_rows, beta
+
+
+def _row_corr_mean(a: torch.Tensor, b: torch.Tensor, eps: float = 1e-9) -> torch.Tensor:
+    a = a - a.mean(dim=1, keepdim=True)
+    b = b - b.mean(dim=1, keepdim=True)
+    den = a.pow(2).sum(dim=1).sqrt() * b.pow(2).sum(dim=1).sqrt() + eps
+    return ((a * b).sum(dim=1) / den).mean()
+
+
+def _weighted_ce_branch(image_features, text_features, logit_scale, dino_features, rho, c_clip, text_sym):
+    """Returns (weighted_loss, dbg).  dbg holds the reference's diagnostic keys as 0-dim tensors (formatting
+    one of them, as train.py:360-364 does every 300 steps, is what synchronises)."""
+    B = image_features.shape[0]
+    img, txt = image_features.float(), text_features.float()
+    logits_i = logit_scale.float() * (img @ txt.T)
+    logits_t = logits_i.T  # one rank: logits_per_text is the exact transpose (loss.py:272-273)
+    labels = torch.arange(B, device=img.device)
+    with torch.no_grad():
+        dn = F.normalize(dino_features.float(), dim=-1)
+        dissim = 1.0 - (dn @ dn.T).clamp(-1, 1)
+        dissim.diagonal().zero_()
+    tilde_i, delta_i, rhat_i, p_i, beta_i = _shift_logits(logits_i, dissim, rho, c_clip)
+    if text_sym:
+        tilde_t, delta_t, rhat_t, p_t, beta_t = _shift_logits(logits_t, dissim.T, rho, c_clip)
+    else:
+        tilde_t, delta_t, rhat_t, p_t, beta_t = logits_t, None, None, None, None
+    ce_i = F.cross_entropy(tilde_i, labels)
+    ce_t = F.cross_entropy(tilde_t, labels)
+    loss = 0.5 * (ce_i + ce_t)
+
+    with torch.no_grad():
+        zero = torch.zeros((), device=img.device)
+        off = float(B * B - B)
+
+        def side(delta, r_hat, p_base, tilde):
+            if delta is None:
+                return dict(pc=zero, dmax=zero, dmean=zero, dstd=zero, diag=zero, corr=zero, pos=zero)
+            p_mod = torch.softmax(tilde, dim=1)
+            d_abs = delta.abs()
+            pos = ((r_hat > 0).float().sum() - (r_hat.diagonal() > 0).float().sum()) / off
+            return dict(pc=(p_base * r_hat).sum(dim=1).abs().mean(), dmax=d_abs.max(), dmean=d_abs.mean(),
+                        dstd=d_abs.std(), diag=r_hat.diagonal().abs().max(),
+                        corr=_row_corr_mean(r_hat, p_mod - p_base), pos=pos)
+
+        si = side(delta_i, rhat_i, p_i.detach(), tilde_i.detach())
+        st = side(delta_t, None if rhat_t is None else rhat_t, None if p_t is None else p_t.detach(),
+                  tilde_t.detach())
+        p_t_base = torch.softmax(logits_t.detach(), dim=1)
+        dbg = {
+            "pc_err_img": si["pc"], "pc_err_txt": st["pc"],
+            "diag_max_img": si["diag"], "diag_max_txt": st["diag"],
+            "delta_img_max": si["dmax"], "delta_img_mean": si["dmean"], "delta_img_std": si["dstd"],
+            "delta_txt_max": st["dmax"], "delta_txt_mean": st["dmean"], "delta_txt_std": st["dstd"],
+            "l1_prob_shift_img": (torch.softmax(tilde_i.detach(), dim=1) - p_i.detach()).abs().sum(dim=1).mean(),
+            "l1_prob_shift_txt": (torch.softmax(tilde_t.detach(), dim=1) - p_t_base).abs().sum(dim=1).mean(),
+            "corr_rhat_dprob_img": si["corr"], "corr_rhat_dprob_txt": st["corr"],
+            "ce_img_base": F.cross_entropy(logits_i.detach(), labels),
+            "ce_txt_base": F.cross_entropy(logits_t.detach(), labels),
+            "ce_img_mod": ce_i.detach(), "ce_txt_mod": ce_t.detach(),
+            "pos_frac_img": si["pos"], "neg_frac_img": 1.0 - si["pos"],
+            "pos_frac_txt": st["pos"], "neg_frac_txt": (1.0 - st["pos"]) if text_sym else zero,
+            "beta_img": beta_i, "beta_txt": beta_t if text_sym else zero,
+            "rho": rho, "clip_c": c_clip,
+        }
+    return loss, dbg
+
+
+# --------------------------------------------------------------------------------------------------
 # the loss module (same class name / ctor / forward signature as loss.py:190-300)
 # --------------------------------------------------------------------------------------------------
 class ClipLossWithDINOEnhancements(nn.Module):
@@ -429,10 +515,13 @@ class ClipLossWithDINOEnhancements(nn.Module):
                 f"Expected input batch_size ({B * self.world_size}) to match target batch_size ({B})."
             )
         lambda_weighted = float(g(args, "lambda_weighted", 0.0))
-        if lambda_weighted > 0.0 and dino_features is not None and B > 1:
-            raise NotImplementedError(
-                "the denominator-modulated CE branch (loss.py:416-471, lambda_weighted > 0) is not "
-                "implemented in the B200 path yet"
+        weighted_on = lambda_weighted > 0.0 and dino_features is not None and B > 1  # loss.py:422
+        if weighted_on and self.world_size > 1:
+            # the reference builds r and the diagonal mask from the LOCAL batch against [b, B] logits
+            # (loss.py:423-446) and fails in the first broadcast; keep the failure
+            raise RuntimeError(
+                f"The size of tensor a ({B * self.world_size}) must match the size of tensor b ({B}) at "
+                "non-singleton dimension 1 (the lambda_weighted branch is single-rank only, loss.py:416-471)"
             )
 
         lambda_soft = float(g(args, "lambda_soft", 0.0))
@@ -487,9 +576,13 @@ class ClipLossWithDINOEnhancements(nn.Module):
         classic_loss = terms[0]
         soft_loss = terms[3] if soft_on else torch.zeros((), device=device)
         weighted_loss = torch.zeros((), device=device, dtype=classic_loss.dtype)
-        # lambda_weighted * weighted_loss is identically zero here (the branch raises above when enabled)
         total_loss = terms[4]
         dbg = {}
+        if weighted_on:
+            weighted_loss, dbg = _weighted_ce_branch(
+                image_features, text_features, logit_scale, dino_features, float(g(args, "rho", 0.1)),
+                float(g(args, "c_clip", 1.0)), bool(g(args, "weight_text_symmetry", False)))
+            total_loss = total_loss + lambda_weighted * weighted_loss  # loss.py:473-477
         if output_dict:
             return {
                 "total_loss": total_loss,

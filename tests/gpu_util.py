@@ -35,7 +35,7 @@ def synth_aligned(seed, B, D, Dd, noise=0.3, device="cpu"):
 def make_args(**kw):
     base = dict(use_projection=False, projection_type="mlp", lambda_soft=0.5, soft_mode="kl_teacher",
                 soft_dino_to_text=True, text_lambda=0.5, text_student_temp=0.02, teacher_temp=0.15,
-                lambda_original=1.0, lambda_weighted=0.0)
+                lambda_original=1.0, lambda_weighted=0.0, rho=0.1, c_clip=1.0, weight_text_symmetry=False)
     base.update(kw)
     return types.SimpleNamespace(**base)
 
@@ -44,7 +44,9 @@ def oracle_cfg(oracle, args, **kw):
     return oracle.OracleConfig(
         lambda_original=args.lambda_original, lambda_soft=args.lambda_soft, soft_mode=args.soft_mode,
         teacher_temp=args.teacher_temp, soft_dino_to_text=args.soft_dino_to_text, text_lambda=args.text_lambda,
-        text_student_temp=args.text_student_temp, **kw)
+        text_student_temp=args.text_student_temp, lambda_weighted=getattr(args, "lambda_weighted", 0.0),
+        rho=getattr(args, "rho", 0.1), c_clip=getattr(args, "c_clip", 1.0),
+        weight_text_symmetry=getattr(args, "weight_text_symmetry", False), **kw)
 
 
 def head_params_of(module, projection_type, layernorm=False):

@@ -54,7 +54,7 @@ def check_against_oracle(pkg, oracle, B, D, Dd, scale, args, seed=0, clustered=T
     cfg = oracle_cfg(oracle, args, round_student_bf16=True)
     ref = oracle.loss_and_grads(img, txt, scale, dino, cfg, proj_params=head,
                                 projection_type=args.projection_type, dtype=torch.float64)["ranks"][0]
-    for k in ("total_loss", "classic_loss", "soft_loss"):
+    for k in ("total_loss", "classic_loss", "soft_loss", "weighted_loss"):
         got = float(out[k].detach())
         print(f"[parity] B={B} D={D} Dd={Dd} s={scale} {k}: got={got:.7f} ref={ref[k]:.7f} rel={abs(got - ref[k]) / max(abs(ref[k]), 1e-30):.2e}")
         # abs floor: logits of magnitude ~scale carry an fp32 ulp of up to 8e-6 into (lse - L_ii)
@@ -92,6 +92,14 @@ def test_config1_mlp_text(pkg, oracle):
 def test_scale_100_linear_head(pkg, oracle):
     check_against_oracle(pkg, oracle, 384, 512, 768, 100.0,
                          make_args(use_projection=True, projection_type="linear", soft_dino_to_text=False))
+
+
+@pytest.mark.parametrize("sym", [False, True])
+def test_weighted_ce_branch(pkg, oracle, sym):
+    """lambda_weighted > 0 (loss.py:416-471): fused classic / soft terms plus the tensor-op weighted branch."""
+    check_against_oracle(pkg, oracle, 256, 128, 192, 30.0,
+                         make_args(use_projection=True, lambda_weighted=0.6, rho=0.2, c_clip=0.5,
+                                   weight_text_symmetry=sym), seed=11)
 
 
 def test_iid_gaussian_flat_teacher(pkg, oracle):

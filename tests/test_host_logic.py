@@ -46,9 +46,13 @@ def test_error_behaviour_mirrors_reference(pkg, oracle):
     m._backend = OracleBackend(oracle)
     with pytest.raises(ValueError, match="Unknown projection_type"):
         m(x, x, torch.tensor(10.0), torch.randn(8, 24), types.SimpleNamespace(projection_type="conv"), output_dict=True)
-    with pytest.raises(NotImplementedError):
-        m(x, x, torch.tensor(10.0), torch.randn(8, 24), types.SimpleNamespace(lambda_weighted=0.5, use_projection=False),
-          output_dict=True)
+    # lambda_weighted > 0 at world_size > 1: the reference's [b, b] DINO mask cannot broadcast against its
+    # [b, B] logits (loss.py:423-446) -> RuntimeError there, RuntimeError here
+    m2 = pkg.ClipLossWithDINOEnhancements(world_size=2, local_loss=True, rank=0)
+    m2._backend = OracleBackend(oracle)
+    with pytest.raises(RuntimeError, match="must match the size of tensor b"):
+        m2(x, x, torch.tensor(10.0), torch.randn(8, 24), types.SimpleNamespace(lambda_weighted=0.5, use_projection=False),
+           output_dict=True)
     with pytest.raises(NotImplementedError):
         pkg.ClipLossWithDINOEnhancements(use_horovod=True)(x, x, torch.tensor(10.0))
 
@@ -69,7 +73,8 @@ def test_labels_and_tau_helpers(pkg):
 
 @pytest.mark.parametrize("fname", ["w1_noproj_text.npz", "w1_classic_only.npz", "w1_scale_below_10.npz",
                                    "w1_mlp_text_scale100.npz", "w1_linear_notext.npz", "w1_mlp_layernorm.npz",
-                                   "w1_residual.npz", "w1_residual_alpha.npz"])
+                                   "w1_residual.npz", "w1_residual_alpha.npz", "w1_weighted.npz",
+                                   "w1_weighted_sym_all_terms.npz"])
 def test_module_wiring_reproduces_reference_fixture(pkg, oracle, fname):
     """Module (host logic) + oracle test double == the reference's own numbers at world_size 1.
     Checks knob decoding, projection-head handling, loss composition and the autograd plumbing."""
@@ -96,6 +101,18 @@ def test_module_wiring_reproduces_reference_fixture(pkg, oracle, fname):
     # the packed operands are bf16: exact for image/text/dino (bf16-representable fixtures); the head output
     # is rounded, which moves the soft term by O(1e-3) relative at most
     tol = 5e-3 if (use_proj and float(getattr(a, "lambda_soft", 0)) > 0) else 1e-6
+    weighted = float(getattr(a, "lambda_weighted", 0.0)) > 0
+    if weighted:  # the weighted branch computes in fp32 tensor ops (loss.py:416-471 restated in the module)
+        tol = max(tol, 2e-5)
+        assert float(out["weighted_loss"]) == pytest.approx(float(z["f64_r0_weighted_loss"]), rel=2e-5)
+        # the keys train.py:360-364 formats every 300 steps, as numbers
+        msg = (f"{out['dbg']['delta_img_max']:.2f}/{out['dbg']['delta_txt_max']:.2f} "
+               f"{out['dbg']['corr_rhat_dprob_img']:.3f}/{out['dbg']['corr_rhat_dprob_txt']:.3f} "
+               f"{out['dbg']['pc_err_img']:.2e}/{out['dbg']['pc_err_txt']:.2e}")
+        assert "nan" not in msg
+        assert float(out["dbg"]["pc_err_img"]) < 1e-2 and float(out["dbg"]["diag_max_img"]) <= float(a.c_clip)
+    else:
+        assert float(out["weighted_loss"]) == 0.0 and out["dbg"] == {}
     for k in ("total_loss", "classic_loss", "soft_loss"):
         assert float(out[k]) == pytest.approx(float(z["f64_r0_" + k]), rel=tol, abs=1e-9), k
     for got, key in ((im.grad, "d_image"), (tx.grad, "d_text")):

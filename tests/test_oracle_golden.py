@@ -24,6 +24,10 @@ def _cfg_from(oracle, z, soft_scope="local"):
         soft_scope=soft_scope,  # the reference computes the soft terms on the local block
         residual_projection=bool(a.get("residual_projection", False)),
         residual_alpha=(None if a.get("residual_alpha") is None else float(a["residual_alpha"])),
+        lambda_weighted=float(a.get("lambda_weighted", 0.0)),
+        rho=float(a.get("rho", 0.1)),
+        c_clip=float(a.get("c_clip", 1.0)),
+        weight_text_symmetry=bool(a.get("weight_text_symmetry", False)),
     ), a
 
 
@@ -45,7 +49,7 @@ def test_oracle_matches_reference_fixture(oracle, fname, tag, dtype, rtol):
     res = oracle.loss_and_grads(img, txt, float(z["scale"]), dino, cfg, proj_params=head,
                                 projection_type=str(a.get("projection_type", "mlp")), dtype=dtype)
     for r, got in enumerate(res["ranks"]):
-        for k in ("total_loss", "classic_loss", "soft_loss"):
+        for k in ("total_loss", "classic_loss", "soft_loss", "weighted_loss"):
             ref = float(z[f"{tag}_r{r}_{k}"])
             assert got[k] == pytest.approx(ref, rel=rtol, abs=rtol), (k, r)
         for k in ("d_image", "d_text"):
