@@ -305,7 +305,20 @@ class _DinoSoftFn(torch.autograd.Function):
         d_text = torch.empty((b, D), dtype=torch.float32, device=dev)
         d_student = torch.empty((b, Dp), dtype=torch.float32, device=dev) if Dp > 0 else None
         d_scale = torch.empty(1, dtype=torch.float32, device=dev)
-        scratch = torch.empty(plan.scratch_numel, dtype=torch.float32, device=dev)
+        try:
+            scratch = torch.empty(plan.scratch_numel, dtype=torch.float32, device=dev)
+        except torch.cuda.OutOfMemoryError:
+            # the fp16 logit-gradient matrices fitted when this shape was first seen but do not now: the saved
+            # forward state does not depend on the backward implementation, so run the fused backward instead
+            s = plan.shape
+            if not (s.flags & _cabi.DSOFT_F_GMAT):
+                raise
+            for key in [k for k in _gmat_decisions if k[0] == s.b and k[1] == s.world]:
+                _gmat_decisions[key] = False
+            plan = be.plan(_cabi.Shape(b=s.b, world=s.world, rank=s.rank, D=s.D, Dp=s.Dp, Dd=s.Dd,
+                                       flags=s.flags & ~_cabi.DSOFT_F_GMAT, teacher_temp=s.teacher_temp,
+                                       text_temp=s.text_temp), dev)
+            scratch = torch.empty(plan.scratch_numel, dtype=torch.float32, device=dev)
         be.backward(plan, gathered, state, scratch, lse_all, gout, ctx.cfg.lambdas, d_image, d_text, d_student, d_scale)
         g_student = None
         if zdt is not None:
