@@ -144,3 +144,41 @@ def test_forked_and_serial_launches_agree_bitwise(pkg):
         assert torch.equal(res[0][3], other[3])
         for a, b in zip(res[0][4], other[4]):
             assert torch.equal(a, b)
+
+
+def test_backward_falls_back_when_the_gradient_matrices_do_not_fit(pkg):
+    """Two-phase backward chosen in the forward, but its scratch cannot be allocated at backward time: the fused
+    backward must take over on the same saved state and give the same gradients (to rounding of the sums)."""
+    from dinosoft_b200 import loss as loss_mod
+
+    img, txt, dino = _inputs(B=384, D=128, Dd=192, seed=9)
+    args = make_args(use_projection=True)
+    old = loss_mod.GMAT
+    grads = []
+    try:
+        for sabotage in (False, True):
+            loss_mod.GMAT = "always"
+            m = pkg.ClipLossWithDINOEnhancements()
+            torch.manual_seed(0)
+            m.init_proj(img.shape[1], dino.shape[1], img.device, "mlp")
+            im = img.clone().requires_grad_(True)
+            tx = txt.clone().requires_grad_(True)
+            sc = torch.tensor(20.0, device="cuda", requires_grad=True)
+            out = m(im, tx, sc, dino, args, output_dict=True)["total_loss"]
+            plan = next(p for p in loss_mod._cuda_backend._plans.values()
+                        if p.shape.b == 384 and p.shape.flags & 16)
+            keep = plan.scratch_numel
+            if sabotage:
+                plan.scratch_numel = 1 << 42  # 16 TiB of fp32: torch raises OutOfMemoryError
+            try:
+                out.backward()
+            finally:
+                plan.scratch_numel = keep
+            torch.cuda.synchronize()
+            grads.append((im.grad.clone(), tx.grad.clone(), sc.grad.clone()))
+    finally:
+        loss_mod.GMAT = old
+        loss_mod._gmat_decisions.clear()
+    for a, b in zip(grads[0], grads[1]):
+        linf, l2 = rel_err(b, a)
+        assert linf < 2e-4 and l2 < 2e-4
