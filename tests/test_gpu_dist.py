@@ -66,7 +66,7 @@ def _worker(rank, world, port, B, D, Dd, scale, argd, ctor, ret, gmat):
 def test_two_gpu_parity(oracle, ctor, argd, gmat):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    B, D, Dd, scale, world = 512, 128, 192, 30.0, 2
+    B, D, Dd, scale, world = 1024, 128, 192, 30.0, 2  # b = 512: two CTA pairs of row blocks per rank
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), B, D, Dd, scale, argd, ctor, ret, gmat), nprocs=world, join=True)
