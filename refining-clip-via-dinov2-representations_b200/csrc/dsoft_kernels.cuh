@@ -1,16 +1,21 @@
 // DINO-Soft streaming row-block kernels for sm_100a (tcgen05 + TMEM + TMA).
 //
-// One CTA owns a block of 128 rows (TMEM lanes) of the B x B similarity matrices and streams
-// 128-column tiles of them.  Nothing of size B x B is ever written to HBM:
-//   * forward ("stats") kernels reduce every tile to per-row soft-max statistics;
-//   * backward kernels recompute the tile, turn it into the logit-gradient tile G (bf16, in shared
-//     memory) and feed G straight back into the tensor core as the A operand of dX += G . Y.
+// One CTA owns a block of 128 rows (TMEM lanes) of the B x B similarity matrices and streams column tiles of
+// them:
+//   * forward ("stats") kernels reduce every tile to per-row soft-max statistics; nothing of size B x B is
+//     written to HBM;
+//   * two-phase backward, phase 1 (MODE_CLIP_G / MODE_SOFT_G of the forward kernel): the tile is recomputed and
+//     turned into the fp16 logit-gradient tile G, which is streamed to HBM in a blocked layout for the gradient
+//     GEMMs of dsoft_gy.cuh (2 bytes per matrix element instead of recomputing per feature chunk);
+//   * fused backward (dsoft_bwd_kernel, fallback when the G matrices do not fit): G stays in shared memory and
+//     is fed straight back into the tensor core as the A operand of dX += G . Y.
 //
 // Reference semantics being reproduced (file:line in /root/reference/src/open_clip/loss.py):
 //   CLIP logits / CE ............ get_logits 254-274, forward 313-319
 //   teacher / student / text KL .. forward 356-397
 // Warp roles (12 warps): 0 = TMA producer, 1 = tcgen05.mma issuer, 2 = TMEM allocator,
-// 3 = idle, 4..11 = epilogue (warp w owns TMEM lanes 32*(w%4).., column half (w-4)/4).
+// 3 = idle (fused backward: DSMEM sender), 4..11 = epilogue (warp w owns TMEM lanes 32*(w%4).., column half
+// (w-4)/4).
 #pragma once
 
 #include "dsoft_ptx.cuh"
