@@ -294,13 +294,19 @@ def loss_and_grads(
     proj_params: Optional[Dict[str, torch.Tensor]] = None,
     projection_type: str = "mlp",
     dtype: torch.dtype = torch.float64,
+    student_values: Optional[torch.Tensor] = None,
 ) -> Dict[str, object]:
     """Evaluate every rank's loss and the gradients the reference's backward would deliver.
 
     Returns, per rank r: the loss terms, ``d_image[r]``/``d_text[r]`` ([b, D], gradient of this rank's
     local features), ``d_logit_scale[r]`` and (with a projection head) ``d_student[r]`` (gradient w.r.t.
     the raw head output) and ``d_proj[r]`` (head parameters).  With ``gather_with_grad=True`` feature
-    gradients are d(sum_r loss_r)/d(local features); otherwise only the rank's own loss contributes."""
+    gradients are d(sum_r loss_r)/d(local features); otherwise only the rank's own loss contributes.
+
+    ``student_values`` ([B, Dp], optional): the student operand the implementation under test really used (its
+    own head output after bf16 rounding).  The head stays in the graph, but its VALUE is replaced by these
+    numbers, so that a head output that lands on the other side of a bf16 rounding boundary in fp32 than in
+    fp64 does not show up as a gradient difference."""
     W = cfg.world_size
     B = image_all.shape[0]
     b = B // W
@@ -326,6 +332,8 @@ def loss_and_grads(
                     student = im + student
                 else:
                     student = cfg.residual_alpha * im + (1 - cfg.residual_alpha) * student
+            if student_values is not None:
+                student = student + (student_values.to(dtype) - student).detach()
             student.retain_grad()
         # this rank's own loss terms
         own = rank_loss(im, tx, sc, dn, student, cfg, rank=r)

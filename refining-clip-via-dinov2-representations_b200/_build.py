@@ -9,7 +9,8 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libdsoft.so")
 SOURCES = ["dsoft_api.cu"]
-HEADERS = ["dsoft_ptx.cuh", "dsoft_kernels.cuh", os.path.join("..", "..", "include", "dsoft.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [
+    os.path.join("..", "..", "include", "dsoft.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -55,12 +55,14 @@ struct dsoft_plan {
   int offI, offT, offZ, offD, row_elems;
   int num_sms;
   // column scopes
-  int ntiles_g;               // clip / global scope
-  int s_col0, s_ncols, ntiles_s;  // soft scope
+  int ntiles_g;               // clip / global scope, 128-column tiles (fused backward)
+  int s_col0, s_ncols, ntiles_s;  // soft scope; ntiles_s counts 256-column tiles (forward / logit-gradient kernels)
+  int ntiles_s128;            // soft scope in 128-column tiles (fused backward)
+  int fast_t;                 // teacher logit gradients in the factorised form (log2(e)/tau_t <= 60)
   SplitPlan f_clip, f_soft, b_clip, b_stu, b_txt;
   int nch_clip, nch_stu, nch_txt;
   // state layout (float offsets)
-  size_t st_scal, st_rinv_t, st_rinv_z, st_rinv_d, st_diag, st_lsecols, st_total;
+  size_t st_scal, st_rinv_t, st_rinv_z, st_rinv_d, st_diag, st_lsecols, st_colfac, st_total;
   // scratch layout (float offsets)
   size_t sc_pc_it, sc_pc_ti, sc_ps, sc_rowloss, sc_acc1, sc_acc2, sc_acc3, sc_acc4, sc_ds1, sc_ds2,
       sc_dsrow, sc_v16, sc_total;
@@ -69,7 +71,7 @@ struct dsoft_plan {
   // DSOFT_F_GMAT: two-phase backward through fp16 logit-gradient matrices in scratch
   int gmat;
   int pitch_c, pitch_s;  // columns of the CLIP / soft G matrices: multiples of 64
-  size_t sc_Gci, sc_Gct, sc_Gs, sc_Gx, sc_Gs2, sc_Gx2, sc_fwd_total;
+  size_t sc_Gci, sc_Gct, sc_Gs, sc_Gx, sc_fwd_total;
   SplitPlan g_clip, g_stu, g_txt;  // K splits of the gradient GEMMs (tps = K steps per split)
   SplitPlan g_clip_t;              // world == 1: dT = G^T . I, K runs over G's rows
   int clip_tr;                     // world == 1 two-phase: one CLIP logit-gradient matrix serves both directions
@@ -159,7 +161,7 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   p->sh = *sh;
   p->num_sms = sms;
   p->B = sh->b * sh->world;
-  p->Bcol = ceil_div(p->B, BN) * BN + BN;
+  p->Bcol = ceil_div(p->B, 2 * BN) * 2 * BN + 2 * BN;  // 256-column tiles may start anywhere up to B - 8
   p->have_soft = soft;
   p->have_text = (sh->flags & DSOFT_F_TEXT) != 0;
   p->have_proj = soft && sh->Dp > 0;
@@ -177,15 +179,17 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   p->ntiles_g = ceil_div(p->B, BN);
   p->s_col0 = p->soft_local ? sh->rank * sh->b : 0;
   p->s_ncols = p->soft_local ? sh->b : p->B;
-  p->ntiles_s = ceil_div(p->s_ncols, BN);
+  p->ntiles_s = ceil_div(p->s_ncols, 2 * BN);
+  p->ntiles_s128 = ceil_div(p->s_ncols, BN);
+  p->fast_t = soft && (1.4426950408889634 / sh->teacher_temp <= 60.0);
   p->nch_clip = ceil_div(sh->D, CHUNK_F);
   p->nch_stu = ceil_div(p->Dz, CHUNK_F);
   p->nch_txt = ceil_div(sh->D, CHUNK_F);
   p->f_clip = choose_split(rbs, 1, ceil_div(p->B, 2 * BN), sms);  // forward CLIP kernel uses 256-column tiles
   p->f_soft = choose_split(rbs, 1, p->ntiles_s, sms);
   p->b_clip = choose_split(rbs, p->nch_clip, p->ntiles_g, sms);
-  p->b_stu = choose_split(rbs, p->nch_stu, p->ntiles_s, sms);
-  p->b_txt = choose_split(rbs, p->nch_txt, p->ntiles_s, sms);
+  p->b_stu = choose_split(rbs, p->nch_stu, p->ntiles_s128, sms);
+  p->b_txt = choose_split(rbs, p->nch_txt, p->ntiles_s128, sms);
   p->gmat = (sh->flags & DSOFT_F_GMAT) != 0;
   p->pitch_c = ceil_div(p->B, 64) * 64;
   p->pitch_s = ceil_div(p->s_ncols, 64) * 64;
@@ -207,6 +211,7 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   p->st_rinv_d = take(p->Bcol);
   p->st_diag = take(sh->b);
   p->st_lsecols = take(static_cast<size_t>(5) * p->Bcol);
+  p->st_colfac = take(static_cast<size_t>(5) * p->Bcol);
   p->st_total = o;
 
   // ---- scratch (floats)
@@ -233,9 +238,6 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
     p->sc_Gct = take(p->clip_tr ? 0 : bpad * p->pitch_c / 2);
     p->sc_Gs = take(soft ? bpad * p->pitch_s / 2 : 0);
     p->sc_Gx = take(p->have_text ? bpad * p->pitch_s / 2 : 0);
-    // world == 1: row-scaled copies of the upper block triangle for the transposed reads of the soft GEMMs
-    p->sc_Gs2 = take(soft && p->clip_tr ? bpad * p->pitch_s / 2 : 0);
-    p->sc_Gx2 = take(p->have_text && p->clip_tr ? bpad * p->pitch_s / 2 : 0);
   }
   p->v_offT = 0;
   p->v_offI = sh->D;
@@ -307,9 +309,9 @@ extern "C" int dsoft_plan_launches_forward(const dsoft_plan_t* p) {
 extern "C" int dsoft_plan_launches_backward(const dsoft_plan_t* p) {
   if (!p) return 0;
   if (p->gmat)
-    return 2 /*relayout, fp16 operands*/ + (p->clip_tr ? 1 : 2) /*clip G*/ + 2 /*clip GEMMs*/ +
+    return 3 /*lse stats, relayout, fp16 operands*/ + (p->clip_tr ? 1 : 2) /*clip G*/ + 2 /*clip GEMMs*/ +
            (p->have_soft ? 2 : 0) /*soft G, student GEMM*/ + (p->have_text ? 1 : 0) + 1 /*finalize*/;
-  return 2 /*relayout, fp16 operands*/ + 2 * chunk_groups(p->nch_clip) + (p->have_soft ? chunk_groups(p->nch_stu) : 0) +
+  return 3 /*lse stats, relayout, fp16 operands*/ + 2 * chunk_groups(p->nch_clip) + (p->have_soft ? chunk_groups(p->nch_stu) : 0) +
          (p->have_text ? chunk_groups(p->nch_txt) : 0) + 1 /*finalize*/;
 }
 
@@ -674,34 +676,86 @@ __device__ bool last_block_done(int* ticket) {
   return is_last != 0;
 }
 
-// [W][5][b] (rank-major, as all-gathered) -> [5][Bcol] indexed by global column, zero padded
+// One block: extremes of the CLIP row log-sum-exps of all ranks (both directions) -> reference exponent c of
+// the factorised CLIP logit gradients 2^(x - c) (2^(c - lse_row) + 2^(c - lse_col)) and whether that form is safe
+// (every 2^(c - lse) inside fp32: spread <= 200 log2 units; c >= -100 keeps 2^(0 - c) of padded entries finite).
+__global__ void __launch_bounds__(1024) lse_stats_kernel(const float* __restrict__ lse_all, int W, int b,
+                                                         float* __restrict__ scal) {
+  __shared__ float smn[32], smx[32];
+  float mn = __int_as_float(0x7f800000), mx = -__int_as_float(0x7f800000);
+  const int n = W * 2 * b;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int r = i / (2 * b), k = i % (2 * b);
+    const float v = lse_all[static_cast<size_t>(r) * 5 * b + k];  // kinds 0 and 1 are contiguous
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w) { mn = fminf(mn, smn[w]); mx = fmaxf(mx, smx[w]); }
+    const float c = 0.5f * (mn + mx);
+    const bool ok = (mx - mn <= 200.f) && (c >= -100.f) && (c <= 1.0e30f);  // false for NaN / inf as well
+    scal[SC_C_CLIP] = ok ? c : 0.f;
+    scal[SC_FAST_CLIP] = ok ? 1.f : 0.f;
+  }
+}
+
+// [W][5][b] (rank-major, as all-gathered) -> by global column, padded:
+//   lsec   [5][Bcol]  the log-sum-exps themselves (zero padded; exact CLIP form and the fused backward)
+//   colfac [5][Bcol]  column factors of the factorised logit gradients: 0 / 1 CLIP 2^(c - lse) for the image-rows
+//                     launch (columns = text rows' lse_ti) and the text-rows launch (lse_it); 2 teacher
+//                     2^(M_t - lt) (exact form: lt); 3 student 2^(M_s - ls); 4 text 2^(M_x - lx).  Zero (teacher
+//                     exact form: +1e30, i.e. 2^(q - 1e30) = 0) for padded columns and wherever the column-side
+//                     terms are dropped (gather_with_grad == False).
 __global__ void lse_relayout_kernel(const float* __restrict__ lse_all, int W, int b, int Bcol,
-                                    float* __restrict__ out) {
+                                    const float* __restrict__ scal, int fast_t, int drop_clip, int drop_soft,
+                                    float* __restrict__ out, float* __restrict__ colfac) {
   const int total = 5 * Bcol;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int k = i / Bcol, j = i % Bcol;
+    const bool real = j < W * b;
     float v = 0.f;
-    if (j < W * b) v = lse_all[(static_cast<size_t>(j / b) * 5 + k) * b + (j % b)];
+    if (real) v = lse_all[(static_cast<size_t>(j / b) * 5 + k) * b + (j % b)];
     out[i] = v;
+    float f;
+    if (k < 2) {
+      // colfac[0] serves the launch whose columns are TEXT rows (their lse is kind 1), colfac[1] the other one
+      const float lo = real ? lse_all[(static_cast<size_t>(j / b) * 5 + (1 - k)) * b + (j % b)] : 0.f;
+      f = (real && !drop_clip) ? exp2f(scal[SC_C_CLIP] - lo) : 0.f;
+    } else if (k == 2) {
+      if (fast_t) f = (real && !drop_soft) ? exp2f(scal[SC_ITT_L2] - v) : 0.f;
+      else f = (real && !drop_soft) ? v : 1.0e30f;
+    } else {
+      f = (real && !drop_soft) ? exp2f(scal[k == 3 ? SC_ITS_L2 : SC_ITX_L2] - v) : 0.f;
+    }
+    colfac[i] = f;
   }
 }
 
 // fp16 copies of the gradient-GEMM operands, one warp per global row:
-//   text | image (as used in the CLIP logits) | student * sigma_z | text * sigma_t
-// sigma = 2^floor(log2(min_j 1/||row_j||)): a power-of-two scaling is exact, and bf16 -> fp16 is exact for
-// |x| in [2^-14, 65504), so the operands reach the tensor core unrounded; 1/(||row_j|| sigma) is folded
-// into the fp16 G tile instead.
+//   text | image (as used in the CLIP logits) | student_j * sigma_j | text_j * sigma_j
+// sigma_j = 2^floor(log2(1/||row_j||)), PER ROW: a power-of-two scaling is exact, the scaled row has a norm in
+// (1/2, 1] whatever the norm spread of the batch (an outlier row cannot push the others into fp16 subnormals),
+// and bf16 -> fp16 is exact for |x| in [2^-14, 65504), so the operands reach the tensor core unrounded; the
+// remaining factor mant(1/||row_j||) in [1, 2) is folded into the fp16 G tile instead.
 __global__ void make_v16_kernel(const __nv_bfloat16* __restrict__ gathered, int row_elems, int B, int D,
                                 int Dz, int offI, int offT, int offZ, int have_soft, int have_text,
-                                const float* __restrict__ scal, __half* __restrict__ v16, int v_row,
+                                const float* __restrict__ rinv_z, const float* __restrict__ rinv_t,
+                                __half* __restrict__ v16, int v_row,
                                 int v_offT, int v_offI, int v_offZn, int v_offTn) {
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= B) return;
   const __nv_bfloat16* src = gathered + static_cast<size_t>(r) * row_elems;
   __half* dst = v16 + static_cast<size_t>(r) * v_row;
-  const float st = have_text ? pow2_floor(scal[SC_RMIN_T]) : 0.f;
-  const float sz = have_soft ? pow2_floor(scal[SC_RMIN_Z]) : 0.f;
+  const float st = have_text ? pow2_of(rinv_t[r]) : 0.f;
+  const float sz = have_soft ? pow2_of(rinv_z[r]) : 0.f;
   for (int c = lane * 2; c < D; c += 64) {
     const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src + offT + c));
     const float2 im = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src + offI + c));
@@ -720,6 +774,7 @@ __global__ void make_v16_kernel(const __nv_bfloat16* __restrict__ gathered, int 
 struct FinBwdArgs {
   int b, D, Dz, row0, row_elems, offI, offT, offZ;
   int have_soft, have_text, have_proj, row_only;
+  int sym_scaled;  // two-phase backward, world == 1: the soft G matrices carry mant(1/||y_i||) of their ROW as well
   int ns_c, ns_c2, ns_s, ns_x;  // split counts of acc1, acc2, acc3, acc4
   int nds;  // d(logit_scale) partials per row: nsplit x cluster size x 2 halves
   const __nv_bfloat16* gathered;
@@ -828,7 +883,7 @@ __global__ void __launch_bounds__(128) finalize_bwd_kernel(FinBwdArgs a) {
   // ---- student KL (loss.py:358-383 backward): d z~ = (g / (b tau_s)) * acc3 ; chain through normalize
   if (a.have_soft) {
     const float rz = a.rinv_z[gi];
-    const float coefs = gs * a.scal[SC_ITS] * inv_b;
+    const float coefs = gs * a.scal[SC_ITS] * inv_b / (a.sym_scaled ? mant12(rz) : 1.f);
     float4 dz[FB_MAXIT], zt[FB_MAXIT];
     float dot = 0.f;
 #pragma unroll
@@ -862,7 +917,7 @@ __global__ void __launch_bounds__(128) finalize_bwd_kernel(FinBwdArgs a) {
   // ---- text-text KL (loss.py:387-397 backward)
   if (a.have_text) {
     const float rt = a.rinv_t[gi];
-    const float coefx = gx * a.scal[SC_ITX] * inv_b;
+    const float coefx = gx * a.scal[SC_ITX] * inv_b / (a.sym_scaled ? mant12(rt) : 1.f);
     float4 dx[FB_MAXIT];
     float dot = 0.f;
 #pragma unroll
@@ -1234,7 +1289,7 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
   if (p->have_soft) {
     memset(&P, 0, sizeof(P));
     P.nprod = p->have_text ? 3 : 2;
-    P.bn = BN;
+    P.bn = 2 * BN;
     P.a_map[0] = P.b_map[0] = 3;  // teacher: dino . dino^T       (loss.py:373)
     P.a_map[1] = P.b_map[1] = 2;  // student: Zs . Zs^T           (loss.py:372)
     P.a_map[2] = P.b_map[2] = 1;  // text:    Tn . Tn^T           (loss.py:394)
@@ -1304,19 +1359,18 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
 
 // Gradient GEMM launch: acc[split][b][dout] = G[b][pitch] . Y16[ycol0 + ..][voff .. voff + dout)
 // transposed = true (world == 1 only): acc[split][col][dout] = G^T . Y16, K runs over G's rows
-// G2 != null (world == 1, symmetric soft G): blocks left of each row pair's diagonal block are read transposed
-// from G2, the row-scaled copy of the upper block triangle
+// tri (world == 1, symmetrically scaled soft G of which only the upper block triangle exists): blocks left of each
+// row pair's diagonal block are read transposed from the same matrix
 static int launch_gy(const dsoft_plan* p, const __half* G, int pitch, const __half* v16, int voff, int dout,
                      int ycol0, const SplitPlan& sp, float* acc, cudaStream_t st, bool transposed = false,
-                     const __half* G2 = nullptr) {
-  const bool tri = G2 != nullptr;
+                     bool tri = false) {
   CUtensorMap gmap, gmap64, vmap;
   int rc;
   // blocked G: 64 columns x (row blocks * K tiles * 128) rows, one 16 KiB box per (row block, K tile)
   const int rbs = ceil_div(p->sh.b, BM);
   const int g_rows = rbs * (pitch / BK) * BM;
   if ((rc = make_map(&gmap, G, g_rows, BK, BK, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, BM))) return rc;
-  if ((rc = make_map(&gmap64, tri ? G2 : G, g_rows, BK, BK, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 64))) return rc;
+  if ((rc = make_map(&gmap64, G, g_rows, BK, BK, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 64))) return rc;
   if ((rc = make_map(&vmap, v16 + voff, p->B, dout, p->v_row, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 64))) return rc;
   GyParams P;
   P.b = p->sh.b;
@@ -1351,6 +1405,7 @@ static int launch_gy(const dsoft_plan* p, const __half* G, int pitch, const __ha
 //   soft (G kernel -> student GEMM -> text GEMM) | CLIP image rows (G -> GEMM) | CLIP text rows (G -> GEMM)
 static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* S, float* X, const float* lse_loc,
                               const float* lsec, const __half* v16, cudaStream_t st) {
+  const float* colfac = S + p->st_colfac;
   const int b = p->sh.b;
   const int rbs = ceil_div(b, BM);
   int rc;
@@ -1373,7 +1428,7 @@ static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* 
     if ((rc = fk.lane(lane++, &ks))) return rc;
     memset(&P, 0, sizeof(P));
     P.nprod = p->have_text ? 3 : 2;
-    P.bn = BN;
+    P.bn = 2 * BN;
     P.a_map[0] = P.b_map[0] = 3;
     P.a_map[1] = P.b_map[1] = 2;
     P.a_map[2] = P.b_map[2] = 1;
@@ -1393,14 +1448,14 @@ static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* 
     P.rinv[2] = S + p->st_rinv_t;
     for (int k = 0; k < 3; ++k) {
       P.lse_row[k] = lse_loc + (2 + k) * b;
-      P.lse_col[k] = lsec + static_cast<size_t>(2 + k) * p->Bcol;
+      // column factors incl. the gather_with_grad == False case (zeros): lse_relayout_kernel.  Local soft scope
+      // keeps the column-side terms: both sides of Zs Zs^T / Tn Tn^T are live local tensors (loss.py:358-397)
+      P.colfac[k] = colfac + static_cast<size_t>(2 + k) * p->Bcol;
     }
+    P.fast_t = p->fast_t;
     P.gout[0] = Gs;
     P.gout[1] = Gx;
     P.g_pitch = p->pitch_s;
-    P.row_only = p->row_only;
-    P.rmin_idx[0] = SC_RMIN_Z;
-    P.rmin_idx[1] = SC_RMIN_T;
     // world == 1: the student / text / teacher matrices are symmetric, so G is: only the tiles from each row
     // pair's diagonal block onwards are computed (half the work), in column chunks small enough to balance the
     // triangular load; the gradient GEMMs read the other half through the transposed blocks
@@ -1408,9 +1463,7 @@ static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* 
     int nsplit = p->f_soft.nsplit;
     if (tri) {
       P.tri = 1;
-      P.gout2[0] = reinterpret_cast<__half*>(X + p->sc_Gs2);
-      P.gout2[1] = reinterpret_cast<__half*>(X + p->sc_Gx2);
-      P.tiles_per_split = std::max(8, ceil_div(p->ntiles_s, 8));
+      P.tiles_per_split = std::max(4, ceil_div(p->ntiles_s, 10));
       nsplit = ceil_div(p->ntiles_s, P.tiles_per_split);
     }
     {
@@ -1420,13 +1473,13 @@ static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* 
     {
       ProfScope ps(PK_BWD_STU, ks);
       if ((rc = launch_gy(p, Gs, p->pitch_s, v16, p->v_offZn, p->Dz, p->s_col0, p->g_stu, X + p->sc_acc3, ks, false,
-                          tri ? P.gout2[0] : nullptr)))
+                          tri)))
         return rc;
     }
     if (p->have_text) {
       ProfScope ps(PK_BWD_TXT, ks);
       if ((rc = launch_gy(p, Gx, p->pitch_s, v16, p->v_offTn, p->sh.D, p->s_col0, p->g_txt, X + p->sc_acc4, ks, false,
-                          tri ? P.gout2[1] : nullptr)))
+                          tri)))
         return rc;
     }
   }
@@ -1435,6 +1488,7 @@ static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* 
     fill_clip_fwd(p, P, d == 0 ? 0 : 1, d == 0 ? 1 : 0, S + p->st_scal, nullptr, nullptr);
     P.lse_row[0] = lse_loc + d * b;
     P.lse_col[0] = lsec + static_cast<size_t>(1 - d) * p->Bcol;
+    P.colfac[0] = colfac + static_cast<size_t>(d) * p->Bcol;
     P.gout[0] = d == 0 ? Gci : Gct;
     P.g_pitch = p->pitch_c;
     P.row_only = p->row_only;
@@ -1479,14 +1533,18 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
   if (rc) return rc;
 
   float* lsec = S + p->st_lsecols;
-  lse_relayout_kernel<<<ceil_div(5 * p->Bcol, 256), 256, 0, st>>>(lse_all, p->sh.world, b, p->Bcol, lsec);
+  lse_stats_kernel<<<1, 1024, 0, st>>>(lse_all, p->sh.world, b, S + p->st_scal);
+  CUDA_TRY(cudaGetLastError());
+  lse_relayout_kernel<<<ceil_div(5 * p->Bcol, 256), 256, 0, st>>>(
+      lse_all, p->sh.world, b, p->Bcol, S + p->st_scal, p->fast_t, p->row_only, p->row_only && !p->soft_local, lsec,
+      S + p->st_colfac);
   CUDA_TRY(cudaGetLastError());
   const float* lse_loc = lse_all + static_cast<size_t>(p->sh.rank) * 5 * b;
   __half* v16 = reinterpret_cast<__half*>(X + p->sc_v16);
   make_v16_kernel<<<ceil_div(p->B, 8), 256, 0, st>>>(
       static_cast<const __nv_bfloat16*>(gathered), p->row_elems, p->B, p->sh.D, p->Dz, p->offI, p->offT,
-      p->offZ, p->have_soft, p->have_text, S + p->st_scal, v16, p->v_row, p->v_offT, p->v_offI, p->v_offZn,
-      p->v_offTn);
+      p->offZ, p->have_soft, p->have_text, S + p->st_rinv_z, S + p->st_rinv_t, v16, p->v_row, p->v_offT, p->v_offI,
+      p->v_offZn, p->v_offTn);
   CUDA_TRY(cudaGetLastError());
   CUtensorMap vmap;
   auto vmap_for = [&](int voff, int cols) {
@@ -1518,16 +1576,16 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
   cudaStream_t ks = st;
   int lane = 0;
   if (p->have_soft) {
-    base(p->b_stu, p->s_col0, p->s_ncols, p->ntiles_s);
+    base(p->b_stu, p->s_col0, p->s_ncols, p->ntiles_s128);
     P.nprod = 2;
     P.a_map[0] = P.b_map[0] = 3;
     P.kchunks[0] = ceil_div(p->sh.Dd, BK);
     P.a_map[1] = P.b_map[1] = 2;
     P.kchunks[1] = ceil_div(p->Dz, BK);
     P.dout = p->Dz;
+    P.row_only = p->row_only && !p->soft_local;  // local scope: live tensors on both sides (loss.py:358-397)
     if ((rc = vmap_for(p->v_offZn, p->Dz))) return rc;
     P.tau_idx = SC_ITS_L2;
-    P.rmin_idx = SC_RMIN_Z;
     P.lse_t_row = lse_loc + 2 * b;
     P.lse_t_col = lsec + 2 * p->Bcol;
     P.lse_y_row = lse_loc + 3 * b;
@@ -1542,16 +1600,16 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
     }
     CUDA_TRY(cudaGetLastError());
     if (p->have_text) {
-      base(p->b_txt, p->s_col0, p->s_ncols, p->ntiles_s);
+      base(p->b_txt, p->s_col0, p->s_ncols, p->ntiles_s128);
       P.nprod = 2;
       P.a_map[0] = P.b_map[0] = 3;
       P.kchunks[0] = ceil_div(p->sh.Dd, BK);
       P.a_map[1] = P.b_map[1] = 1;
       P.kchunks[1] = ceil_div(p->sh.D, BK);
       P.dout = p->sh.D;
+      P.row_only = p->row_only && !p->soft_local;
       if ((rc = vmap_for(p->v_offTn, p->sh.D))) return rc;
       P.tau_idx = SC_ITX_L2;
-      P.rmin_idx = SC_RMIN_T;
       P.lse_t_row = lse_loc + 2 * b;
       P.lse_t_col = lsec + 2 * p->Bcol;
       P.lse_y_row = lse_loc + 4 * b;
@@ -1620,6 +1678,7 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
   fa.have_text = p->have_text;
   fa.have_proj = p->have_proj;
   fa.row_only = p->row_only;
+  fa.sym_scaled = p->gmat && p->clip_tr;
   fa.ns_c = p->gmat ? p->g_clip.nsplit : p->b_clip.nsplit;
   fa.ns_c2 = (p->gmat && p->clip_tr) ? p->g_clip_t.nsplit : fa.ns_c;
   fa.nds = p->gmat ? 2 * p->f_clip.nsplit : 2 * p->b_clip.nsplit * chunk_cluster(p->nch_clip);

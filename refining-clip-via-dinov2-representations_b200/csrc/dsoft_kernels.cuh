@@ -60,12 +60,10 @@ enum {
   SC_RMIN_D = 10,   // min_j 1/||dino_j||
   SC_TICKET_F = 12, // (int) blocks of finalize_fwd_kernel that are done: the last one reduces the row losses
   SC_TICKET_B = 13, // (int) same for finalize_bwd_kernel
+  SC_C_CLIP = 14,   // reference exponent c of the factorised CLIP logit gradients (lse_prepare_kernel)
+  SC_FAST_CLIP = 15,// 1.0: all CLIP log-sum-exps lie within 200 log2 units -> one exponential per pair
   SC_COUNT = 16
 };
-
-// Power-of-two scale sigma <= min_j rinv_j: operand rows times sigma have norm <= 1, and the scaling is
-// exact in fp16, so the fp16 gradient operand carries the bf16 features without any rounding.
-__device__ __forceinline__ float pow2_floor(float x) { return exp2f(floorf(log2f(x))); }
 
 struct TileMaps {
   CUtensorMap m[4];  // 0 = image, 1 = text, 2 = student, 3 = dino; box = 64 features x 128 rows, SW128
@@ -80,10 +78,10 @@ struct FwdParams {
   int b;            // local rows
   int col0;         // first global column in scope
   int ncols;        // number of columns in scope
-  int ntiles;       // ceil(ncols / 128)
+  int ntiles;       // ceil(ncols / bn)
   int tiles_per_split;
   int npart;        // nsplit * 2 (two column halves per split)
-  int bn;           // columns per tile: 128, or 256 (clip only: one N=256 MMA per K step, 2 TMEM slots)
+  int bn;           // columns per tile: 256 (one N=256 MMA per K step, 2 TMEM slots); 128 only in the self test
   int resident;     // single product with K <= 512: the row block's operand stays in smem (8 boxes),
                     // only the column operand streams through a ring of 16 KiB stages
   const float* scal;
@@ -92,17 +90,19 @@ struct FwdParams {
   float* diag;           // clip: raw dot product on the diagonal [b]
   // ---- logit-gradient modes (MODE_CLIP_G / MODE_SOFT_G: first phase of the two-phase backward)
   const float* lse_row[3];  // per product: LSE (log2) of this rank's rows (soft: 0 teacher, 1 student, 2 text)
-  const float* lse_col[3];  // per product: LSE by global column (clip: the OTHER direction's)
+  const float* lse_col[3];  // clip, exact form: LSE by global column (the OTHER direction's)
+  const float* colfac[3];   // per product, by global column: 2^(c - lse_col) of the factorised logit gradients
+                            // (soft teacher in the exact form: lse_col itself), written by lse_prepare_kernel;
+                            // zero (exact: +1e30) when the column-side terms are dropped
+  int fast_t;               // soft G: teacher in the factorised form (log2(e)/tau_t <= 60)
   __half* gout[2];          // fp16 logit gradients, blocked [row block][64-col K tile][128 rows][64 cols]:
                             // clip -> gout[0]; soft -> gout[0] student, gout[1] text
-  __half* gout2[2];         // soft, tri: same tiles scaled for the transposed read (see the epilogue)
   int g_pitch;              // columns of G (multiple of 64 >= ncols)
-  int row_only;             // gather_with_grad == False: drop the column-side terms
-  int rmin_idx[2];          // soft: SC_RMIN_Z, SC_RMIN_T (scale of the fp16 gradient operand)
+  int row_only;             // clip, exact form: gather_with_grad == False drops the column-side terms
   float* ds_part;           // clip: d(logit_scale) row partials [npart][b]
-  int tri;                  // soft G, world == 1: the matrices are symmetric -> only the column tiles from the row
-                            // pair's own 256-column diagonal block onwards are computed (tile 2 * (rb / 2) ..);
-                            // the gradient GEMM takes the missing part from the transposed blocks
+  int tri;                  // soft G, world == 1: the matrices are symmetric -> only the 256-column tiles from the
+                            // row pair's own diagonal tile (index rb / 2) onwards are computed and stored, scaled
+                            // symmetrically; the gradient GEMM reads the missing part from the transposed blocks
   int ds_both;              // clip, world == 1: one launch serves both directions (the text rows' matrix is the
                             // transpose), so the row partial also takes the column-side term
 };
@@ -119,7 +119,6 @@ struct BwdParams {
   int want_ds;     // clip: also accumulate the d(logit_scale) row term
   const float* scal;
   int tau_idx;             // soft: SC_ITS_L2 or SC_ITX_L2
-  int rmin_idx;            // soft: SC_RMIN_Z or SC_RMIN_T (scale of the fp16 gradient operand)
   const float* lse_row;    // clip: this direction's row LSE (log2), local rows
   const float* lse_col;    // clip: other direction's LSE by global column (padded)
   const float* lse_t_row;  // soft: teacher LSE, local rows
@@ -175,32 +174,6 @@ __device__ __forceinline__ void store_g32(__half* dst, const float (&g)[32]) {
     st_cs_v8(dst + 16 * i, w);
   }
 }
-// same with one factor for the whole row chunk
-__device__ __forceinline__ void store_g32_scaled(__half* dst, const float (&g)[32], float f) {
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    uint32_t w[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) w[k] = pack_f16x2(g[16 * i + 2 * k] * f, g[16 * i + 2 * k + 1] * f);
-    st_cs_v8(dst + 16 * i, w);
-  }
-}
-// same with per-column factors min(rinv[e] * isig, 1e4) (rinv: 32 floats in shared memory)
-__device__ __forceinline__ void store_g32_colscaled(__half* dst, const float (&g)[32], const float4* rinv, float isig) {
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    uint32_t w[8];
-#pragma unroll
-    for (int k4 = 0; k4 < 4; ++k4) {
-      const float4 r = rinv[4 * i + k4];
-      const int e = 16 * i + 4 * k4;
-      w[2 * k4 + 0] = pack_f16x2(g[e + 0] * fminf(r.x * isig, 1.0e4f), g[e + 1] * fminf(r.y * isig, 1.0e4f));
-      w[2 * k4 + 1] = pack_f16x2(g[e + 2] * fminf(r.z * isig, 1.0e4f), g[e + 3] * fminf(r.w * isig, 1.0e4f));
-    }
-    st_cs_v8(dst + 16 * i, w);
-  }
-}
-
 // ================================================================================================
 // Forward: per-row soft-max statistics
 // ================================================================================================
@@ -209,13 +182,23 @@ __device__ __forceinline__ void store_g32_colscaled(__half* dst, const float (&g
 //  (w = 2^(q-m); student/text use the fixed maximum log2(e)/tau, reached on the diagonal.)
 // CG = 2: the kernel runs as clusters of two CTAs (consecutive row blocks) that drive cta_group::2 MMAs
 // (M = 256): each CTA loads its own 128 rows of the row-side operand and HALF of the column-side tile, the
-// leader issues one MMA for both.  Shared-memory operand reads per MMA drop from 8 KiB to 6 KiB (N = 128)
-// or 4 KiB per 64 cycles-equivalent (N = 256), which is what bounds the M=128 x N=128 form at ~40 %.
+// leader issues one MMA for both.
+//
+// Tile width.  What bounds these kernels is the L2 -> SM operand stream (~6300 B/clk for the whole chip, i.e.
+// ~42 B/clk per SM): an M=256 x N=128 pair tile with a streamed row operand pulls 24 KiB per CTA per 64-deep K
+// step = 96 B/clk at the full MMA rate (round 1: 49 % tensor activity, 11.3 TB/s from L2), an M=256 x N=256 tile
+// 32 KiB per twice the math = 64 B/clk (the gradient GEMM's ratio: 93 %).  All modes therefore run 256-column
+// tiles: two TMEM slots of 256 columns, every epilogue thread owns one row x 128 columns of each product.  The
+// soft epilogues keep the teacher strip of those 128 columns in registers across the student and text products
+// (w / E below); setmaxnreg moves the registers the producer / MMA / allocator warps do not need to the two
+// epilogue warpgroups (56 / 216 per thread).
 template <int MODE, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ FwdParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_1024(smem_raw);
+  constexpr bool kSoftMode = (MODE == MODE_SOFT || MODE == MODE_SOFT_G);
+  static_assert(!kSoftMode || CG == 2, "the soft modes are written for CTA pairs");
   // streaming mode: stages of (A box | B boxes); resident mode: 8 A boxes, then B-only stages
   const bool resident = P.resident != 0;
   const int bn = P.bn;
@@ -223,7 +206,8 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   const int boxr = (CG == 2) ? 64 : BM;      // rows per TMA box (maps are built accordingly)
   const int box_bytes = boxr * 128;
   const int stage_bytes = (resident ? 0 : TILE_BYTES) + brows * 128;
-  const int nstages = min(8, (resident ? 6 : 14) * TILE_BYTES / stage_bytes);
+  // soft modes: 6 stages of 32 KiB; the 32 KiB behind them hold the staged per-column vectors
+  const int nstages = kSoftMode ? 6 : min(8, (resident ? 6 : 14) * TILE_BYTES / stage_bytes);
   const int nslots = TMEM_COLS / bn;  // 4 x 128 or 2 x 256 columns
   uint8_t* ring = resident ? smem + 8 * TILE_BYTES : smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F_STAGES * 2 * TILE_BYTES + 2 * TILE_BYTES);
@@ -233,30 +217,27 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   uint64_t* s_empty = s_full + F_SLOTS;  // (CG = 2: the leader's copy collects both CTAs' epilogues)
   uint64_t* a_full = s_empty + F_SLOTS;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_full + 1);
-  // soft modes (streaming ring of 8 x 24 KiB = 192 KiB): the per-column vectors of a tile (inverse norms, and
-  // column LSEs in the G mode; 128 columns each) are staged by the producer with bulk copies into the 32 KiB
-  // the ring leaves free, COL_BUFS tiles deep.  The epilogue reads them as shared-memory broadcasts instead of
-  // ~16 dependent global loads per 32-column chunk (measured: those loads, not MUFU or the tensor pipe,
-  // bounded the epilogue).
-  constexpr bool kSoftMode = (MODE == MODE_SOFT || MODE == MODE_SOFT_G);
-  static_assert(!kSoftMode || CG == 2, "the column-vector buffers live in the hole the CG = 2 soft ring leaves");
-  constexpr int COL_VECS = 6, COL_BUFS = 4;
-  float* colbuf = reinterpret_cast<float*>(smem + 8 * 24576);            // [COL_BUFS][COL_VECS][128]
-  uint64_t* col_full = reinterpret_cast<uint64_t*>(colbuf + COL_BUFS * COL_VECS * BN);  // [COL_BUFS]
+  // soft modes: the per-column vectors of a tile (inverse norms; column soft-max factors in the G mode; 256
+  // columns each) are staged by the producer with bulk copies, COL_BUFS tiles deep.  The epilogue reads them as
+  // shared-memory broadcasts instead of dependent global loads per 32-column chunk.
+  constexpr int COL_VECS = 6, COL_BUFS = 2, CT = 256;
+  float* colbuf = reinterpret_cast<float*>(smem + 6 * 2 * TILE_BYTES);            // [COL_BUFS][COL_VECS][256]
+  uint64_t* col_full = reinterpret_cast<uint64_t*>(colbuf + COL_BUFS * COL_VECS * CT);  // [COL_BUFS]
   uint64_t* col_empty = col_full + COL_BUFS;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int rb = blockIdx.x;
   const int split = blockIdx.y;
-  // triangular mode: column chunks are aligned from the END of the row for every row pair, so that the CTAs of
-  // one chunk index (launched next to each other) stream the same column tiles at the same time and share them
-  // in L2; a pair's lowest chunk is cut at its diagonal block and the chunks left of it are empty
+  // triangular mode (soft G, world == 1, 256-column tiles): a row pair only computes the tiles from its own
+  // diagonal tile onwards.  Column chunks are aligned from the END of the row for every row pair, so that the
+  // CTAs of one chunk index (launched next to each other) stream the same column tiles at the same time and
+  // share them in L2; a pair's lowest chunk is cut at its diagonal tile and the chunks left of it are empty
   int t0 = split * P.tiles_per_split;
   int t1 = min(t0 + P.tiles_per_split, P.ntiles);
   if (P.tri) {
     t1 = P.ntiles - split * P.tiles_per_split;
-    t0 = max(t1 - P.tiles_per_split, 2 * (rb >> 1));  // may be >= t1: nothing to do
+    t0 = max(t1 - P.tiles_per_split, rb >> 1);  // may be >= t1: nothing to do
   }
   const int prank = (CG == 2) ? (rb & 1) : 0;  // rank in the pair (== cluster rank)
   const bool leader = prank == 0;
@@ -286,6 +267,10 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
+  // the register hand-over sits INSIDE the role branches: ptxas budgets the code dominated by a setmaxnreg with
+  // its value (placed before the branch it compiled the whole kernel, epilogues included, for 56 registers)
+  if (warp < EPI_WARP0) {
+  if constexpr (kSoftMode) setmaxnreg_dec<40>();
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (warp-uniform loop)
     int stage = 0;
@@ -311,13 +296,13 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
         if (elect_one()) {
           const uint32_t full = smem_u32(&col_full[cb]);
           const int nvec = (MODE == MODE_SOFT_G ? 2 : 1) * P.nprod;
-          mbar_arrive_expect_tx(full, nvec * BN * 4);
-          float* dst = colbuf + cb * COL_VECS * BN;
-          const size_t c0 = static_cast<size_t>(P.col0) + static_cast<size_t>(t) * BN;
+          mbar_arrive_expect_tx(full, nvec * CT * 4);
+          float* dst = colbuf + cb * COL_VECS * CT;
+          const size_t c0 = static_cast<size_t>(P.col0) + static_cast<size_t>(t) * CT;
           for (int p = 0; p < P.nprod; ++p) {
-            bulk_copy_g2s(smem_u32(dst + p * BN), P.rinv[p] + c0, BN * 4, full);
+            bulk_copy_g2s(smem_u32(dst + p * CT), P.rinv[p] + c0, CT * 4, full);
             if constexpr (MODE == MODE_SOFT_G)
-              bulk_copy_g2s(smem_u32(dst + (3 + p) * BN), P.lse_col[p] + c0, BN * 4, full);
+              bulk_copy_g2s(smem_u32(dst + (3 + p) * CT), P.colfac[p] + c0, CT * 4, full);
           }
         }
         __syncwarp();
@@ -384,13 +369,16 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
         }
       }
     }
-  } else if (warp >= EPI_WARP0) {
+  }
+  } else {
     // ------------------------------------------------------------------ epilogue
+    if constexpr (kSoftMode) setmaxnreg_inc<232>();
     const int q = warp & 3;
     const int half = (warp - EPI_WARP0) >> 2;
     const int row = q * 32 + lane;
     const int li = rb * BM + row;  // local row
     const int gi = P.row0 + li;    // global index of this row
+    const int gw0 = P.row0 + rb * BM + q * 32;  // first global row of this warp (diagonal test, warp-uniform)
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int sp = split * 2 + half;
     float v[32];
@@ -475,20 +463,28 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       }
     } else if constexpr (MODE == MODE_CLIP_G) {
       // G_aj = 2^(x - lse_row_a) + 2^(x - lse_col_j), j != a (the diagonal entry incl. its -2 one-hot part and
-      // the s/(2b) factor are applied in fp32 by finalize_bwd_kernel); ds_a = sum_j 2^(x - lse_row_a) dot_aj
+      // the s/(2b) factor are applied in fp32 by finalize_bwd_kernel); ds_a = sum_j 2^(x - lse_row_a) dot_aj.
+      // Fast form (SC_FAST_CLIP, set on the device when the log-sum-exps of all rows and columns lie within 200
+      // log2 units of each other): G_aj = 2^(x - c) (2^(c - lse_row_a) + 2^(c - lse_col_j)), ONE exponential per
+      // pair; the column factors are precomputed by lse_prepare_kernel.  The exact two-exponential form bounded
+      // this kernel at the MUFU rate (2 x 128 ex2 per thread and tile = the MMA time of the tile).
       const float s2 = P.scal[SC_SCALE_L2];
       const float la = P.lse_row[0][min(li, P.b - 1)];
-      const bool row_only = P.row_only != 0;
+      const bool fast = P.scal[SC_FAST_CLIP] != 0.f;
+      const float cref = P.scal[SC_C_CLIP];
+      const float fr = fast ? exp2f(cref - la) : 0.f;
+      const float* colv = fast ? P.colfac[0] : P.lse_col[0];  // per column: 2^(c - lse_col) or lse_col
+      const bool row_only = P.row_only != 0;  // exact form only: the fast form's column factors are zero then
       const bool real_block = rb * BM < P.b;  // the odd pair member past the last row block owns no G rows
       const bool live_row = li < P.b;         // rows past b are K entries of the transposed GEMM: keep them zero
       const bool ds_both = P.ds_both != 0;
       float dsacc = 0.f;
-      // column LSEs of the NEXT 32-column chunk are fetched while the current one is processed (two register
+      // column values of the NEXT 32-column chunk are fetched while the current one is processed (two register
       // buffers, loop fully unrolled so that they are addressed statically); launched with bn == 256 only
       float4 lcA[8], lcB[8];
       auto load_cols = [&](float4 (&d)[8], int gj0) {
 #pragma unroll
-        for (int e4 = 0; e4 < 8; ++e4) d[e4] = ldg_nc_v4_volatile(P.lse_col[0] + gj0 + 4 * e4);
+        for (int e4 = 0; e4 < 8; ++e4) d[e4] = ldg_nc_v4_volatile(colv + gj0 + 4 * e4);
       };
       if (t0 < t1) load_cols(lcA, P.col0 + t0 * 256 + half * 128);
       int it = 0;
@@ -506,19 +502,42 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
           float4(&nxt)[8] = (c & 1) ? lcA : lcB;
           if (c < 3) load_cols(nxt, gj0 + 32);
           else if (t + 1 < t1) load_cols(nxt, P.col0 + (t + 1) * 256 + half * 128);
+          // masking (diagonal, ragged columns, rows past b) only where a chunk can need it: warp-uniform
+          const bool need_mask = (gw0 < gj0 + 32 && gj0 < gw0 + 32) || jrel0 + 32 > P.ncols || !real_block ||
+                                 rb * BM + q * 32 + 32 > P.b;
           float g[32];
+          if (fast) {
 #pragma unroll
-          for (int e4 = 0; e4 < 8; ++e4) {
-            const float ll[4] = {cur[e4].x, cur[e4].y, cur[e4].z, cur[e4].w};
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const float fc[4] = {cur[e4].x, cur[e4].y, cur[e4].z, cur[e4].w};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int e = 4 * e4 + k;
-              const float x2 = v[e] * s2;
-              const float e1 = fast_exp2(x2 - la);
-              const float e2 = row_only ? 0.f : fast_exp2(x2 - ll[k]);
-              dsacc = fmaf(ds_both ? e1 + e2 : e1, v[e], dsacc);  // ragged columns carry dot = 0
-              g[e] = (gj0 + e == gi || jrel0 + e >= P.ncols || !live_row) ? 0.f : e1 + e2;
+              for (int k = 0; k < 4; ++k) {
+                const int e = 4 * e4 + k;
+                const float ex = fast_exp2(fmaf(v[e], s2, -cref));
+                const float gg = ex * (fr + fc[k]);
+                dsacc = fmaf(ds_both ? gg : ex * fr, v[e], dsacc);  // ragged columns carry dot = 0
+                g[e] = gg;
+              }
             }
+          } else {
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const float ll[4] = {cur[e4].x, cur[e4].y, cur[e4].z, cur[e4].w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int e = 4 * e4 + k;
+                const float x2 = v[e] * s2;
+                const float e1 = fast_exp2(x2 - la);
+                const float e2 = row_only ? 0.f : fast_exp2(x2 - ll[k]);
+                dsacc = fmaf(ds_both ? e1 + e2 : e1, v[e], dsacc);
+                g[e] = e1 + e2;
+              }
+            }
+          }
+          if (need_mask) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (gj0 + e == gi || jrel0 + e >= P.ncols || !live_row) g[e] = 0.f;
           }
           if (real_block && jrel0 + 32 <= P.g_pitch) store_g32(P.gout[0] + g_index(li, jrel0, P.g_pitch), g);
         }
@@ -527,32 +546,47 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       }
       if (li < P.b) P.ds_part[sp * P.b + li] = dsacc;
     } else if constexpr (MODE == MODE_SOFT_G) {
-      // G_aj = [(2^(p-ls_a) + 2^(p-ls_j)) - (2^(q-lt_a) + 2^(q-lt_j))] / (||y_j|| sigma), j != a, for the
-      // student (-> gout[0]) and the text term (-> gout[1]) from ONE teacher tile
+      // G_aj = [(2^(p-ls_a) + 2^(p-ls_j)) - (2^(q-lt_a) + 2^(q-lt_j))] * mant(1/||y_j||), j != a, for the
+      // student (-> gout[0]) and the text term (-> gout[1]) from ONE teacher tile.
+      //  * student / text: p - ls = (p - M) + (M - ls) with the fixed maximum M = log2(e)/tau (reached on the
+      //    diagonal, so M <= ls <= M + log2 B): 2^(p-M) (2^(M-ls_a) + 2^(M-ls_j)), one exponential per pair;
+      //  * teacher: the same form with M_t = log2(e)/tau_t when M_t <= 60 (fast_t, decided on the host from
+      //    tau_t: every exponent then stays inside fp32), else the exact two-exponential form;
+      //  the column factors 2^(M - l_j) (teacher exact form: l_j itself) come staged from lse_prepare_kernel, which
+      //  writes zeros (exact form: +1e30) when the column-side terms are dropped (gather_with_grad == False).
+      //  * the fp16 gradient operand row is y_j * 2^floor(log2(1/||y_j||)) (exact), so G carries the remaining
+      //    mantissa of 1/||y_j|| in [1, 2) of its COLUMN; world == 1 (tri): also that of its ROW, which makes the
+      //    stored matrix symmetric - the gradient GEMM reads the blocks left of the diagonal transposed from the
+      //    same matrix and finalize_bwd_kernel divides the row factor out again.
       const int lic = min(li, P.b - 1);
       const float cq = P.rinv[0][gi] * P.scal[SC_ITT_L2];
+      const float mt = P.scal[SC_ITT_L2];
       const float lt = P.lse_row[0][lic];
-      const bool row_only = P.row_only != 0;
+      const bool fast_t = P.fast_t != 0;
+      const float frt = fast_t ? exp2f(mt - lt) : 0.f;
       const bool real_block = rb * BM < P.b;
       const bool live_row = li < P.b;  // rows past b are K entries of the transposed gradient GEMM: keep them zero
-      float E[64];  // -(teacher terms) of this thread's 64 columns, kept across the student / text products
+      float E[128];  // -(teacher terms) of this thread's 128 columns, kept across the student / text products
       int it = 0;
       for (int t = t0; t < t1; ++t, it += P.nprod) {
-        const int jt0 = t * BN + half * 64;
-        // this tile's column vectors (staged by the producer): [p] inverse norms, [3 + p] column LSEs
+        const int jt0 = t * CT + half * 128;
+        // this tile's column vectors (staged by the producer): [p] inverse norms, [3 + p] column factors
         const int cb = (t - t0) % COL_BUFS;
         mbar_wait(smem_u32(&col_full[cb]), static_cast<uint32_t>((t - t0) / COL_BUFS) & 1);
-        const float* cv = colbuf + cb * COL_VECS * BN + half * 64;
+        const float* cv = colbuf + cb * COL_VECS * CT + half * 128;
         {
-          const int slot = (it + 0) % F_SLOTS;
-          mbar_wait(smem_u32(&s_full[slot]), static_cast<uint32_t>((it + 0) / F_SLOTS) & 1);
+          const int slot = (it + 0) % 2;
+          mbar_wait(smem_u32(&s_full[slot]), static_cast<uint32_t>((it + 0) / 2) & 1);
           tc_fence_after();
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const int gj0 = P.col0 + jt0 + c * 32;
-            tmem_ld32(lane_addr + slot * BN + half * 64 + c * 32, v);
-            const float4* rc = reinterpret_cast<const float4*>(cv + 0 * BN + c * 32);
-            const float4* lc = reinterpret_cast<const float4*>(cv + 3 * BN + c * 32);
+          for (int c = 0; c < 4; ++c) {
+            tmem_ld32(lane_addr + slot * CT + half * 128 + c * 32, v);
+            if (c == 3) {
+              tc_fence_before();
+              release_slot(slot);
+            }
+            const float4* rc = reinterpret_cast<const float4*>(cv + 0 * CT + c * 32);
+            const float4* lc = reinterpret_cast<const float4*>(cv + 3 * CT + c * 32);
 #pragma unroll
             for (int e4 = 0; e4 < 8; ++e4) {
               const float4 r4 = rc[e4];
@@ -563,56 +597,60 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
               for (int k = 0; k < 4; ++k) {
                 const int e = 4 * e4 + k;
                 const float q2 = v[e] * cq * rr[k];
-                const float e1 = fast_exp2(q2 - lt);
-                const float e2 = row_only ? 0.f : fast_exp2(q2 - ll[k]);
-                E[c * 32 + e] = -(e1 + e2);
+                if (fast_t) {
+                  E[c * 32 + e] = -fast_exp2(q2 - mt) * (frt + ll[k]);
+                } else {
+                  E[c * 32 + e] = -(fast_exp2(q2 - lt) + fast_exp2(q2 - ll[k]));
+                }
               }
             }
           }
-          tc_fence_before();
-          release_slot(slot);
         }
         for (int p = 1; p < P.nprod; ++p) {
-          const int slot = (it + p) % F_SLOTS;
-          mbar_wait(smem_u32(&s_full[slot]), static_cast<uint32_t>((it + p) / F_SLOTS) & 1);
+          const int slot = (it + p) % 2;
+          mbar_wait(smem_u32(&s_full[slot]), static_cast<uint32_t>((it + p) / 2) & 1);
           tc_fence_after();
-          const float cy = P.rinv[p][gi] * P.scal[(p == 1) ? SC_ITS_L2 : SC_ITX_L2];
-          const float ly = P.lse_row[p][lic];
-          const float isig = 1.f / pow2_floor(P.scal[P.rmin_idx[p - 1]]);
+          const float my = P.scal[(p == 1) ? SC_ITS_L2 : SC_ITX_L2];
+          const float ry = P.rinv[p][gi];
+          const float cy = ry * my;
+          const float fry = exp2f(my - P.lse_row[p][lic]);
+          const float rowf = P.tri ? mant12(ry) : 1.f;
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
+          for (int c = 0; c < 4; ++c) {
             const int jrel0 = jt0 + c * 32;
             const int gj0 = P.col0 + jrel0;
-            tmem_ld32(lane_addr + slot * BN + half * 64 + c * 32, v);
-            if (c == 1) {
+            tmem_ld32(lane_addr + slot * CT + half * 128 + c * 32, v);
+            if (c == 3) {
               tc_fence_before();
               release_slot(slot);
             }
-            float g[32];
-            const float4* rc = reinterpret_cast<const float4*>(cv + p * BN + c * 32);
-            const float4* lc = reinterpret_cast<const float4*>(cv + (3 + p) * BN + c * 32);
+            const bool need_mask = (gw0 < gj0 + 32 && gj0 < gw0 + 32) || jrel0 + 32 > P.ncols || !real_block ||
+                                   rb * BM + q * 32 + 32 > P.b;
+            const float4* rc = reinterpret_cast<const float4*>(cv + p * CT + c * 32);
+            const float4* lc = reinterpret_cast<const float4*>(cv + (3 + p) * CT + c * 32);
+            uint32_t w16[16];
 #pragma unroll
             for (int e4 = 0; e4 < 8; ++e4) {
               const float4 r4 = rc[e4];
               const float4 l4 = lc[e4];
               const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
               const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
+              float g4[4];
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const int e = 4 * e4 + k;
-                const float p2 = v[e] * cy * rr[k];
-                const float e1 = fast_exp2(p2 - ly);
-                const float e2 = row_only ? 0.f : fast_exp2(p2 - ll[k]);
-                const bool dead = (gj0 + e == gi) || (jrel0 + e >= P.ncols) || !live_row;
-                g[e] = dead ? 0.f : E[c * 32 + e] + (e1 + e2);  // symmetric in (a, j) when world == 1
+                const float ex = fast_exp2(fmaf(v[e] * cy, rr[k], -my));
+                float g = fmaf(ex, fry + ll[k], E[c * 32 + e]);  // symmetric in (a, j) when world == 1
+                if (need_mask && ((gj0 + e == gi) || (jrel0 + e >= P.ncols) || !live_row)) g = 0.f;
+                g4[k] = g * (rowf * mant12(rr[k]));
               }
+              w16[2 * e4 + 0] = pack_f16x2(g4[0], g4[1]);
+              w16[2 * e4 + 1] = pack_f16x2(g4[2], g4[3]);
             }
             if (real_block && jrel0 + 32 <= P.g_pitch) {
-              // the fp16 operand row is y_j * sigma (exact), so G carries 1 / (||y_j|| sigma) of its COLUMN ...
-              const size_t go = g_index(li, jrel0, P.g_pitch);
-              store_g32_colscaled(P.gout[p - 1] + go, g, rc, isig);
-              // ... and the copy the triangular GEMM reads transposed (K index = this row) that of its ROW
-              if (P.tri) store_g32_scaled(P.gout2[p - 1] + go, g, fminf(P.rinv[p][gi] * isig, 1.0e4f));
+              __half* dst = P.gout[p - 1] + g_index(li, jrel0, P.g_pitch);
+              st_cs_v8(dst, reinterpret_cast<const uint32_t(&)[8]>(w16[0]));
+              st_cs_v8(dst + 16, reinterpret_cast<const uint32_t(&)[8]>(w16[8]));
             }
           }
         }
@@ -626,25 +664,28 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       const float cr = has_text ? P.rinv[2][gi] * P.scal[SC_ITX_L2] : 0.f;
       const float mx2 = P.scal[SC_ITX_L2];
       float m = M_FLOOR, zt = 0.f, aq = 0.f, ap = 0.f, ar = 0.f, zs = 0.f, zx = 0.f;
-      float w[64];  // teacher weights 2^(q - m) of this thread's 64 columns, kept across the three products
+      float w[128];  // teacher weights 2^(q - m) of this thread's 128 columns, kept across the three products
       int it = 0;
       for (int t = t0; t < t1; ++t, it += P.nprod) {
-        const int jt0 = t * BN + half * 64;  // first column (relative to col0) of this thread's 64 columns
-        const bool ragged = jt0 + 64 > P.ncols;
+        const int jt0 = t * CT + half * 128;  // first column (relative to col0) of this thread's 128 columns
+        const bool ragged = jt0 + 128 > P.ncols;
         // this tile's inverse column norms per product, staged by the producer
         const int cb = (t - t0) % COL_BUFS;
         mbar_wait(smem_u32(&col_full[cb]), static_cast<uint32_t>((t - t0) / COL_BUFS) & 1);
-        const float* cv = colbuf + cb * COL_VECS * BN + half * 64;
-        // ---- teacher: q (log2 units) for all 64 columns, then ONE running-max update for the tile; the
+        const float* cv = colbuf + cb * COL_VECS * CT + half * 128;
+        // ---- teacher: q (log2 units) for all 128 columns, then ONE running-max update for the tile; the
         // TMEM slot goes back to the MMA issuer as soon as the values are in registers
         {
-          const int slot = (it + 0) % F_SLOTS;
-          mbar_wait(smem_u32(&s_full[slot]), static_cast<uint32_t>((it + 0) / F_SLOTS) & 1);
+          const int slot = (it + 0) % 2;
+          mbar_wait(smem_u32(&s_full[slot]), static_cast<uint32_t>((it + 0) / 2) & 1);
           tc_fence_after();
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const int gj0 = P.col0 + jt0 + c * 32;
-            tmem_ld32(lane_addr + slot * BN + half * 64 + c * 32, v);
+          for (int c = 0; c < 4; ++c) {
+            tmem_ld32(lane_addr + slot * CT + half * 128 + c * 32, v);
+            if (c == 3) {
+              tc_fence_before();
+              release_slot(slot);
+            }
             const float4* rc = reinterpret_cast<const float4*>(cv + c * 32);
 #pragma unroll
             for (int e4 = 0; e4 < 8; ++e4) {
@@ -655,23 +696,21 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
               w[c * 32 + 4 * e4 + 3] = v[4 * e4 + 3] * cq * r.w;
             }
           }
-          tc_fence_before();
-          release_slot(slot);
           const int gj0 = P.col0 + jt0;
-          if (ragged || (gi >= gj0 && gi < gj0 + 64)) {
+          if (ragged || (gw0 < gj0 + 128 && gj0 < gw0 + 32)) {  // warp-uniform
 #pragma unroll
-            for (int e = 0; e < 64; ++e)
+            for (int e = 0; e < 128; ++e)
               if (jt0 + e >= P.ncols || gj0 + e == gi) w[e] = NEG_BIG;  // teacher diag masked: loss.py:376-377
           }
           float cm[4] = {w[0], w[1], w[2], w[3]};
 #pragma unroll
-          for (int e = 4; e < 64; ++e) cm[e & 3] = fmaxf(cm[e & 3], w[e]);
+          for (int e = 4; e < 128; ++e) cm[e & 3] = fmaxf(cm[e & 3], w[e]);
           const float mnew = fmaxf(m, fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])));
           const float alpha = fast_exp2(m - mnew);
           m = mnew;
           float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int e = 0; e < 64; ++e) {
+          for (int e = 0; e < 128; ++e) {
             const float q2 = w[e];
             const float we = fast_exp2(q2 - mnew);
             a0[e & 3] += we;
@@ -685,21 +724,22 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
         }
         // ---- student (p = 1) and text (p = 2, loss.py:387-397): sum w*p and the fixed-max exp sum
         for (int p = 1; p < P.nprod; ++p) {
-          const int slot = (it + p) % F_SLOTS;
-          mbar_wait(smem_u32(&s_full[slot]), static_cast<uint32_t>((it + p) / F_SLOTS) & 1);
+          const int slot = (it + p) % 2;
+          mbar_wait(smem_u32(&s_full[slot]), static_cast<uint32_t>((it + p) / 2) & 1);
           tc_fence_after();
           const float cs = (p == 1) ? cp : cr;
           const float mfix = (p == 1) ? ms2 : mx2;
           float b0[4] = {0.f, 0.f, 0.f, 0.f}, b1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
+          for (int c = 0; c < 4; ++c) {
             const int jrel0 = jt0 + c * 32;
-            tmem_ld32(lane_addr + slot * BN + half * 64 + c * 32, v);
-            if (c == 1) {
+            tmem_ld32(lane_addr + slot * CT + half * 128 + c * 32, v);
+            if (c == 3) {
               tc_fence_before();
               release_slot(slot);
             }
-            const float4* rc = reinterpret_cast<const float4*>(cv + p * BN + c * 32);
+            const float4* rc = reinterpret_cast<const float4*>(cv + p * CT + c * 32);
+            const bool rag = ragged && jrel0 + 32 > P.ncols;
 #pragma unroll
             for (int e4 = 0; e4 < 8; ++e4) {
               const float4 r = rc[e4];
@@ -708,7 +748,7 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
               for (int k = 0; k < 4; ++k) {
                 const int e = 4 * e4 + k;
                 float p2 = v[e] * cs * rr[k];
-                if (ragged && jrel0 + e >= P.ncols) p2 = NEG_BIG;
+                if (rag && jrel0 + e >= P.ncols) p2 = NEG_BIG;
                 b0[k] += fast_exp2(p2 - mfix);
                 b1[k] = fmaf(w[c * 32 + e], p2, b1[k]);
               }
@@ -981,7 +1021,7 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     float v[32];
     float dsacc = 0.f;
 
-    float c_a = 0.f, c_b = 0.f, l_a = 0.f, l_b = 0.f, inv_sigma = 1.f;
+    float c_a = 0.f, c_b = 0.f, l_a = 0.f, l_b = 0.f;
     if constexpr (MODE == MODE_RAW) {
       c_a = 1.f;
     } else if constexpr (MODE == MODE_CLIP) {
@@ -992,7 +1032,6 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       l_a = P.lse_t_row[lic];
       c_b = P.rinv_y[gi] * P.scal[P.tau_idx];  // student / text
       l_b = P.lse_y_row[lic];
-      inv_sigma = 1.f / pow2_floor(P.scal[P.rmin_idx]);
     }
 
     // 32 fp32 -> fp16, 4 x 16-byte swizzled stores into the K-major SW128 A-operand layout
@@ -1070,10 +1109,11 @@ dsoft_bwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
               const float p2 = v[e] * c_b * rr[k];
               const float e1 = fast_exp2(p2 - l_b);
               const float e2 = row_only ? 0.f : fast_exp2(p2 - ll[k]);
-              // the fp16 operand row is y_j * sigma (exact), so G carries 1/(||y_j|| sigma) <= ~1;
-              // diagonal (teacher masked, student parallel to y_a) and ragged columns dropped
+              // the fp16 operand row is y_j * 2^floor(log2(1/||y_j||)) (exact), so G carries the remaining
+              // mantissa of 1/||y_j|| in [1, 2); diagonal (teacher masked, student parallel to y_a) and ragged
+              // columns dropped
               const bool dead = (gj0 + e == gi) || (jrel0 + e >= P.ncols);
-              g[e] = dead ? 0.f : (E[c * 32 + e] + (e1 + e2)) * fminf(rr[k] * inv_sigma, 1.0e4f);
+              g[e] = dead ? 0.f : (E[c * 32 + e] + (e1 + e2)) * mant12(rr[k]);
             }
           }
           store_g(g, c);

@@ -354,6 +354,24 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// x = m * 2^e (normal, positive): mant12(x) = m in [1, 2), pow2_of(x) = 2^e; both exact bit operations.
+// Zero maps to (1, 0), +inf to (1, inf): callers only meet those on padded / masked entries.
+__device__ __forceinline__ float mant12(float x) {
+  return __uint_as_float((__float_as_uint(x) & 0x007fffffu) | 0x3f800000u);
+}
+__device__ __forceinline__ float pow2_of(float x) { return __uint_as_float(__float_as_uint(x) & 0x7f800000u); }
+
+// Register reallocation between warpgroups (the epilogue warps of the soft kernels hold a 128-column strip of
+// teacher weights per thread; the TMA / MMA / allocator warps need almost nothing).
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 __device__ __forceinline__ float fast_log2(float x) {
   float y;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

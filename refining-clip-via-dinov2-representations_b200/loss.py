@@ -411,6 +411,17 @@ def _weighted_ce_branch(image_features, text_features, logit_scale, dino_feature
     return loss, dbg
 
 
+def _normalize_out_dtype(x: torch.Tensor) -> torch.dtype:
+    """dtype of F.normalize(x) where the reference computes it (inside train.py's autocast region or not)."""
+    if x.dtype == torch.float32 or x.dtype == torch.float64:
+        return x.dtype
+    try:
+        autocast = torch.is_autocast_enabled(x.device.type)
+    except TypeError:  # older torch: no device argument
+        autocast = torch.is_autocast_enabled()
+    return torch.float32 if autocast else x.dtype
+
+
 # --------------------------------------------------------------------------------------------------
 # the loss module (same class name / ctor / forward signature as loss.py:190-300)
 # --------------------------------------------------------------------------------------------------
@@ -562,13 +573,16 @@ class ClipLossWithDINOEnhancements(nn.Module):
         teacher_temp = text_temp = 0.0
         if soft_on:
             flags |= _cabi.DSOFT_F_SOFT
-            zs_dtype = student.dtype if student is not None else image_features.dtype
-            # tau_t is materialised in the student's dtype by the reference (loss.py:368-369)
+            # tau_t / tau_txt are materialised in the dtype of Zs / Tn = F.normalize(...) by the reference
+            # (loss.py:368-369, 392-393); under CUDA autocast F.normalize returns fp32 whatever its input is
+            # (`norm` is on autocast's fp32 list), so the temperatures are rounded through THAT dtype
+            zs_dtype = _normalize_out_dtype(student if student is not None else image_features)
             teacher_temp = float(torch.as_tensor(float(g(args, "teacher_temp", 0.15)), dtype=zs_dtype))
             if text_on:
                 flags |= _cabi.DSOFT_F_TEXT
                 text_temp = float(
-                    torch.as_tensor(float(g(args, "text_student_temp", 0.05)), dtype=text_features.dtype)
+                    torch.as_tensor(float(g(args, "text_student_temp", 0.05)),
+                                    dtype=_normalize_out_dtype(text_features))
                 )
             if self.world_size > 1 and self.soft_scope == "local":
                 flags |= _cabi.DSOFT_F_SOFT_LOCAL

@@ -1,9 +1,13 @@
-"""BASELINE's full size (global batch 32768, D=512, Dd=768, MLP head, text term): the fp64 oracle would need
-~100 GB here, so the CUDA path is checked through size-independent properties instead."""
+"""BASELINE's full size (global batch 32768, D=512, Dd=768, MLP head, text term).  The fp64 oracle would need
+~100 GB of B x B matrices here, so the CUDA path is compared with a ROW-BLOCKED fp64 evaluation on the device
+(tests/chunked_ref.py, validated against the oracle by tests/test_chunked_ref.py): all loss terms and
+d(logit_scale) at 1e-4 / 1e-3, and d_image / d_text / d_student of three sampled 128-row blocks (first, middle,
+last) at 1e-3 - plus size-independent properties (determinism, linearity, finite differences)."""
 import pytest
 import torch
 
-from gpu_util import make_args, synth
+from chunked_ref import chunked_reference
+from gpu_util import head_params_of, make_args, rel_err, synth
 
 pytestmark = pytest.mark.gpu
 
@@ -42,6 +46,36 @@ def run(loss, args, img, txt, dino, scale, gscale=1.0):
     (gscale * out["total_loss"]).backward()
     torch.cuda.synchronize()
     return out, im.grad, tx.grad, sc.grad
+
+
+def test_sampled_blocks_against_fp64(setup):
+    """Headline size against the fp64 row-blocked reference: loss 1e-4, gradients 1e-3 (north_star's bars)."""
+    loss, args, img, txt, dino = setup
+    head = {k: v.detach() for k, v in head_params_of(loss.image_to_dino_proj, "mlp").items()}
+    grabbed = {}
+    hook = loss.image_to_dino_proj.register_forward_hook(
+        lambda mod, inp, out: (grabbed.__setitem__("student", out.detach().to(torch.bfloat16).float()),
+                               out.register_hook(lambda g: grabbed.__setitem__("d_student", g.detach().clone())))
+        and None)
+    try:
+        out, gi, gt, gs = run(loss, args, img, txt, dino, 14.2857)
+    finally:
+        hook.remove()
+    blocks = [(0, 128), (B // 2 + 128, 128), (B - 128, 128)]
+    ref = chunked_reference(img, txt, dino, 14.2857, head=head, blocks=blocks, lambdas=(1.0, 0.5, 0.5),
+                            teacher_temp=0.15, text_temp=0.02, slab=2048, student_values=grabbed["student"])
+    for k in ("total_loss", "classic_loss", "soft_loss"):
+        got = float(out[k].detach())
+        print(f"[fullsize] {k}: got={got:.7f} ref={ref[k]:.7f} rel={abs(got - ref[k]) / abs(ref[k]):.2e}")
+        assert got == pytest.approx(ref[k], rel=1e-4), k
+    print(f"[fullsize] d_logit_scale got={float(gs):.6e} ref={ref['d_logit_scale']:.6e}")
+    assert float(gs) == pytest.approx(ref["d_logit_scale"], rel=1e-3, abs=1e-7)
+    for blk in ref["blocks"]:
+        rows = slice(blk["row0"], blk["row0"] + blk["rows"])
+        for name, got in (("d_image", gi[rows]), ("d_text", gt[rows]), ("d_student", grabbed["d_student"][rows])):
+            linf, l2 = rel_err(got, blk[name])
+            print(f"[fullsize] rows {blk['row0']}..: {name} linf={linf:.2e} l2={l2:.2e}")
+            assert linf < 1e-3 and l2 < 1e-3, (blk["row0"], name, linf, l2)
 
 
 def test_deterministic_and_finite(setup):

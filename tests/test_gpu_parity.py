@@ -37,9 +37,20 @@ def run_cuda(pkg, img, txt, dino, scale, args, head_seed=7, **ctor):
         torch.manual_seed(head_seed)
         loss.init_proj(img.shape[1], dino.shape[1], dev, args.projection_type,
                        layernorm=getattr(args, "use_layernorm", False))
+    grabbed = {}
+    hook = None
+    if loss.image_to_dino_proj is not None:  # gradient w.r.t. the raw head output = the kernels' d_student
+        hook = loss.image_to_dino_proj.register_forward_hook(
+            lambda mod, inp, o: (grabbed.__setitem__("student", o.detach().to(torch.bfloat16).float().cpu()),
+                                 o.register_hook(lambda g: grabbed.__setitem__("d_student", g.detach().clone())))
+            and None)
     out = loss(im, tx, sc, dn, args, output_dict=True)
     out["total_loss"].backward()
     torch.cuda.synchronize()
+    if hook is not None:
+        hook.remove()
+    loss._test_d_student = grabbed.get("d_student")
+    loss._test_student = grabbed.get("student")
     return loss, out, im.grad, tx.grad, sc.grad
 
 
@@ -52,8 +63,12 @@ def check_against_oracle(pkg, oracle, B, D, Dd, scale, args, seed=0, clustered=T
                 head_params_of(loss.image_to_dino_proj, args.projection_type,
                                getattr(args, "use_layernorm", False)).items()}
     cfg = oracle_cfg(oracle, args, round_student_bf16=True)
+    # the oracle evaluates the head in fp64; it is handed the VALUES of the student operand the CUDA path used
+    # (its fp32 head output rounded to bf16), so that a value on a bf16 rounding boundary cannot differ
+    sv = loss._test_student if (head is not None and not getattr(args, "residual_projection", False)) else None
     ref = oracle.loss_and_grads(img, txt, scale, dino, cfg, proj_params=head,
-                                projection_type=args.projection_type, dtype=torch.float64)["ranks"][0]
+                                projection_type=args.projection_type, dtype=torch.float64,
+                                student_values=sv)["ranks"][0]
     for k in ("total_loss", "classic_loss", "soft_loss", "weighted_loss"):
         got = float(out[k].detach())
         print(f"[parity] B={B} D={D} Dd={Dd} s={scale} {k}: got={got:.7f} ref={ref[k]:.7f} rel={abs(got - ref[k]) / max(abs(ref[k]), 1e-30):.2e}")
@@ -65,6 +80,10 @@ def check_against_oracle(pkg, oracle, B, D, Dd, scale, args, seed=0, clustered=T
         assert linf < GRAD_RTOL and l2 < GRAD_RTOL, (name, linf, l2)
     print(f"[parity] d_logit_scale got={float(gs):.6e} ref={ref['d_logit_scale']:.6e}")
     assert float(gs) == pytest.approx(ref["d_logit_scale"], rel=GRAD_RTOL, abs=1e-7)
+    if "d_student" in ref and loss._test_d_student is not None and not getattr(args, "residual_projection", False):
+        linf, l2 = rel_err(loss._test_d_student, ref["d_student"])
+        print(f"[parity] B={B} D={D} Dd={Dd} s={scale} d_student: linf={linf:.2e} l2={l2:.2e}")
+        assert linf < GRAD_RTOL and l2 < GRAD_RTOL, ("d_student", linf, l2)
     if head is not None and "d_proj" in ref:
         got_head = head_params_of(loss.image_to_dino_proj, args.projection_type, getattr(args, "use_layernorm", False))
         for k, want in ref["d_proj"].items():
@@ -72,7 +91,7 @@ def check_against_oracle(pkg, oracle, B, D, Dd, scale, args, seed=0, clustered=T
                 continue
             linf, l2 = rel_err(got_head[k].grad, want)
             print(f"[parity] head {k}: linf={linf:.2e} l2={l2:.2e}")
-            assert linf < 3 * GRAD_RTOL and l2 < 3 * GRAD_RTOL, ("head " + k, linf, l2)
+            assert linf < GRAD_RTOL and l2 < GRAD_RTOL, ("head " + k, linf, l2)
     return out, ref
 
 
