@@ -10,10 +10,14 @@ one NCCL all-gather of the packed bf16 embeddings per step.
 
 One JSON line is printed by rank 0.  `value` = samples/s with inputs resident in HBM; `e2e` = the same
 metric through the module with pinned HOST inputs (H2D inside the timed region, loss read back);
-`roofline` = the dominant tile kernel against the measured bf16 tensor peak; `cpu_baseline` = the CPU
-oracle (a port of the reference loss) timed on this box's host cores on a bounded sample.
-`--impl reference` times only that CPU port (the reference itself is Python that cannot travel to the
-GPU box; the oracle is pinned to it by tests/golden).
+`roofline` = the dominant tile kernel against the measured bf16 tensor peak; `cpu_baseline` = the reference's
+own loss.py (staged as oracle/_ref/loss.py by oracle/make_ref.py; the oracle port only if that copy is absent,
+and `kind` says which) timed on this box's host cores on a bounded sample; `gpu_eager_baseline` = the same
+reference code run eagerly on this B200 under bf16 autocast (cuBLAS + ATen element-wise kernels), the comparator
+SURVEY.md 2a names.  `--impl reference` times only the CPU reference.
+
+Other BASELINE configs: `--batch 4096` (config 2), `--clip-dim 768 --dino-dim 1024 --no-head --batch 65536`
+under torchrun with 8 ranks (config 4).
 """
 from __future__ import annotations
 
@@ -44,6 +48,18 @@ LOSS_ARGS = dict(use_projection=True, projection_type="mlp", lambda_soft=0.5, so
                  lambda_original=1.0, lambda_weighted=0.0)
 
 
+def load_reference_module():
+    """The reference's own loss.py staged under oracle/_ref (None if it was never staged)."""
+    spec = importlib.util.spec_from_file_location("dsoft_make_ref", os.path.join(ROOT, "oracle", "make_ref.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    try:
+        return mod.load_reference()
+    except Exception as e:  # checksum mismatch etc.: say so, fall back to the port
+        print(f"[bench] oracle/_ref unusable: {e}", file=sys.stderr)
+        return None
+
+
 def load_oracle():
     spec = importlib.util.spec_from_file_location("dinosoft_oracle", os.path.join(ROOT, "oracle", "dinosoft_oracle.py"))
     mod = importlib.util.module_from_spec(spec)
@@ -70,64 +86,136 @@ def synth(seed, rows, D, Dd, device, clustered=True):
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU port (oracle) timing
+# reference timing (CPU, and eagerly on the GPU)
 # --------------------------------------------------------------------------------------------------
+USE_HEAD = True
+
+
 def cpu_port_step(oracle, img, txt, dino, head, scale, cfg):
-    """One fwd+bwd of the reference algorithm (fp32, torch CPU ops, all host threads)."""
+    """One fwd+bwd of the oracle port (fp32, torch CPU ops, all host threads): only used when oracle/_ref is absent."""
     im = img.clone().requires_grad_(True)
     tx = txt.clone().requires_grad_(True)
     sc = torch.tensor(scale, requires_grad=True)
-    pp = {k: v.clone().requires_grad_(True) for k, v in head.items()}
-    student = oracle.mlp_head(im, pp, "mlp")
+    pp = None if head is None else {k: v.clone().requires_grad_(True) for k, v in head.items()}
+    student = None if pp is None else oracle.mlp_head(im, pp, "mlp")
     out = oracle.rank_loss(im, tx, sc, dino, student, cfg, rank=0)
     out["total_loss"].backward()
     return float(out["total_loss"].detach())
 
 
-def cpu_port_setup(oracle, B):
-    torch.manual_seed(0)
-    img, txt, dino = synth(4321, B, D_CLIP, D_DINO, "cpu")
-    H = (D_CLIP + D_DINO) // 2
-    l0, l1 = torch.nn.Linear(D_CLIP, H), torch.nn.Linear(H, D_DINO)
-    head = {"w0": l0.weight.detach(), "b0": l0.bias.detach(), "w1": l1.weight.detach(), "b1": l1.bias.detach()}
-    cfg = oracle.OracleConfig(lambda_soft=0.5, soft_mode="kl_teacher", soft_dino_to_text=True, text_lambda=0.5,
-                              text_student_temp=0.02, teacher_temp=0.15)
-    return img, txt, dino, head, cfg
+class ReferenceRunner:
+    """fwd+bwd of the reference loss (or the port) on `device` for a batch of B rows of the bench workload."""
+
+    def __init__(self, B, device, autocast=False):
+        self.ref = load_reference_module()
+        self.kind = "reference" if self.ref is not None else "port"
+        self.device, self.autocast, self.B = device, autocast, B
+        torch.manual_seed(0)
+        self.img, self.txt, self.dino = synth(4321, B, D_CLIP, D_DINO, device)
+        self.args = types.SimpleNamespace(**dict(LOSS_ARGS, use_projection=USE_HEAD))
+        self.scale = 14.2857
+        if self.ref is not None:
+            self.loss = self.ref.ClipLossWithDINOEnhancements(local_loss=False, gather_with_grad=False,
+                                                              cache_labels=False, rank=0, world_size=1)
+            if USE_HEAD:
+                self.loss.init_proj(D_CLIP, D_DINO, device, "mlp")
+        else:
+            self.oracle = load_oracle()
+            H = (D_CLIP + D_DINO) // 2
+            self.head = None
+            if USE_HEAD:
+                l0, l1 = torch.nn.Linear(D_CLIP, H), torch.nn.Linear(H, D_DINO)
+                self.head = {"w0": l0.weight.detach(), "b0": l0.bias.detach(), "w1": l1.weight.detach(),
+                             "b1": l1.bias.detach()}
+            self.cfg = self.oracle.OracleConfig(lambda_soft=0.5, soft_mode="kl_teacher", soft_dino_to_text=True,
+                                                text_lambda=0.5, text_student_temp=0.02, teacher_temp=0.15)
+
+    def step(self):
+        if self.ref is None:
+            return cpu_port_step(self.oracle, self.img, self.txt, self.dino, self.head, self.scale, self.cfg)
+        im = self.img.clone().requires_grad_(True)
+        tx = self.txt.clone().requires_grad_(True)
+        sc = torch.tensor(self.scale, device=self.device, requires_grad=True)
+        if self.loss.image_to_dino_proj is not None:
+            for p in self.loss.image_to_dino_proj.parameters():
+                p.grad = None
+        if self.autocast:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = self.loss(im, tx, sc, self.dino, self.args, output_dict=True)
+        else:
+            out = self.loss(im, tx, sc, self.dino, self.args, output_dict=True)
+        out["total_loss"].backward()
+        return out["total_loss"].detach()
 
 
-def time_cpu_port(sample_B, iters, warmup=1):
-    oracle = load_oracle()
+def time_cpu_reference(sample_B, iters, warmup=1):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    img, txt, dino, head, cfg = cpu_port_setup(oracle, sample_B)
+    run = ReferenceRunner(sample_B, "cpu")
     for _ in range(warmup):
-        cpu_port_step(oracle, img, txt, dino, head, 14.2857, cfg)
+        run.step()
     times = []
     for _ in range(iters):
         t0 = time.perf_counter()
-        cpu_port_step(oracle, img, txt, dino, head, 14.2857, cfg)
+        float(run.step())
         times.append(time.perf_counter() - t0)
-    return times, cores
+    return times, cores, run.kind
+
+
+def time_gpu_eager(B, device, iters=5, warmup=2):
+    """The reference loss.py itself on the GPU: eager PyTorch under bf16 autocast, CUDA-event timed."""
+    run = ReferenceRunner(B, device, autocast=True)
+    if run.ref is None:
+        return None
+    for _ in range(warmup):
+        run.step()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run.step()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    del run
+    torch.cuda.empty_cache()
+    return statistics.median(times)
+
+
+REF_SAMPLE_B = 4096
+
+
+def sample_note(kind, B, cores):
+    what = ("the reference's own src/open_clip/loss.py (oracle/_ref/loss.py, unmodified)" if kind == "reference"
+            else "the oracle port of the reference loss (oracle/_ref not staged)")
+    return (f"{what}: B={B} rows of the bench workload per step (D={D_CLIP}, Dd={D_DINO}, "
+            f"{'MLP head, ' if USE_HEAD else ''}text-symmetric), fp32 torch CPU ops, {cores} threads.  The full "
+            f"B={GLOBAL_B} step needs ~40 GiB of fp32 B x B intermediates and minutes per step on a CPU; cost per "
+            f"sample grows linearly with B, so samples/s at B={GLOBAL_B} is about {B}/{GLOBAL_B} of this figure")
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample: B = 2048 rows of the same workload per step (the full B = 32768 needs ~40 GiB of
-    # fp32 B x B intermediates and minutes per step on CPU); cost per sample grows linearly with B.
-    sample_B = 2048
-    times, cores = time_cpu_port(sample_B, args.steps, args.warmup)
+    times, cores, kind = time_cpu_reference(REF_SAMPLE_B, args.steps, max(args.warmup, 1))
     total = sum(times)
-    value = sample_B * len(times) / total
+    value = REF_SAMPLE_B * len(times) / total
+    # one larger sample to show the O(B^2) growth the note claims (3 steps)
+    big_times, _, _ = time_cpu_reference(2 * REF_SAMPLE_B, 3, 1)
+    big = 2 * REF_SAMPLE_B / statistics.median(big_times)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": f"B={sample_B} rows per step of the same workload (D=512, Dd=768, MLP head, "
-                                   f"text-symmetric), fp32 torch CPU ops, {cores} threads"},
+        "sample_batch": REF_SAMPLE_B,
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": kind,
+                         "sample": sample_note(kind, REF_SAMPLE_B, cores),
+                         "median_ms_per_step": 1e3 * statistics.median(times),
+                         "samples_per_s_at_2x_sample": big,
+                         "extrapolated_to_global_batch": value * REF_SAMPLE_B / GLOBAL_B},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -135,13 +223,33 @@ def run_reference_arm(args):
 
 
 def workload_config(n):
+    head = "MLP projection head" if USE_HEAD else "no projection head"
+    packed_mb = GLOBAL_B * (2 * D_CLIP + (D_DINO if USE_HEAD else 0) + D_DINO) * 2 / 1e6
     return {
-        "workload": f"DINO-Soft loss fwd+bwd, global batch {GLOBAL_B} (BASELINE config 3 batch), D={D_CLIP}, "
-                    f"DINOv2 dim {D_DINO}, MLP projection head, text-symmetric soft term, logit_scale=14.2857",
+        "workload": f"DINO-Soft loss fwd+bwd, global batch {GLOBAL_B}, D={D_CLIP}, DINOv2 dim {D_DINO}, {head}, "
+                    f"text-symmetric soft term, logit_scale=14.2857",
         "global_batch": GLOBAL_B, "local_batch": GLOBAL_B // n, "D": D_CLIP, "Dd": D_DINO,
         "parallelism": f"row-block x{n}" if n > 1 else "single GPU",
-        "l2": "inputs larger than L2 (packed bf16 embeddings 168 MB, fp16 gradient operands 151 MB)",
+        "l2": (f"inputs larger than L2 (packed bf16 embeddings {packed_mb:.0f} MB + fp16 gradient operands)"
+               if packed_mb > 126 else
+               f"L2 flushed between steps by the step's own logit-gradient matrices "
+               f"({2e-6 * GLOBAL_B * GLOBAL_B / n:.0f} MB per matrix; packed embeddings {packed_mb:.0f} MB)"),
     }
+
+
+def load_ncu_traffic():
+    """DRAM bytes (read + write) per launch from the tracked ncu --set full summary of THIS workload
+    (profiles/ncu_traffic.csv: kernel,dram_bytes,source,git_sha); {} if the file is absent."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.csv")
+    out = {}
+    try:
+        for ln in open(path):
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) >= 2 and not ln.startswith("#") and f[0] != "kernel":
+                out[f[0]] = float(f[1])
+    except OSError:
+        pass
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -233,14 +341,16 @@ def run_ours(args):
         sampler.start()
 
     img, txt, dino = synth(1234 + rank, b, D_CLIP, D_DINO, dev)
-    larg = types.SimpleNamespace(**LOSS_ARGS)
+    larg = types.SimpleNamespace(**dict(LOSS_ARGS, use_projection=USE_HEAD))
     loss = pkg.ClipLossWithDINOEnhancements(local_loss=True, gather_with_grad=True, rank=rank, world_size=world)
     torch.manual_seed(99)
-    loss.init_proj(D_CLIP, D_DINO, dev, "mlp")
+    params = []
+    if USE_HEAD:
+        loss.init_proj(D_CLIP, D_DINO, dev, "mlp")
+        params = list(loss.image_to_dino_proj.parameters())
     scale = torch.tensor(14.2857, device=dev, requires_grad=True)
     img.requires_grad_(True)
     txt.requires_grad_(True)
-    params = list(loss.image_to_dino_proj.parameters())
 
     def zero_grads():
         img.grad = txt.grad = scale.grad = None
@@ -305,6 +415,7 @@ def run_ours(args):
     h_txt = txt.detach().cpu().pin_memory()
     h_dino = dino.detach().cpu().pin_memory()
     h2d_bytes = (h_img.numel() + h_txt.numel() + h_dino.numel()) * 4
+    del p0, p1
     host_out = torch.empty(3, dtype=torch.float32).pin_memory()
 
     # double-buffered device staging: the H2D copy of step n+1 is issued on a side stream before step n runs
@@ -383,11 +494,9 @@ def run_ours(args):
             avg_ms = ms_sum[k] / cnt[k]
             kern[name] = {"ms": round(avg_ms, 4), "alg_tflops": round(alg[k] / avg_ms / 1e9, 1),
                           "exec_tflops": round(exe[k] / avg_ms / 1e9, 1), "launches": cnt[k]}
-        # DRAM bytes (read + write) per launch from the ncu --set full capture of this exact workload
-        # (profiles/r01c_ncu_full_tile_kernels.csv); only meaningful for the default configuration
-        ncu_traffic = {"fwd_clip_i2t": 74.3e6, "fwd_clip_t2i": 74.3e6, "fwd_soft": 1702.8e6,
-                       "bwd_clip_image": 2345.1e6, "bwd_clip_text": 2347.1e6, "bwd_student": 2622.9e6,
-                       "bwd_text": 2346.0e6, "bwd_build_g_clip": 2321.0e6, "bwd_build_g_soft": 13604.2e6}
+        # DRAM bytes (read + write) per launch: loaded from the tracked ncu summary of the default workload
+        default_workload = (GLOBAL_B == 32768 and world == 1 and D_CLIP == 512 and D_DINO == 768 and USE_HEAD)
+        ncu_traffic = load_ncu_traffic() if default_workload else {}
         # dominant kernel = the longest launch that carries algorithmic FLOPs (the logit-gradient kernels of
         # the two-phase backward only recompute similarity tiles: SURVEY 8(d) counts those products once, in
         # the forward; their executed FLOPs are in `kernels`)
@@ -399,22 +508,42 @@ def run_ours(args):
         step_ms = ms / args.steps
         step_alg_tflops = plan.flops / step_ms / 1e9  # this rank's algorithmic FLOPs / step time
         cpu_baseline = None
+        gpu_eager = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu_times, cores = time_cpu_port(4096, 2, 1)
+            sb = min(REF_SAMPLE_B, GLOBAL_B)
+            cpu_times, cores, kind = time_cpu_reference(sb, 5, 1)
+            med = statistics.median(cpu_times)
             cpu_baseline = {
-                "value": 4096 * len(cpu_times) / sum(cpu_times), "unit": "samples/s", "cores": cores, "kind": "port",
-                "sample": "B=4096 rows of the same workload (D=512, Dd=768, MLP head, text-symmetric), fp32 torch "
-                          "CPU ops, 1 warm-up + 2 timed fwd+bwd; per-sample cost grows linearly with B"}
+                "value": sb / med, "unit": "samples/s", "cores": cores, "kind": kind,
+                "sample": sample_note(kind, sb, cores) + "; 1 warm-up + 5 timed fwd+bwd, median",
+                "extrapolated_to_global_batch": sb / med * sb / GLOBAL_B}
+            # the comparator SURVEY 2a names: the same reference code, eager on this GPU under bf16 autocast
+            gpu_eager = {"impl": "reference loss.py, eager PyTorch, torch.autocast(bf16), CUDA events, median of 5",
+                         "runs": []}
+            for eb in (8192, 16384):
+                if eb > GLOBAL_B:
+                    continue
+                try:
+                    ems = time_gpu_eager(eb, dev)
+                except torch.cuda.OutOfMemoryError:
+                    ems = None
+                    torch.cuda.empty_cache()
+                if ems is not None:
+                    gpu_eager["runs"].append({"batch": eb, "ms_per_step": round(ems, 3),
+                                              "samples_per_s": round(eb / ems * 1e3, 1),
+                                              "extrapolated_to_global_batch": round(eb / ems * 1e3 * eb / GLOBAL_B, 1)})
+            if not gpu_eager["runs"]:
+                gpu_eager = None
         launches_per_step = plan.launches_fwd + plan.launches_bwd  # pack, scalars, norms, tiles, finalize ...
         line = {
             "metric": METRIC, "value": GLOBAL_B * args.steps / (ms / 1e3), "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": dict(workload_config(world),
-                           backward=("two-phase: fp16 logit-gradient matrices + M=256xN=256 gradient GEMMs"
-                                     + (", symmetric shortcuts (world 1)" if world == 1 else "")
-                                     if plan.shape.flags & _cabi.DSOFT_F_GMAT else
-                                     "fused: logit gradients stay in shared memory")),
+            "config": workload_config(world),
+            "backward_impl": ("two-phase: fp16 logit-gradient matrices + M=256xN=256 gradient GEMMs"
+                              + (", symmetric shortcuts (world 1)" if world == 1 else "")
+                              if plan.shape.flags & _cabi.DSOFT_F_GMAT else
+                              "fused: logit gradients stay in shared memory"),
             "clocks": clocks,
             "e2e": None if args.no_e2e else {
                 "value": GLOBAL_B * args.steps / (ms_e2e / 1e3), "unit": "samples/s",
@@ -422,7 +551,7 @@ def run_ours(args):
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": round(achieved, 1), "peak": peak_sust,
                          "unit": "TFLOP/s", "frac": round(achieved / peak_sust, 4),
-                         "traffic": ncu_traffic.get(dom) if (GLOBAL_B == 32768 and world == 1) else None,
+                         "traffic": ncu_traffic.get(dom),
                          "peak_source": peak_src, "peak_burst": peak_burst,
                          "executed_tflops": kern[dom]["exec_tflops"],
                          "executed_frac": round(kern[dom]["exec_tflops"] / peak_sust, 4),
@@ -439,6 +568,7 @@ def run_ours(args):
                                       "ms_per_step launches them on forked streams"},
             "kernels": kern,
             "cpu_baseline": cpu_baseline,
+            "gpu_eager_baseline": gpu_eager,
             "loss": final_loss,
         }
         print(json.dumps(line), flush=True)
@@ -448,7 +578,7 @@ def run_ours(args):
 
 
 def main():
-    global GLOBAL_B
+    global GLOBAL_B, D_CLIP, D_DINO, USE_HEAD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -457,8 +587,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU port timing (profiling runs)")
     ap.add_argument("--batch", type=int, default=32768, help="global batch (default: BASELINE's 32768)")
+    ap.add_argument("--clip-dim", type=int, default=512, help="CLIP embedding dim D (config 4: 768)")
+    ap.add_argument("--dino-dim", type=int, default=768, help="DINOv2 feature dim (config 4: 1024)")
+    ap.add_argument("--no-head", action="store_true", help="student = image features (no projection head)")
     args = ap.parse_args()
-    GLOBAL_B = args.batch
+    GLOBAL_B, D_CLIP, D_DINO, USE_HEAD = args.batch, args.clip_dim, args.dino_dim, not args.no_head
     if args.impl == "reference":
         run_reference_arm(args)
     else:
