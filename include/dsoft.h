@@ -99,12 +99,30 @@ int dsoft_plan_launches_forward(const dsoft_plan_t* plan);
 int dsoft_plan_launches_backward(const dsoft_plan_t* plan);
 
 /* Round the local embeddings to bf16 and write them into rows [rank*b, rank*b+b) of `gathered`.
- * student_dev may be NULL when Dp == 0; dino_dev may be NULL when Dd == 0.  ld* are row strides in
- * elements.  Replaces the operand preparation of loss.py:313, 330-347, 358-359, 392. */
+ * student_dev may be NULL when Dp == 0; dino_dev may be NULL when Dd == 0 - or when the caller writes the DINO
+ * columns itself with dsoft_gather_rows (device feature table).  ld* are row strides in elements.  Replaces the
+ * operand preparation of loss.py:313, 330-347, 358-359, 392. */
 int dsoft_pack(const dsoft_plan_t* plan, const void* image_dev, int image_dtype, int64_t ld_image,
                const void* text_dev, int text_dtype, int64_t ld_text, const void* student_dev,
                int student_dtype, int64_t ld_student, const void* dino_dev, int dino_dtype,
                int64_t ld_dino, void* gathered_dev, void* stream);
+
+/* Column (in elements) of the DINO block inside a packed row: where dsoft_gather_rows must write when the caller
+ * fills the DINO columns of `gathered` itself (dsoft_pack with dino_dev == NULL). */
+size_t dsoft_plan_dino_col_offset(const dsoft_plan_t* plan);
+
+/* Device-resident DINO feature table: out[i, :] = table[indices[i], :] for i < n, converted to out_dtype, with
+ * the index range check done ON THE DEVICE.  Replaces the reference's per-step CPU gather from a pinned table,
+ * H2D copy and `.item()` range check (src/open_clip_train/main.py:693-741, src/open_clip_train/train.py:250-280).
+ * `out_dev` may be a plain [n, cols] matrix or the DINO columns of the packed `gathered` buffer (out_dev =
+ * gathered + (rank*b) * row_elems + dsoft_plan_dino_col_offset, ld_out = row_elems, out_dtype = DSOFT_DT_BF16), so
+ * that the gather feeds the loss kernels directly.  Rows with an index outside [0, n_rows) are written as zeros
+ * and recorded in status_dev (4 x int64, sticky across calls, initialise to {0, INT64_MAX, INT64_MIN, -1}):
+ * [0] number of bad indices, [1] smallest index seen, [2] largest index seen, [3] one bad index value.
+ * cols must be a multiple of 8; table rows and out rows 16-byte aligned. */
+int dsoft_gather_rows(const void* table_dev, int table_dtype, int64_t ld_table, int64_t n_rows, int32_t cols,
+                      const int64_t* indices_dev, int32_t n, void* out_dev, int out_dtype, int64_t ld_out,
+                      long long* status_dev, void* stream);
 
 /* Forward statistics pass.  logit_scale_dev: one fp32 (already exp'd, reference model.py:571).
  * lambdas (HOST, 3 floats): {lambda_original, lambda_soft, text_lambda} (loss.py:387-388, 474).

@@ -4,14 +4,15 @@ Import as ``dinosoft_b200`` (see the shim at the repo root).  Contents:
 
     loss.py      the nn.Module with the reference's ctor/forward signature, gather_features,
                  compute_student_tau, install_into_open_clip
-    feature_store.py  device-resident DINO feature table helper
+    feature_store.py  device-resident DINO feature store: bf16 table in HBM, gather kernel with on-device range
+                 check writing straight into the packed operand buffer
     _cabi.py     ctypes binding of libdsoft.so (include/dsoft.h)
     _build.py    nvcc recipe for csrc/ (sm_100a only)
     csrc/        hand-written tcgen05 / TMEM / TMA kernels + the C ABI
 """
 from . import _build, _cabi
 from ._build import build
-from .feature_store import lookup as dino_lookup, to_device_table
+from .feature_store import DinoFeatureStore, DinoRows, lookup as dino_lookup, to_device_table
 from .loss import (
     ClipLossWithDINOEnhancements,
     CudaBackend,
@@ -28,6 +29,8 @@ __all__ = [
     "gather_features",
     "install_into_open_clip",
     "build",
+    "DinoFeatureStore",
+    "DinoRows",
     "to_device_table",
     "dino_lookup",
 ]

@@ -44,6 +44,9 @@ PROTOTYPES = {
     "dsoft_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]),
     "dsoft_plan_launches_forward": (C.c_int, [C.c_void_p]),
     "dsoft_plan_launches_backward": (C.c_int, [C.c_void_p]),
+    "dsoft_plan_dino_col_offset": (C.c_size_t, [C.c_void_p]),
+    "dsoft_gather_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int32,
+                                    C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "dsoft_pack": (C.c_int, [C.c_void_p,
                              C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int64,
                              C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int64,

@@ -62,7 +62,7 @@ struct dsoft_plan {
   SplitPlan f_clip, f_soft, b_clip, b_stu, b_txt;
   int nch_clip, nch_stu, nch_txt;
   // state layout (float offsets)
-  size_t st_scal, st_rinv_t, st_rinv_z, st_rinv_d, st_diag, st_lsecols, st_colfac, st_total;
+  size_t st_scal, st_rinv_t, st_rinv_z, st_rinv_d, st_diag, st_lsecols, st_colfac, st_lsestat, st_total;
   // scratch layout (float offsets)
   size_t sc_pc_it, sc_pc_ti, sc_ps, sc_rowloss, sc_acc1, sc_acc2, sc_acc3, sc_acc4, sc_ds1, sc_ds2,
       sc_dsrow, sc_v16, sc_total;
@@ -212,6 +212,7 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   p->st_diag = take(sh->b);
   p->st_lsecols = take(static_cast<size_t>(5) * p->Bcol);
   p->st_colfac = take(static_cast<size_t>(5) * p->Bcol);
+  p->st_lsestat = take(2 * 64);
   p->st_total = o;
 
   // ---- scratch (floats)
@@ -367,6 +368,7 @@ static int make_maps(const dsoft_plan* p, const void* gathered, TileMaps* tm, in
   } else {
     tm->m[3] = tm->m[0];
   }
+  tm->g[0] = tm->g[1] = tm->m[0];  // only the logit-gradient launches replace (and use) these
   return 0;
 }
 
@@ -676,15 +678,17 @@ __device__ bool last_block_done(int* ticket) {
   return is_last != 0;
 }
 
-// One block: extremes of the CLIP row log-sum-exps of all ranks (both directions) -> reference exponent c of
-// the factorised CLIP logit gradients 2^(x - c) (2^(c - lse_row) + 2^(c - lse_col)) and whether that form is safe
-// (every 2^(c - lse) inside fp32: spread <= 200 log2 units; c >= -100 keeps 2^(0 - c) of padded entries finite).
-__global__ void __launch_bounds__(1024) lse_stats_kernel(const float* __restrict__ lse_all, int W, int b,
-                                                         float* __restrict__ scal) {
-  __shared__ float smn[32], smx[32];
+// Extremes of the CLIP row log-sum-exps of all ranks (both directions), LSE_NB blocks -> partial (min, max) pairs;
+// lse_relayout_kernel folds them into the reference exponent c of the factorised CLIP logit gradients
+// 2^(x - c) (2^(c - lse_row) + 2^(c - lse_col)) and decides whether that form is safe (every 2^(c - lse) inside
+// fp32: spread <= 200 log2 units; c >= -100 keeps 2^(0 - c) of padded entries finite).
+constexpr int LSE_NB = 64;
+__global__ void __launch_bounds__(256) lse_stats_kernel(const float* __restrict__ lse_all, int W, int b,
+                                                        float* __restrict__ part) {
+  __shared__ float smn[8], smx[8];
   float mn = __int_as_float(0x7f800000), mx = -__int_as_float(0x7f800000);
   const int n = W * 2 * b;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int r = i / (2 * b), k = i % (2 * b);
     const float v = lse_all[static_cast<size_t>(r) * 5 * b + k];  // kinds 0 and 1 are contiguous
     mn = fminf(mn, v);
@@ -698,11 +702,9 @@ __global__ void __launch_bounds__(1024) lse_stats_kernel(const float* __restrict
   if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w) { mn = fminf(mn, smn[w]); mx = fmaxf(mx, smx[w]); }
-    const float c = 0.5f * (mn + mx);
-    const bool ok = (mx - mn <= 200.f) && (c >= -100.f) && (c <= 1.0e30f);  // false for NaN / inf as well
-    scal[SC_C_CLIP] = ok ? c : 0.f;
-    scal[SC_FAST_CLIP] = ok ? 1.f : 0.f;
+    for (int w = 1; w < 8; ++w) { mn = fminf(mn, smn[w]); mx = fmaxf(mx, smx[w]); }
+    part[blockIdx.x] = mn;
+    part[LSE_NB + blockIdx.x] = mx;
   }
 }
 
@@ -713,9 +715,31 @@ __global__ void __launch_bounds__(1024) lse_stats_kernel(const float* __restrict
 //                     2^(M_t - lt) (exact form: lt); 3 student 2^(M_s - ls); 4 text 2^(M_x - lx).  Zero (teacher
 //                     exact form: +1e30, i.e. 2^(q - 1e30) = 0) for padded columns and wherever the column-side
 //                     terms are dropped (gather_with_grad == False).
-__global__ void lse_relayout_kernel(const float* __restrict__ lse_all, int W, int b, int Bcol,
-                                    const float* __restrict__ scal, int fast_t, int drop_clip, int drop_soft,
-                                    float* __restrict__ out, float* __restrict__ colfac) {
+__global__ void __launch_bounds__(256) lse_relayout_kernel(const float* __restrict__ lse_all, int W, int b, int Bcol,
+                                                           float* __restrict__ scal, const float* __restrict__ part,
+                                                           int fast_t, int drop_clip, int drop_soft,
+                                                           float* __restrict__ out, float* __restrict__ colfac) {
+  __shared__ float s_c;
+  if (threadIdx.x < 32) {  // every block folds the LSE_NB partial extremes itself (64 + 64 floats)
+    float mn = fminf(part[threadIdx.x], part[threadIdx.x + 32]);
+    float mx = fmaxf(part[LSE_NB + threadIdx.x], part[LSE_NB + threadIdx.x + 32]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (threadIdx.x == 0) {
+      const float c = 0.5f * (mn + mx);
+      const bool ok = (mx - mn <= 200.f) && (c >= -100.f) && (c <= 1.0e30f);  // false for NaN / inf as well
+      s_c = ok ? c : 0.f;
+      if (blockIdx.x == 0) {
+        scal[SC_C_CLIP] = ok ? c : 0.f;
+        scal[SC_FAST_CLIP] = ok ? 1.f : 0.f;
+      }
+    }
+  }
+  __syncthreads();
+  const float cclip = s_c;
   const int total = 5 * Bcol;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int k = i / Bcol, j = i % Bcol;
@@ -727,7 +751,7 @@ __global__ void lse_relayout_kernel(const float* __restrict__ lse_all, int W, in
     if (k < 2) {
       // colfac[0] serves the launch whose columns are TEXT rows (their lse is kind 1), colfac[1] the other one
       const float lo = real ? lse_all[(static_cast<size_t>(j / b) * 5 + (1 - k)) * b + (j % b)] : 0.f;
-      f = (real && !drop_clip) ? exp2f(scal[SC_C_CLIP] - lo) : 0.f;
+      f = (real && !drop_clip) ? exp2f(cclip - lo) : 0.f;
     } else if (k == 2) {
       if (fast_t) f = (real && !drop_soft) ? exp2f(scal[SC_ITT_L2] - v) : 0.f;
       else f = (real && !drop_soft) ? v : 1.0e30f;
@@ -964,6 +988,145 @@ __global__ void __launch_bounds__(128) finalize_bwd_kernel(FinBwdArgs a) {
   }
 }
 
+// Same computation, ONE WARP PER ROW (feature widths up to 128 * NV): lane l owns the float4 groups l, l + 32, ...
+// of every vector of its row, the two dot products of the normalise backward are warp shuffles, and nothing waits
+// on a block barrier.  The block-per-row kernel above was latency bound (0.33 ms for ~0.6 GB at B = 32768: two
+// __syncthreads-based reductions per row with 4 warps per row); it remains the path for wider features.
+// NVD / NVZ: float4 groups per lane for the CLIP width D / the student width Dz; PROJ: the student gradient leaves
+// through d_student (its registers die before the text part) instead of being added to d_image.
+template <int NVD, int NVZ, bool PROJ>
+__global__ void __launch_bounds__(256, 2) finalize_bwd_warp_kernel(FinBwdArgs a) {
+  __shared__ float ds_sh[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float LN2 = 0.6931471805599453f;
+  const float inv_b = 1.f / static_cast<float>(a.b);
+  const float g_soft = a.gout[3] + a.lam_soft * a.gout[4];
+  const float gc = a.gout[0] + a.lam_orig * a.gout[4];
+  const float gs = a.gout[1] + g_soft;
+  const float gx = a.gout[2] + a.text_lambda * g_soft;
+  const float coefc = gc * a.scal[SC_SCALE] * 0.5f * inv_b;
+  float ds_warp = 0.f;
+  auto warp_sum = [](float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  };
+  for (int i = blockIdx.x * 8 + warp; i < a.b; i += gridDim.x * 8) {
+    const size_t gi = static_cast<size_t>(a.row0) + i;
+    const __nv_bfloat16* rowp = a.gathered + gi * a.row_elems;
+    const float xd = a.scal[SC_SCALE_L2] * a.diag[i];
+    const float dm_it = expm1f(LN2 * (xd - a.lse_loc[0 * a.b + i]));
+    const float dm_ti = expm1f(LN2 * (xd - a.lse_loc[1 * a.b + i]));
+    const float dg_img = a.row_only ? dm_it : dm_it + dm_ti;
+    const float dg_txt = a.row_only ? dm_ti : dm_it + dm_ti;
+    float4 xs[NVZ];  // student term: d_student, or the share of d_image when the student IS the image feature
+    float4 tf[NVD];  // text features
+    float4 xt[NVD];  // text-text term's share of d_text
+    // ---- student KL (loss.py:358-383 backward): (g / (b tau_s)) * acc3, chained through normalize
+    if (a.have_soft) {
+      const float rz = a.rinv_z[gi];
+      const float coefs = gs * a.scal[SC_ITS] * inv_b / (a.sym_scaled ? mant12(rz) : 1.f);
+      float4 zn[NVZ];
+      float dot = 0.f;
+#pragma unroll
+      for (int it = 0; it < NVZ; ++it) {
+        const int f = (it * 32 + lane) * 4;
+        if (f < a.Dz) {
+          float4 u = sum_splits4(a.acc3, a.ns_s, a.b, a.Dz, i, f);
+          float4 z = load_bf16x4(rowp + a.offZ + f);
+          z.x *= rz; z.y *= rz; z.z *= rz; z.w *= rz;
+          u.x *= coefs; u.y *= coefs; u.z *= coefs; u.w *= coefs;
+          dot += z.x * u.x + z.y * u.y + z.z * u.z + z.w * u.w;
+          xs[it] = u;
+          zn[it] = z;
+        }
+      }
+      dot = warp_sum(dot);
+#pragma unroll
+      for (int it = 0; it < NVZ; ++it) {
+        const int f = (it * 32 + lane) * 4;
+        if (f < a.Dz) {
+          const float4 g4 = make_float4(rz * (xs[it].x - zn[it].x * dot), rz * (xs[it].y - zn[it].y * dot),
+                                        rz * (xs[it].z - zn[it].z * dot), rz * (xs[it].w - zn[it].w * dot));
+          if constexpr (PROJ) *reinterpret_cast<float4*>(a.d_student + static_cast<size_t>(i) * a.Dz + f) = g4;
+          else xs[it] = g4;
+        }
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < NVD; ++it) {
+      const int f = (it * 32 + lane) * 4;
+      if (f < a.D) tf[it] = load_bf16x4(rowp + a.offT + f);
+    }
+    // ---- text-text KL (loss.py:387-397 backward)
+    if (a.have_text) {
+      const float rt = a.rinv_t[gi];
+      const float coefx = gx * a.scal[SC_ITX] * inv_b / (a.sym_scaled ? mant12(rt) : 1.f);
+      float dot = 0.f;
+#pragma unroll
+      for (int it = 0; it < NVD; ++it) {
+        const int f = (it * 32 + lane) * 4;
+        if (f < a.D) {
+          float4 u = sum_splits4(a.acc4, a.ns_x, a.b, a.D, i, f);
+          u.x *= coefx; u.y *= coefx; u.z *= coefx; u.w *= coefx;
+          const float4 t = tf[it];
+          dot += rt * (t.x * u.x + t.y * u.y + t.z * u.z + t.w * u.w);
+          xt[it] = u;
+        }
+      }
+      dot = warp_sum(dot);
+#pragma unroll
+      for (int it = 0; it < NVD; ++it) {
+        const int f = (it * 32 + lane) * 4;
+        if (f < a.D) {
+          const float4 t = tf[it];
+          xt[it] = make_float4(rt * (xt[it].x - rt * t.x * dot), rt * (xt[it].y - rt * t.y * dot),
+                               rt * (xt[it].z - rt * t.z * dot), rt * (xt[it].w - rt * t.w * dot));
+        }
+      }
+    }
+    // ---- CLIP part (loss.py:317-319 backward) + outputs
+    const bool add_s = a.have_soft && !PROJ;  // student == image features: same lane owns the same features
+#pragma unroll
+    for (int it = 0; it < NVD; ++it) {
+      const int f = (it * 32 + lane) * 4;
+      if (f < a.D) {
+        const float4 u1 = sum_splits4(a.acc1, a.ns_c, a.b, a.D, i, f);
+        const float4 u2 = sum_splits4(a.acc2, a.ns_c2, a.b, a.D, i, f);
+        const float4 t = tf[it];
+        const float4 im = load_bf16x4(rowp + a.offI + f);
+        float4 di = make_float4(coefc * fmaf(dg_img, t.x, u1.x), coefc * fmaf(dg_img, t.y, u1.y),
+                                coefc * fmaf(dg_img, t.z, u1.z), coefc * fmaf(dg_img, t.w, u1.w));
+        float4 dt = make_float4(coefc * fmaf(dg_txt, im.x, u2.x), coefc * fmaf(dg_txt, im.y, u2.y),
+                                coefc * fmaf(dg_txt, im.z, u2.z), coefc * fmaf(dg_txt, im.w, u2.w));
+        if constexpr (!PROJ) {
+          if (add_s) { di.x += xs[it].x; di.y += xs[it].y; di.z += xs[it].z; di.w += xs[it].w; }
+        }
+        if (a.have_text) { dt.x += xt[it].x; dt.y += xt[it].y; dt.z += xt[it].z; dt.w += xt[it].w; }
+        *reinterpret_cast<float4*>(a.d_image + static_cast<size_t>(i) * a.D + f) = di;
+        *reinterpret_cast<float4*>(a.d_text + static_cast<size_t>(i) * a.D + f) = dt;
+      }
+    }
+    float d = 0.f;
+    for (int s = lane; s < a.nds; s += 32) d += a.ds1[s * a.b + i] + a.ds2[s * a.b + i];
+    d = warp_sum(d);
+    ds_warp += d - 2.f * a.diag[i];
+  }
+  // ---- d logit_scale = g_classic / (2b) * sum_i dsrow[i], finished by the last block (fixed order: deterministic)
+  if (lane == 0) ds_sh[warp] = ds_warp;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += ds_sh[w];
+    a.dsrow[blockIdx.x] = t;
+  }
+  if (last_block_done(a.ticket)) {
+    __shared__ double sum1[1];
+    block_reduce_rows(a.dsrow, gridDim.x, 1, sum1);
+    if (threadIdx.x == 0) a.d_scale[0] = static_cast<float>(sum1[0] * static_cast<double>(gc) * 0.5 / a.b);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // optional per-kernel timing (bench.py's roofline): CUDA events around each tile-kernel launch
 // ------------------------------------------------------------------------------------------------
@@ -1185,7 +1348,7 @@ extern "C" int dsoft_pack(const dsoft_plan_t* p, const void* image, int image_dt
                           int64_t ld_dino, void* gathered, void* stream) {
   if (!p || !image || !text || !gathered) return fail(DSOFT_EINVAL, "null argument");
   if (p->have_proj && !student) return fail(DSOFT_EINVAL, "plan has Dp > 0 but student pointer is null");
-  if (p->have_soft && !dino) return fail(DSOFT_EINVAL, "plan has soft term but dino pointer is null");
+  // dino == NULL with a soft term: the caller fills the DINO columns itself (dsoft_gather_rows)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* base =
       static_cast<__nv_bfloat16*>(gathered) + static_cast<size_t>(p->sh.rank) * p->sh.b * p->row_elems;
@@ -1207,7 +1370,7 @@ extern "C" int dsoft_pack(const dsoft_plan_t* p, const void* image, int image_dt
   if ((rc = add(image, image_dt, ld_image, p->sh.D, p->offI))) return rc;
   if ((rc = add(text, text_dt, ld_text, p->sh.D, p->offT))) return rc;
   if (p->have_proj && (rc = add(student, student_dt, ld_student, p->sh.Dp, p->offZ))) return rc;
-  if (p->have_soft && (rc = add(dino, dino_dt, ld_dino, p->sh.Dd, p->offD))) return rc;
+  if (p->have_soft && dino && (rc = add(dino, dino_dt, ld_dino, p->sh.Dd, p->offD))) return rc;
   bool vec8 = reinterpret_cast<uintptr_t>(base) % 16 == 0 && a.dst_ld % 8 == 0;
   for (int k = 0; k < a.nmat; ++k) {
     const PackSrc& m = a.m[k];
@@ -1220,6 +1383,86 @@ extern "C" int dsoft_pack(const dsoft_plan_t* p, const void* image, int image_dt
   const int blocks = static_cast<int>(std::min<int64_t>((total + threads - 1) / threads, 148 * 16));
   if (vec8) pack_rows8_kernel<<<blocks, threads, 0, st>>>(a, base);
   else pack_rows_kernel<<<blocks, threads, 0, st>>>(a, base);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-resident DINO feature table: gather by index with the range check on the device
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 load_oct_as_bf16(const void* src, int dtype, int64_t idx) {
+  if (dtype == DSOFT_DT_BF16) return __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(src) + idx));
+  if (dtype == DSOFT_DT_F32) {
+    const float4 x0 = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(src) + idx));
+    const float4 x1 = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(src) + idx + 4));
+    return make_uint4(pack_bf16x2(x0.x, x0.y), pack_bf16x2(x0.z, x0.w), pack_bf16x2(x1.x, x1.y), pack_bf16x2(x1.z, x1.w));
+  }
+  const uint4 raw = __ldg(reinterpret_cast<const uint4*>(static_cast<const __half*>(src) + idx));
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+    o[q] = pack_bf16x2(f.x, f.y);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// one warp per output row; lanes move 8 elements (16 bytes of bf16) at a time
+__global__ void __launch_bounds__(256) gather_rows_kernel(const void* __restrict__ table, int table_dt, int64_t ld_table,
+                                                          int64_t n_rows, int cols, const int64_t* __restrict__ indices,
+                                                          int n, void* __restrict__ out, int out_dt, int64_t ld_out,
+                                                          long long* __restrict__ status) {
+  const int lane = threadIdx.x & 31;
+  for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += gridDim.x * 8) {
+    const long long idx = indices[i];
+    const bool ok = idx >= 0 && idx < n_rows;
+    if (lane == 0) {  // sticky range record (train.py:255-268 reads min / max / examples on the host every step)
+      atomicMin(status + 1, idx);
+      atomicMax(status + 2, idx);
+      if (!ok) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(status), 1ull);
+        status[3] = idx;
+      }
+    }
+    for (int c = lane * 8; c < cols; c += 256) {
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (ok) v = load_oct_as_bf16(table, table_dt, idx * ld_table + c);
+      if (out_dt == DSOFT_DT_BF16) {
+        *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out) + i * ld_out + c) = v;
+      } else {  // fp32 output
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        float* o = static_cast<float*>(out) + i * ld_out + c;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[q]));
+          o[2 * q] = f.x;
+          o[2 * q + 1] = f.y;
+        }
+      }
+    }
+  }
+}
+
+extern "C" size_t dsoft_plan_dino_col_offset(const dsoft_plan_t* p) { return p ? p->offD : 0; }
+
+extern "C" int dsoft_gather_rows(const void* table, int table_dt, int64_t ld_table, int64_t n_rows, int32_t cols,
+                                 const int64_t* indices, int32_t n, void* out, int out_dt, int64_t ld_out,
+                                 long long* status, void* stream) {
+  if (!table || !indices || !out || !status) return fail(DSOFT_EINVAL, "null argument");
+  if (table_dt < DSOFT_DT_F32 || table_dt > DSOFT_DT_F16) return fail(DSOFT_EINVAL, "unknown table dtype %d", table_dt);
+  if (out_dt != DSOFT_DT_BF16 && out_dt != DSOFT_DT_F32) return fail(DSOFT_EINVAL, "output must be bf16 or fp32");
+  if (cols <= 0 || cols % 8 || n < 0 || n_rows <= 0) return fail(DSOFT_EINVAL, "bad shape (cols=%d n=%d)", cols, n);
+  const int64_t in_align = table_dt == DSOFT_DT_F32 ? 4 : 8, out_align = out_dt == DSOFT_DT_F32 ? 4 : 8;
+  if (ld_table % in_align || ld_out % out_align || reinterpret_cast<uintptr_t>(table) % 16 ||
+      reinterpret_cast<uintptr_t>(out) % 16)
+    return fail(DSOFT_EINVAL, "gather needs 16-byte aligned rows");
+  if (n == 0) return 0;
+  int sms = 0;
+  int rc = query_num_sms(&sms);
+  if (rc) return rc;
+  gather_rows_kernel<<<std::min(ceil_div(n, 8), sms * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      table, table_dt, ld_table, n_rows, cols, indices, n, out, out_dt, ld_out, status);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -1403,6 +1646,12 @@ static int launch_gy(const dsoft_plan* p, const __half* G, int pitch, const __ha
 // DSOFT_F_GMAT backward.  Phase 1: the forward main loop again, its epilogue writing fp16 logit-gradient
 // tiles; phase 2: gradient GEMMs.  Three independent lanes on forked streams:
 //   soft (G kernel -> student GEMM -> text GEMM) | CLIP image rows (G -> GEMM) | CLIP text rows (G -> GEMM)
+// store map of a blocked fp16 G matrix: 64 columns x (row blocks * K tiles * 128) rows, box = 64 x 32, SW128
+static int make_gstore_map(const dsoft_plan* p, CUtensorMap* map, const __half* G, int pitch) {
+  const int rbs = ceil_div(p->sh.b, BM);
+  return make_map(map, G, rbs * (pitch / BK) * BM, BK, BK, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 32);
+}
+
 static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* S, float* X, const float* lse_loc,
                               const float* lsec, const __half* v16, cudaStream_t st) {
   const float* colfac = S + p->st_colfac;
@@ -1456,6 +1705,8 @@ static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* 
     P.gout[0] = Gs;
     P.gout[1] = Gx;
     P.g_pitch = p->pitch_s;
+    if ((rc = make_gstore_map(p, &tm.g[0], Gs, p->pitch_s))) return rc;
+    if ((rc = make_gstore_map(p, &tm.g[1], p->have_text ? Gx : Gs, p->pitch_s))) return rc;
     // world == 1: the student / text / teacher matrices are symmetric, so G is: only the tiles from each row
     // pair's diagonal block onwards are computed (half the work), in column chunks small enough to balance the
     // triangular load; the gradient GEMMs read the other half through the transposed blocks
@@ -1491,6 +1742,8 @@ static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* 
     P.colfac[0] = colfac + static_cast<size_t>(d) * p->Bcol;
     P.gout[0] = d == 0 ? Gci : Gct;
     P.g_pitch = p->pitch_c;
+    if ((rc = make_gstore_map(p, &tm.g[0], P.gout[0], p->pitch_c))) return rc;
+    tm.g[1] = tm.g[0];
     P.row_only = p->row_only;
     P.ds_part = X + (d == 0 ? p->sc_ds1 : p->sc_ds2);
     P.ds_both = p->clip_tr;
@@ -1533,11 +1786,11 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
   if (rc) return rc;
 
   float* lsec = S + p->st_lsecols;
-  lse_stats_kernel<<<1, 1024, 0, st>>>(lse_all, p->sh.world, b, S + p->st_scal);
+  lse_stats_kernel<<<LSE_NB, 256, 0, st>>>(lse_all, p->sh.world, b, S + p->st_lsestat);
   CUDA_TRY(cudaGetLastError());
-  lse_relayout_kernel<<<ceil_div(5 * p->Bcol, 256), 256, 0, st>>>(
-      lse_all, p->sh.world, b, p->Bcol, S + p->st_scal, p->fast_t, p->row_only, p->row_only && !p->soft_local, lsec,
-      S + p->st_colfac);
+  lse_relayout_kernel<<<ceil_div(5 * p->Bcol, 1024), 256, 0, st>>>(
+      lse_all, p->sh.world, b, p->Bcol, S + p->st_scal, S + p->st_lsestat, p->fast_t, p->row_only,
+      p->row_only && !p->soft_local, lsec, S + p->st_colfac);
   CUDA_TRY(cudaGetLastError());
   const float* lse_loc = lse_all + static_cast<size_t>(p->sh.rank) * 5 * b;
   __half* v16 = reinterpret_cast<__half*>(X + p->sc_v16);
@@ -1708,10 +1961,21 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
   fa.d_scale = d_scale;
   {
     const int width = std::max(p->sh.D, p->Dz);
-    const dim3 grid(std::min(b, p->num_sms * 16));
-    if (width <= 512) finalize_bwd_kernel<1><<<grid, 128, 0, st>>>(fa);
-    else if (width <= 1024) finalize_bwd_kernel<2><<<grid, 128, 0, st>>>(fa);
-    else finalize_bwd_kernel<4><<<grid, 128, 0, st>>>(fa);
+    if (width <= 1024) {  // one warp per row, 8 rows per block; lanes own ceil(width / 128) float4 groups
+      const dim3 grid(std::min(ceil_div(b, 8), p->num_sms * 16));
+      const int nd = p->sh.D <= 512 ? 4 : (p->sh.D <= 768 ? 6 : 8);
+      const int nz = p->Dz <= 512 ? 4 : (p->Dz <= 768 ? 6 : 8);
+#define DSOFT_FIN(ND, NZ)                                                                         \
+  if (nd == ND && nz == NZ) {                                                                     \
+    if (p->have_proj) finalize_bwd_warp_kernel<ND, NZ, true><<<grid, 256, 0, st>>>(fa);           \
+    else finalize_bwd_warp_kernel<ND, NZ, false><<<grid, 256, 0, st>>>(fa);                       \
+  }
+      DSOFT_FIN(4, 4) DSOFT_FIN(4, 6) DSOFT_FIN(4, 8) DSOFT_FIN(6, 4) DSOFT_FIN(6, 6) DSOFT_FIN(6, 8)
+      DSOFT_FIN(8, 4) DSOFT_FIN(8, 6) DSOFT_FIN(8, 8)
+#undef DSOFT_FIN
+    } else {
+      finalize_bwd_kernel<4><<<dim3(std::min(b, p->num_sms * 16)), 128, 0, st>>>(fa);
+    }
   }
   CUDA_TRY(cudaGetLastError());
   return 0;

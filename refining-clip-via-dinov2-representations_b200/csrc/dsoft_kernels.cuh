@@ -67,6 +67,9 @@ enum {
 
 struct TileMaps {
   CUtensorMap m[4];  // 0 = image, 1 = text, 2 = student, 3 = dino; box = 64 features x 128 rows, SW128
+  CUtensorMap g[2];  // logit-gradient modes: the blocked fp16 G matrices (gout[0], gout[1]) as 64 columns x
+                     // (row blocks * K tiles * 128) rows, box = 64 columns x 32 rows, SW128: TMA STORES of the
+                     // epilogue warps' staged 32-row strips
 };
 
 struct FwdParams {
@@ -206,8 +209,15 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   const int boxr = (CG == 2) ? 64 : BM;      // rows per TMA box (maps are built accordingly)
   const int box_bytes = boxr * 128;
   const int stage_bytes = (resident ? 0 : TILE_BYTES) + brows * 128;
-  // soft modes: 6 stages of 32 KiB; the 32 KiB behind them hold the staged per-column vectors
-  const int nstages = kSoftMode ? 6 : min(8, (resident ? 6 : 14) * TILE_BYTES / stage_bytes);
+  // soft modes: 6 stages of 32 KiB (logit-gradient mode: 5); the 32 KiB behind them hold the staged per-column
+  // vectors.  Logit-gradient modes keep 32 KiB (at 192 KiB; soft: at 160 KiB) for the G staging strips.
+  constexpr bool kGMode = (MODE == MODE_CLIP_G || MODE == MODE_SOFT_G);
+  const int nstages = MODE == MODE_SOFT_G ? 5 : (kSoftMode ? 6 :
+                      min(MODE == MODE_CLIP_G ? (resident ? 4 : 6) : 8, (resident ? 6 : 14) * TILE_BYTES / stage_bytes));
+  // G staging: one 4 KiB strip (32 rows x 64 columns fp16, 128-byte swizzle) per epilogue warp.  A strip is written
+  // with conflict-free 16-byte shared stores and leaves through ONE TMA tensor store; per-thread 32-byte global
+  // stores (32 different lines per warp instruction) kept the L1TEX pipe at 78 % and the tensor pipe at 62 %.
+  uint8_t* gstage = smem + (MODE == MODE_SOFT_G ? 5 : 6) * 2 * TILE_BYTES;
   const int nslots = TMEM_COLS / bn;  // 4 x 128 or 2 x 256 columns
   uint8_t* ring = resident ? smem + 8 * TILE_BYTES : smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F_STAGES * 2 * TILE_BYTES + 2 * TILE_BYTES);
@@ -244,6 +254,10 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) tma_prefetch_desc(&maps.m[i]);
+    if constexpr (kGMode) {
+      tma_prefetch_desc(&maps.g[0]);
+      tma_prefetch_desc(&maps.g[1]);
+    }
     for (int i = 0; i < 8; ++i) {
       mbar_init(smem_u32(&ring_full[i]), 1);
       mbar_init(smem_u32(&ring_empty[i]), 1);
@@ -382,6 +396,29 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int sp = split * 2 + half;
     float v[32];
+    // ---- G staging (logit-gradient modes): this warp's strip, its swizzled row, and the TMA store of a finished
+    // 64-column box.  Strip reuse: the issuing lane waits until its previous store has read the strip.
+    const uint32_t gs_base = smem_u32(gstage) + static_cast<uint32_t>(warp - EPI_WARP0) * 4096u;
+    const uint32_t gs_row = gs_base + static_cast<uint32_t>(lane) * 128u;
+    const int gsw = lane & 7;
+    auto stage_begin = [&]() {  // before the first write of a box
+      if (lane == 0) bulk_wait_group_read<0>();
+      __syncwarp();
+    };
+    auto stage_put32 = [&](const uint32_t (&w16)[16], int chalf) {  // 32 fp16 pairs = columns chalf * 32 .. + 32
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4)
+        st_shared_v4(gs_row + (((chalf * 4 + k4) ^ gsw) << 4), w16[4 * k4], w16[4 * k4 + 1], w16[4 * k4 + 2],
+                     w16[4 * k4 + 3]);
+    };
+    auto stage_store = [&](const CUtensorMap* gm, int box_row) {  // after the second half of a box is written
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(gm, gs_base, 0, box_row);
+        bulk_commit_group();
+      }
+    };
     auto release_slot = [&](int slot) {  // the MMA issuer lives in the pair's leader
       if constexpr (CG == 2) {
         // relaxed: a .release arrive is a MEMBAR that waits for every earlier memory operation of the thread
@@ -479,29 +516,46 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       const bool live_row = li < P.b;         // rows past b are K entries of the transposed GEMM: keep them zero
       const bool ds_both = P.ds_both != 0;
       float dsacc = 0.f;
-      // column values of the NEXT 32-column chunk are fetched while the current one is processed (two register
-      // buffers, loop fully unrolled so that they are addressed statically); launched with bn == 256 only
-      float4 lcA[8], lcB[8];
-      auto load_cols = [&](float4 (&d)[8], int gj0) {
-#pragma unroll
-        for (int e4 = 0; e4 < 8; ++e4) d[e4] = ldg_nc_v4_volatile(colv + gj0 + 4 * e4);
-      };
-      if (t0 < t1) load_cols(lcA, P.col0 + t0 * 256 + half * 128);
+      // per-column values: lane l fetches columns 4l .. 4l+3 of this warp's 128-column strip ONE TILE AHEAD (a
+      // single coalesced 16-byte load per lane and tile) and the warp broadcasts them with shuffles.  Eight
+      // broadcast loads per 32-column chunk, one chunk ahead, left the epilogue waiting on L2 (long-scoreboard
+      // stalls right after every chunk boundary); launched with bn == 256 only
+      float4 ccur = make_float4(0.f, 0.f, 0.f, 0.f), cnxt = ccur;
+      if (t0 < t1) cnxt = ldg_nc_v4_volatile(colv + P.col0 + t0 * 256 + half * 128 + 4 * lane);
       int it = 0;
       for (int t = t0; t < t1; ++t, ++it) {
         const int slot = it % nslots;
         const uint32_t use = static_cast<uint32_t>(it / nslots);
+        ccur = cnxt;
+        if (t + 1 < t1) cnxt = ldg_nc_v4_volatile(colv + P.col0 + (t + 1) * 256 + half * 128 + 4 * lane);
         mbar_wait(smem_u32(&s_full[slot]), use & 1);
         tc_fence_after();
+        // TMEM loads run one 32-column chunk ahead of the arithmetic (two register buffers)
+        uint32_t rA[32], rB[32];
+        tmem_ld32_nowait(lane_addr + slot * 256 + half * 128, rA);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int jrel0 = t * 256 + half * 128 + c * 32;
           const int gj0 = P.col0 + jrel0;
-          tmem_ld32(lane_addr + slot * 256 + half * 128 + c * 32, v);
-          float4(&cur)[8] = (c & 1) ? lcB : lcA;
-          float4(&nxt)[8] = (c & 1) ? lcA : lcB;
-          if (c < 3) load_cols(nxt, gj0 + 32);
-          else if (t + 1 < t1) load_cols(nxt, P.col0 + (t + 1) * 256 + half * 128);
+          uint32_t(&rcur)[32] = (c & 1) ? rB : rA;
+          uint32_t(&rnxt)[32] = (c & 1) ? rA : rB;
+          tmem_ld_wait(rcur);
+          if (c < 3) {
+            tmem_ld32_nowait(lane_addr + slot * 256 + half * 128 + (c + 1) * 32, rnxt);
+          } else {  // every value of this slot is in registers: hand it back before the last chunk's arithmetic
+            tc_fence_before();
+            release_slot(slot);
+          }
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(rcur[e]);
+          float4 cur[8];  // this chunk's 32 column values: column 4 e4 + k lives in lane c * 8 + e4, component k
+#pragma unroll
+          for (int e4 = 0; e4 < 8; ++e4) {
+            cur[e4].x = __shfl_sync(0xffffffffu, ccur.x, c * 8 + e4);
+            cur[e4].y = __shfl_sync(0xffffffffu, ccur.y, c * 8 + e4);
+            cur[e4].z = __shfl_sync(0xffffffffu, ccur.z, c * 8 + e4);
+            cur[e4].w = __shfl_sync(0xffffffffu, ccur.w, c * 8 + e4);
+          }
           // masking (diagonal, ragged columns, rows past b) only where a chunk can need it: warp-uniform
           const bool need_mask = (gw0 < gj0 + 32 && gj0 < gw0 + 32) || jrel0 + 32 > P.ncols || !real_block ||
                                  rb * BM + q * 32 + 32 > P.b;
@@ -539,11 +593,18 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
             for (int e = 0; e < 32; ++e)
               if (gj0 + e == gi || jrel0 + e >= P.ncols || !live_row) g[e] = 0.f;
           }
-          if (real_block && jrel0 + 32 <= P.g_pitch) store_g32(P.gout[0] + g_index(li, jrel0, P.g_pitch), g);
+          if (real_block && jrel0 + 32 <= P.g_pitch) {  // warp-uniform (the pitch is a multiple of 64 columns)
+            uint32_t w16[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) w16[k] = pack_f16x2(g[2 * k], g[2 * k + 1]);
+            if ((c & 1) == 0) stage_begin();
+            stage_put32(w16, c & 1);
+            if (c & 1)
+              stage_store(&maps.g[0], (rb * (P.g_pitch >> 6) + (jrel0 >> 6)) * BM + q * 32);
+          }
         }
-        tc_fence_before();
-        release_slot(slot);
       }
+      if (lane == 0) bulk_wait_group<0>();  // the stores have landed before the CTA may exit
       if (li < P.b) P.ds_part[sp * P.b + li] = dsacc;
     } else if constexpr (MODE == MODE_SOFT_G) {
       // G_aj = [(2^(p-ls_a) + 2^(p-ls_j)) - (2^(q-lt_a) + 2^(q-lt_j))] * mant(1/||y_j||), j != a, for the
@@ -578,13 +639,21 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
           const int slot = (it + 0) % 2;
           mbar_wait(smem_u32(&s_full[slot]), static_cast<uint32_t>((it + 0) / 2) & 1);
           tc_fence_after();
+          uint32_t rA[32], rB[32];  // TMEM loads run one chunk ahead of the arithmetic
+          tmem_ld32_nowait(lane_addr + slot * CT + half * 128, rA);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            tmem_ld32(lane_addr + slot * CT + half * 128 + c * 32, v);
-            if (c == 3) {
+            uint32_t(&rcur)[32] = (c & 1) ? rB : rA;
+            uint32_t(&rnxt)[32] = (c & 1) ? rA : rB;
+            tmem_ld_wait(rcur);
+            if (c < 3) {
+              tmem_ld32_nowait(lane_addr + slot * CT + half * 128 + (c + 1) * 32, rnxt);
+            } else {
               tc_fence_before();
               release_slot(slot);
             }
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(rcur[e]);
             const float4* rc = reinterpret_cast<const float4*>(cv + 0 * CT + c * 32);
             const float4* lc = reinterpret_cast<const float4*>(cv + 3 * CT + c * 32);
 #pragma unroll
@@ -615,15 +684,23 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
           const float cy = ry * my;
           const float fry = exp2f(my - P.lse_row[p][lic]);
           const float rowf = P.tri ? mant12(ry) : 1.f;
+          uint32_t rA[32], rB[32];
+          tmem_ld32_nowait(lane_addr + slot * CT + half * 128, rA);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const int jrel0 = jt0 + c * 32;
             const int gj0 = P.col0 + jrel0;
-            tmem_ld32(lane_addr + slot * CT + half * 128 + c * 32, v);
-            if (c == 3) {
+            uint32_t(&rcur)[32] = (c & 1) ? rB : rA;
+            uint32_t(&rnxt)[32] = (c & 1) ? rA : rB;
+            tmem_ld_wait(rcur);
+            if (c < 3) {
+              tmem_ld32_nowait(lane_addr + slot * CT + half * 128 + (c + 1) * 32, rnxt);
+            } else {
               tc_fence_before();
               release_slot(slot);
             }
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(rcur[e]);
             const bool need_mask = (gw0 < gj0 + 32 && gj0 < gw0 + 32) || jrel0 + 32 > P.ncols || !real_block ||
                                    rb * BM + q * 32 + 32 > P.b;
             const float4* rc = reinterpret_cast<const float4*>(cv + p * CT + c * 32);
@@ -647,15 +724,17 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
               w16[2 * e4 + 0] = pack_f16x2(g4[0], g4[1]);
               w16[2 * e4 + 1] = pack_f16x2(g4[2], g4[3]);
             }
-            if (real_block && jrel0 + 32 <= P.g_pitch) {
-              __half* dst = P.gout[p - 1] + g_index(li, jrel0, P.g_pitch);
-              st_cs_v8(dst, reinterpret_cast<const uint32_t(&)[8]>(w16[0]));
-              st_cs_v8(dst + 16, reinterpret_cast<const uint32_t(&)[8]>(w16[8]));
+            if (real_block && jrel0 + 32 <= P.g_pitch) {  // warp-uniform (the pitch is a multiple of 64 columns)
+              if ((c & 1) == 0) stage_begin();
+              stage_put32(w16, c & 1);
+              if (c & 1)
+                stage_store(&maps.g[p - 1], (rb * (P.g_pitch >> 6) + (jrel0 >> 6)) * BM + q * 32);
             }
           }
         }
         mbar_arrive(smem_u32(&col_empty[cb]));
       }
+      if (lane == 0) bulk_wait_group<0>();  // the stores have landed before the CTA may exit
     } else {
       const float cq = P.rinv[0][gi] * P.scal[SC_ITT_L2];
       const float cp = P.rinv[1][gi] * P.scal[SC_ITS_L2];
@@ -679,13 +758,21 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
           const int slot = (it + 0) % 2;
           mbar_wait(smem_u32(&s_full[slot]), static_cast<uint32_t>((it + 0) / 2) & 1);
           tc_fence_after();
+          uint32_t rA[32], rB[32];  // TMEM loads run one chunk ahead of the arithmetic
+          tmem_ld32_nowait(lane_addr + slot * CT + half * 128, rA);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            tmem_ld32(lane_addr + slot * CT + half * 128 + c * 32, v);
-            if (c == 3) {
+            uint32_t(&rcur)[32] = (c & 1) ? rB : rA;
+            uint32_t(&rnxt)[32] = (c & 1) ? rA : rB;
+            tmem_ld_wait(rcur);
+            if (c < 3) {
+              tmem_ld32_nowait(lane_addr + slot * CT + half * 128 + (c + 1) * 32, rnxt);
+            } else {
               tc_fence_before();
               release_slot(slot);
             }
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(rcur[e]);
             const float4* rc = reinterpret_cast<const float4*>(cv + c * 32);
 #pragma unroll
             for (int e4 = 0; e4 < 8; ++e4) {
@@ -730,14 +817,22 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
           const float cs = (p == 1) ? cp : cr;
           const float mfix = (p == 1) ? ms2 : mx2;
           float b0[4] = {0.f, 0.f, 0.f, 0.f}, b1[4] = {0.f, 0.f, 0.f, 0.f};
+          uint32_t rA[32], rB[32];
+          tmem_ld32_nowait(lane_addr + slot * CT + half * 128, rA);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const int jrel0 = jt0 + c * 32;
-            tmem_ld32(lane_addr + slot * CT + half * 128 + c * 32, v);
-            if (c == 3) {
+            uint32_t(&rcur)[32] = (c & 1) ? rB : rA;
+            uint32_t(&rnxt)[32] = (c & 1) ? rA : rB;
+            tmem_ld_wait(rcur);
+            if (c < 3) {
+              tmem_ld32_nowait(lane_addr + slot * CT + half * 128 + (c + 1) * 32, rnxt);
+            } else {
               tc_fence_before();
               release_slot(slot);
             }
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(rcur[e]);
             const float4* rc = reinterpret_cast<const float4*>(cv + p * CT + c * 32);
             const bool rag = ragged && jrel0 + 32 > P.ncols;
 #pragma unroll

@@ -42,6 +42,7 @@ except ImportError:  # pragma: no cover
     has_distributed = False
 
 from . import _cabi
+from .feature_store import DinoRows
 
 __all__ = [
     "gather_features",
@@ -100,7 +101,7 @@ _DTYPES = {torch.float32: _cabi.DT_F32, torch.bfloat16: _cabi.DT_BF16, torch.flo
 
 class _Plan:
     __slots__ = ("handle", "row_elems", "state_numel", "scratch_numel", "fwd_scratch_numel", "flops",
-                 "launches_fwd", "launches_bwd", "shape")
+                 "launches_fwd", "launches_bwd", "shape", "dino_col")
 
 
 def _rowmajor(x: torch.Tensor) -> torch.Tensor:
@@ -143,6 +144,7 @@ class CudaBackend:
             p.flops = float(self._lib.dsoft_plan_algorithmic_flops(h))
             p.launches_fwd = int(self._lib.dsoft_plan_launches_forward(h))
             p.launches_bwd = int(self._lib.dsoft_plan_launches_backward(h))
+            p.dino_col = int(self._lib.dsoft_plan_dino_col_offset(h))
             p.shape = shape
             self._plans[key] = p
         return p
@@ -273,8 +275,13 @@ class _DinoSoftFn(torch.autograd.Function):
         )
         plan = be.plan(shape, dev) if dev.type == "cuda" else be.plan(shape)
         gathered = torch.empty((b * W, plan.row_elems), dtype=torch.bfloat16, device=dev)
+        lazy_dino = isinstance(dino, DinoRows)
         be.pack(plan, image.detach(), text.detach(), None if student is None or not soft else student.detach(),
-                None if dino is None or not soft else dino.detach(), gathered)
+                None if (dino is None or not soft or lazy_dino) else dino.detach(), gathered)
+        if lazy_dino and soft:
+            # device feature store: the rows are gathered by index straight into the DINO columns of the packed
+            # buffer (range check on the device), replacing train.py:250-280's CPU gather + H2D copy
+            dino.store.gather_into_packed(dino, gathered, r * b, plan.dino_col)
         if W > 1:
             # the only feature exchange of the path: one all-gather of the packed bf16 rows (loss.py:23-81)
             dist.all_gather_into_tensor(gathered.view(-1), gathered[r * b:(r + 1) * b].view(-1), group=cfg.group)
@@ -606,6 +613,8 @@ class ClipLossWithDINOEnhancements(nn.Module):
         total_loss = terms[4]
         dbg = {}
         if weighted_on:
+            if isinstance(dino_features, DinoRows):
+                dino_features = dino_features.materialize()
             weighted_loss, dbg = _weighted_ce_branch(
                 image_features, text_features, logit_scale, dino_features, float(g(args, "rho", 0.1)),
                 float(g(args, "c_clip", 1.0)), bool(g(args, "weight_text_symmetry", False)))

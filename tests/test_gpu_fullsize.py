@@ -123,3 +123,31 @@ def test_finite_difference_consistency(setup):
         fd = (f(s0, ip, tp) - f(s0, im_, tm_)) / 2
         want = float((gi * dv).sum() + (gt * dw).sum())
         assert fd == pytest.approx(want, rel=5e-2, abs=1e-4)
+
+
+def test_config4_dims_b8192_against_fp64(pkg, backward_path):
+    """BASELINE config 4's per-GPU problem shape (D = 768, DINOv2-L dim 1024, student = image features,
+    text-symmetric) at B = 8192 against the row-blocked fp64 reference."""
+    Bc, Dc, Ddc, scale = 8192, 768, 1024, 50.0
+    img, txt, dino = synth(41, Bc, Dc, Ddc, device="cuda")
+    loss = pkg.ClipLossWithDINOEnhancements()
+    args = make_args(use_projection=False)
+    im = img.clone().requires_grad_(True)
+    tx = txt.clone().requires_grad_(True)
+    sc = torch.tensor(scale, device="cuda", requires_grad=True)
+    out = loss(im, tx, sc, dino, args, output_dict=True)
+    out["total_loss"].backward()
+    torch.cuda.synchronize()
+    blocks = [(0, 128), (Bc // 2 - 64, 128), (Bc - 128, 128)]
+    ref = chunked_reference(img, txt, dino, scale, head=None, blocks=blocks, slab=2048)
+    for k in ("total_loss", "classic_loss", "soft_loss"):
+        got = float(out[k].detach())
+        print(f"[config4] {k}: got={got:.7f} ref={ref[k]:.7f}")
+        assert got == pytest.approx(ref[k], rel=1e-4), k
+    assert float(sc.grad) == pytest.approx(ref["d_logit_scale"], rel=1e-3, abs=1e-7)
+    for blk in ref["blocks"]:
+        rows = slice(blk["row0"], blk["row0"] + blk["rows"])
+        for name, got in (("d_image", im.grad[rows]), ("d_text", tx.grad[rows])):
+            linf, l2 = rel_err(got, blk[name])
+            print(f"[config4] rows {blk['row0']}..: {name} linf={linf:.2e} l2={l2:.2e}")
+            assert linf < 1e-3 and l2 < 1e-3, (blk["row0"], name, linf, l2)

@@ -120,7 +120,18 @@ def cuda_ranks(pkg, img, txt, dino, student, scale, W, scope, gwg, gmat):
 @pytest.mark.parametrize("scope", ["global", "local"])
 @pytest.mark.parametrize("W,b,proj", [(2, 384, True), (4, 256, False), (8, 128, True), (8, 136, False)])
 def test_every_rank_against_oracle(pkg, oracle, W, b, proj, scope, gwg, gmat):
-    B, D, Dd, scale = W * b, 128, 192, 30.0
+    _run_case(pkg, oracle, W, b, proj, scope, gwg, gmat, 128, 192)
+
+
+@pytest.mark.parametrize("gmat", [True, False], ids=["two_phase", "fused"])
+def test_config4_dims_every_rank(pkg, oracle, gmat):
+    """BASELINE config 4 feature dims (ViT-L/14: D = 768, DINOv2-L: 1024, no head, text-symmetric) at world 4:
+    the CLIP kernels stream their row operand (K > 512), the gradient GEMMs run three 256-feature tiles."""
+    _run_case(pkg, oracle, 4, 256, False, "global", True, gmat, 768, 1024)
+
+
+def _run_case(pkg, oracle, W, b, proj, scope, gwg, gmat, D, Dd):
+    B, scale = W * b, 30.0
     img, txt, dino = synth(31 + W, B, D, Dd)
     student = None
     if proj:  # a raw (un-normalised) head output, bf16-representable like the module's straight-through rounding

@@ -120,3 +120,11 @@ def test_module_wiring_reproduces_reference_fixture(pkg, oracle, fname):
         err = np.abs(got.numpy() - ref).max() / np.abs(ref).max()
         assert err < max(tol * 4, 1e-6), (key, err)
     assert float(sc.grad) == pytest.approx(float(z["f64_r0_d_logit_scale"]), rel=max(tol, 1e-6), abs=1e-9)
+
+
+def test_feature_store_needs_cuda(pkg):
+    """No CPU path: the device feature store refuses a CPU device."""
+    import torch
+
+    with pytest.raises(RuntimeError, match="needs a CUDA device"):
+        pkg.DinoFeatureStore(torch.zeros(4, 8), "cpu")
