@@ -326,10 +326,15 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA sm_100 device (no CPU fallback for the product path)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    stdout_fd = None
     if world > 1:
-        # NCCL prints its version banner to stdout at VERSION level; stdout must carry the JSON line only
+        # NCCL prints its version banner to stdout (fd 1) when the communicator is created; stdout must carry the
+        # JSON line only, so fd 1 points at stderr until the line is printed
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
+        sys.stdout.flush()
+        stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     assert GLOBAL_B % world == 0
     b = GLOBAL_B // world
@@ -571,6 +576,9 @@ def run_ours(args):
             "gpu_eager_baseline": gpu_eager,
             "loss": final_loss,
         }
+        if stdout_fd is not None:
+            sys.stdout.flush()
+            os.dup2(stdout_fd, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DSOFT_VERSION 100 /* 0.1.0 */
+#define DSOFT_VERSION 200 /* 0.2.0 */
 
 /* error codes */
 #define DSOFT_EINVAL (-1)  /* bad argument / unsupported shape            */
@@ -42,6 +42,11 @@ extern "C" {
                                   2 bytes per element of the local [b x columns] blocks), and the feature
                                   gradients come from plain M=256 x N=256 gradient GEMMs.  Same results as
                                   the fused backward, faster when the scratch memory can be spared.       */
+
+#define DSOFT_F_WEIGHTED 32u    /* denominator-modulated ("weighted") CE branch, loss.py:416-471 + diagnostics
+                                  479-595: DINO-dissimilarity offsets on the CLIP logits.  Single-rank only, like
+                                  the reference; its backward needs DSOFT_F_GMAT.                        */
+#define DSOFT_F_WSYM 64u        /* weight_text_symmetry: modulate the text direction too (loss.py:449-463) */
 
 /* element types accepted by dsoft_pack */
 #define DSOFT_DT_F32 0
@@ -61,6 +66,8 @@ typedef struct dsoft_shape {
   uint32_t flags; /* DSOFT_F_*                                                      */
   float teacher_temp; /* tau_t  (loss.py:368)                                       */
   float text_temp;    /* tau_txt (loss.py:391)                                      */
+  float rho;          /* weighted CE: beta = rho * median(row std) / c_clip (loss.py:418, 443) */
+  float c_clip;       /* weighted CE: clamp of the centred dissimilarity (loss.py:419)  */
 } dsoft_shape_t;
 
 typedef struct dsoft_plan dsoft_plan_t; /* opaque: packed layout, tile/split schedule, workspace map */
@@ -125,17 +132,22 @@ int dsoft_gather_rows(const void* table_dev, int table_dtype, int64_t ld_table, 
                       long long* status_dev, void* stream);
 
 /* Forward statistics pass.  logit_scale_dev: one fp32 (already exp'd, reference model.py:571).
- * lambdas (HOST, 3 floats): {lambda_original, lambda_soft, text_lambda} (loss.py:387-388, 474).
- * Outputs: lse_local_dev [5][b] fp32 (log2-domain row log-sum-exps: clip i->t, clip t->i, teacher,
- * student, text) and losses_dev[5] = {classic_loss, soft_imgimg, soft_texttext,
- * soft = imgimg + text_lambda * texttext, total = lambda_original * classic + lambda_soft * soft}
- * (loss.py:317-319, 383, 396-397, 473-477), the first three already divided by b. */
+ * lambdas (HOST, 4 floats): {lambda_original, lambda_soft, text_lambda, lambda_weighted} (loss.py:387-388,
+ * 417, 474).  Outputs: lse_local_dev [5][b] fp32 (log2-domain row log-sum-exps: clip i->t, clip t->i,
+ * teacher, student, text) and losses_dev[6] = {classic_loss, soft_imgimg, soft_texttext,
+ * soft = imgimg + text_lambda * texttext, total = lambda_original * classic + lambda_soft * soft
+ * + lambda_weighted * weighted, weighted_loss} (loss.py:317-319, 383, 396-397, 466, 473-477), the first three
+ * already divided by b.  With DSOFT_F_WEIGHTED, dbg_dev (32 floats, may be NULL to skip the diagnostics pass)
+ * receives the reference's diagnostic scalars (loss.py:479-595): [0,1] pc_err img/txt, [2,3] diag_max, [4..6]
+ * delta_img max/mean/std, [7..9] delta_txt, [10,11] l1_prob_shift, [12,13] corr_rhat_dprob, [14..17] ce_img_base,
+ * ce_txt_base, ce_img_mod, ce_txt_mod, [18..21] pos/neg_frac img, pos/neg_frac txt, [22,23] beta img/txt,
+ * [24] rho, [25] c_clip.  beta stays on the device: no host synchronisation (the reference calls .item()). */
 int dsoft_forward(const dsoft_plan_t* plan, const void* gathered_dev, const float* logit_scale_dev,
                   const float* lambdas_host, void* state_dev, void* scratch_dev, float* lse_local_dev,
-                  float* losses_dev, void* stream);
+                  float* losses_dev, float* dbg_dev, void* stream);
 
 /* Backward pass.  lse_all_dev [world][5][b] = all ranks' lse_local (all-gathered by the caller when
- * world > 1).  gout_dev[5] = upstream gradients of the five forward outputs (the chain rule through
+ * world > 1).  gout_dev[6] = upstream gradients of the six forward outputs (the chain rule through
  * `soft` and `total` is applied on the device with the same lambdas).  Outputs (fp32):
  * d_image [b][D], d_text [b][D], d_student [b][Dp] (ignored when Dp == 0), d_logit_scale [1].
  * Gradients follow the reference's per-rank convention (sum over ranks' losses == W x gradient of the

@@ -10,6 +10,8 @@ import threading
 from . import _build
 
 DSOFT_F_SOFT, DSOFT_F_TEXT, DSOFT_F_SOFT_LOCAL, DSOFT_F_ROW_ONLY, DSOFT_F_GMAT = 1, 2, 4, 8, 16
+DSOFT_F_WEIGHTED, DSOFT_F_WSYM = 32, 64
+DBG_N = 32
 DT_F32, DT_BF16, DT_F16 = 0, 1, 2
 
 
@@ -20,6 +22,7 @@ class Shape(C.Structure):
         ("b", C.c_int32), ("world", C.c_int32), ("rank", C.c_int32),
         ("D", C.c_int32), ("Dp", C.c_int32), ("Dd", C.c_int32),
         ("flags", C.c_uint32), ("teacher_temp", C.c_float), ("text_temp", C.c_float),
+        ("rho", C.c_float), ("c_clip", C.c_float),
     ]
 
     def key(self):
@@ -51,7 +54,7 @@ PROTOTYPES = {
                              C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int64,
                              C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int64,
                              C.c_void_p, C.c_void_p]),
-    "dsoft_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)] + [C.c_void_p] * 5),
+    "dsoft_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)] + [C.c_void_p] * 6),
     "dsoft_backward": (C.c_int, [C.c_void_p] * 6 + [C.POINTER(C.c_float)] + [C.c_void_p] * 5),
     "dsoft_selftest_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "dsoft_selftest_chain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

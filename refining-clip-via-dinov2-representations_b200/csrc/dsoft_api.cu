@@ -50,6 +50,8 @@ struct dsoft_plan {
   int B;           // global batch
   int Bcol;        // padded length of per-column fp32 vectors
   int have_soft, have_text, have_proj, soft_local, row_only;
+  int weighted, wsym;  // denominator-modulated CE branch (loss.py:416-471), world == 1 only
+  SplitPlan f_wce;     // column split of its tile passes
   int Dz;          // student width (Dp or D)
   // packed row layout (elements)
   int offI, offT, offZ, offD, row_elems;
@@ -62,8 +64,9 @@ struct dsoft_plan {
   SplitPlan f_clip, f_soft, b_clip, b_stu, b_txt;
   int nch_clip, nch_stu, nch_txt;
   // state layout (float offsets)
-  size_t st_scal, st_rinv_t, st_rinv_z, st_rinv_d, st_diag, st_lsecols, st_colfac, st_lsestat, st_total;
+  size_t st_scal, st_rinv_t, st_rinv_z, st_rinv_d, st_diag, st_lsecols, st_colfac, st_lsestat, st_wstat, st_total;
   // scratch layout (float offsets)
+  size_t sc_wpart, sc_wrows;  // weighted CE: split partials [11][npart][b], per-row results [2][WR_N][b]
   size_t sc_pc_it, sc_pc_ti, sc_ps, sc_rowloss, sc_acc1, sc_acc2, sc_acc3, sc_acc4, sc_ds1, sc_ds2,
       sc_dsrow, sc_v16, sc_total;
   // fp16 gradient-operand buffer [B][v_row]: text | image | normalised student | normalised text
@@ -149,6 +152,13 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   if (soft && !(sh->teacher_temp > 0.f)) return fail(DSOFT_EINVAL, "teacher_temp must be > 0");
   if ((sh->flags & DSOFT_F_TEXT) && !(sh->text_temp > 0.f))
     return fail(DSOFT_EINVAL, "text_temp must be > 0");
+  if (sh->flags & DSOFT_F_WEIGHTED) {
+    // the reference builds r and the diagonal mask from the LOCAL batch against [b, B] logits and fails in the
+    // first broadcast when world > 1 (loss.py:423-446)
+    if (sh->world != 1) return fail(DSOFT_EINVAL, "the weighted CE branch is single-rank only (loss.py:416-471)");
+    if (sh->Dd == 0) return fail(DSOFT_EINVAL, "DSOFT_F_WEIGHTED needs Dd > 0");
+    if (!(sh->c_clip > 0.f)) return fail(DSOFT_EINVAL, "c_clip must be > 0");
+  }
   if (static_cast<long>(sh->b) * sh->world > (1L << 30)) return fail(DSOFT_EINVAL, "batch too large");
   if (sh->D > 2048 || sh->Dp > 2048) return fail(DSOFT_EINVAL, "feature dims above 2048 are not supported");
 
@@ -165,6 +175,8 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   p->have_soft = soft;
   p->have_text = (sh->flags & DSOFT_F_TEXT) != 0;
   p->have_proj = soft && sh->Dp > 0;
+  p->weighted = (sh->flags & DSOFT_F_WEIGHTED) != 0;
+  p->wsym = p->weighted && (sh->flags & DSOFT_F_WSYM) != 0;
   p->soft_local = (sh->flags & DSOFT_F_SOFT_LOCAL) != 0 && sh->world > 1;
   p->row_only = (sh->flags & DSOFT_F_ROW_ONLY) != 0 && sh->world > 1;
   p->Dz = p->have_proj ? sh->Dp : sh->D;
@@ -173,7 +185,7 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   p->offT = sh->D;
   p->offZ = p->have_proj ? 2 * sh->D : 0;
   p->offD = 2 * sh->D + (p->have_proj ? sh->Dp : 0);
-  p->row_elems = p->offD + (soft ? sh->Dd : 0);
+  p->row_elems = p->offD + ((soft || p->weighted) ? sh->Dd : 0);
 
   const int rbs = ceil_div(sh->b, BM);
   p->ntiles_g = ceil_div(p->B, BN);
@@ -187,6 +199,7 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   p->nch_txt = ceil_div(sh->D, CHUNK_F);
   p->f_clip = choose_split(rbs, 1, ceil_div(p->B, 2 * BN), sms);  // forward CLIP kernel uses 256-column tiles
   p->f_soft = choose_split(rbs, 1, p->ntiles_s, sms);
+  p->f_wce = choose_split(rbs, 1, ceil_div(p->B, 2 * BN), sms);
   p->b_clip = choose_split(rbs, p->nch_clip, p->ntiles_g, sms);
   p->b_stu = choose_split(rbs, p->nch_stu, p->ntiles_s128, sms);
   p->b_txt = choose_split(rbs, p->nch_txt, p->ntiles_s128, sms);
@@ -213,6 +226,7 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   p->st_lsecols = take(static_cast<size_t>(5) * p->Bcol);
   p->st_colfac = take(static_cast<size_t>(5) * p->Bcol);
   p->st_lsestat = take(2 * 64);
+  p->st_wstat = take(p->weighted ? static_cast<size_t>(8) * p->Bcol : 0);
   p->st_total = o;
 
   // ---- scratch (floats)
@@ -222,6 +236,8 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   p->sc_pc_ti = take(2 * 2 * p->f_clip.nsplit * b);
   p->sc_ps = take(soft ? 7 * 2 * p->f_soft.nsplit * b : 0);
   p->sc_rowloss = take(3 * b);
+  p->sc_wpart = take(p->weighted ? 11 * 2 * p->f_wce.nsplit * b : 0);
+  p->sc_wrows = take(p->weighted ? 2 * 10 * b : 0);
   p->sc_fwd_total = o;  // the forward only needs the statistics partials above
   const size_t ns_c = p->gmat ? std::max(p->g_clip.nsplit, p->g_clip_t.nsplit) : p->b_clip.nsplit;
   const size_t ns_s = p->gmat ? p->g_stu.nsplit : p->b_stu.nsplit;
@@ -230,8 +246,9 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   p->sc_acc2 = take(ns_c * b * sh->D);
   p->sc_acc3 = take(soft ? ns_s * b * p->Dz : 0);
   p->sc_acc4 = take(p->have_text ? ns_x * b * sh->D : 0);
-  p->sc_ds1 = take(p->gmat ? 2 * p->f_clip.nsplit * b : 2 * X_MAXC * p->b_clip.nsplit * b);
-  p->sc_ds2 = take(p->gmat ? 2 * p->f_clip.nsplit * b : 2 * X_MAXC * p->b_clip.nsplit * b);
+  const size_t nds_g = 2 * std::max(p->f_clip.nsplit, p->weighted ? p->f_wce.nsplit : 0);
+  p->sc_ds1 = take(p->gmat ? nds_g * b : 2 * X_MAXC * p->b_clip.nsplit * b);
+  p->sc_ds2 = take(p->gmat ? nds_g * b : 2 * X_MAXC * p->b_clip.nsplit * b);
   p->sc_dsrow = take(b);
   if (p->gmat) {
     const size_t bpad = static_cast<size_t>(rbs) * BM;  // blocked layout holds whole 128-row blocks
@@ -363,7 +380,7 @@ static int make_maps(const dsoft_plan* p, const void* gathered, TileMaps* tm, in
   if ((rc = make_map(&tm->m[0], g + p->offI, p->B, p->sh.D, p->row_elems, bf, box_rows))) return rc;
   if ((rc = make_map(&tm->m[1], g + p->offT, p->B, p->sh.D, p->row_elems, bf, box_rows))) return rc;
   if ((rc = make_map(&tm->m[2], g + p->offZ, p->B, p->Dz, p->row_elems, bf, box_rows))) return rc;
-  if (p->have_soft) {
+  if (p->have_soft || p->weighted) {
     if ((rc = make_map(&tm->m[3], g + p->offD, p->B, p->sh.Dd, p->row_elems, bf, box_rows))) return rc;
   } else {
     tm->m[3] = tm->m[0];
@@ -638,6 +655,7 @@ __global__ void __launch_bounds__(128) finalize_fwd_kernel(FinFwdArgs a) {
       a.losses[2] = s_txt;
       a.losses[3] = soft;
       a.losses[4] = a.lam_orig * classic + a.lam_soft * soft;            // loss.py:473-477
+      a.losses[5] = 0.f;                                                 // weighted CE: wce_final_kernel
     }
   }
 }
@@ -799,6 +817,12 @@ struct FinBwdArgs {
   int b, D, Dz, row0, row_elems, offI, offT, offZ;
   int have_soft, have_text, have_proj, row_only;
   int sym_scaled;  // two-phase backward, world == 1: the soft G matrices carry mant(1/||y_i||) of their ROW as well
+  // weighted CE (world == 1): the CLIP logit-gradient matrix already carries g_c and g_w; the diagonal entry of
+  // both directions is applied here in fp32
+  int weighted, wsym;
+  const float* wstat;  // [2 directions][4][Bcol]: c, lse~, A, (std)
+  int Bcol;
+  float lam_w;
   int ns_c, ns_c2, ns_s, ns_x;  // split counts of acc1, acc2, acc3, acc4
   int nds;  // d(logit_scale) partials per row: nsplit x cluster size x 2 halves
   const __nv_bfloat16* gathered;
@@ -854,6 +878,42 @@ __device__ __forceinline__ float4 load_bf16x4(const __nv_bfloat16* p) {
   return make_float4(a.x, a.y, b.x, b.y);
 }
 
+// Diagonal entry of the CLIP logit-gradient matrix (applied in fp32: near convergence p_aa -> 1 and the entry is a
+// small residual), the coefficient of the CLIP part and the diagonal's share of d(logit_scale).
+//   classic:  dg = (p_it_aa - 1) + (p_ti_aa - 1); the matrix is unscaled, g_c s / (2b) is applied here; the row
+//             partials of d(logit_scale) include the diagonal's probabilities, hence the - 2 dot_aa
+//   weighted (world == 1): the matrix already carries g_c and g_w and has no diagonal;
+//             dg = g_c [(p_it_aa - 1) + (p_ti_aa - 1)] + g_w [(p~_it_aa - 1 + beta A_a p_it_aa c_a) + text direction]
+//             (d CE~_a / d x_aa = p~_aa - 1 - beta A_a p_aa (r_aa - c_a) with r_aa = 0, loss.py:416-471)
+struct ClipDiag { float dg_img, dg_txt, coefc, ds_diag; };
+__device__ __forceinline__ ClipDiag clip_diag(const FinBwdArgs& a, int i, float gc, float inv_b) {
+  const float LN2 = 0.6931471805599453f;
+  const float xd = a.scal[SC_SCALE_L2] * a.diag[i];
+  const float dm_it = expm1f(LN2 * (xd - a.lse_loc[0 * a.b + i]));
+  const float dm_ti = expm1f(LN2 * (xd - a.lse_loc[1 * a.b + i]));
+  ClipDiag r;
+  if (!a.weighted) {
+    r.dg_img = a.row_only ? dm_it : dm_it + dm_ti;
+    r.dg_txt = a.row_only ? dm_ti : dm_it + dm_ti;
+    r.coefc = gc * a.scal[SC_SCALE] * 0.5f * inv_b;
+    r.ds_diag = -2.f * a.diag[i];
+  } else {
+    const float gw = a.gout[5] + a.lam_w * a.gout[4];
+    const float* wi = a.wstat;
+    const float* wt = a.wstat + static_cast<size_t>(4) * a.Bcol;
+    const float g_img = expm1f(LN2 * (xd - wi[1 * a.Bcol + i])) +
+                        a.scal[SC_WBETA + 0] * wi[2 * a.Bcol + i] * (dm_it + 1.f) * wi[0 * a.Bcol + i];
+    const float g_txt = a.wsym ? expm1f(LN2 * (xd - wt[1 * a.Bcol + i])) +
+                                     a.scal[SC_WBETA + 1] * wt[2 * a.Bcol + i] * (dm_ti + 1.f) * wt[0 * a.Bcol + i]
+                               : dm_ti;
+    const float dg = gc * (dm_it + dm_ti) + gw * (g_img + g_txt);
+    r.dg_img = r.dg_txt = dg;
+    r.coefc = a.scal[SC_SCALE] * 0.5f * inv_b;
+    r.ds_diag = dg * a.diag[i];
+  }
+  return r;
+}
+
 template <int FB_MAXIT>
 __global__ void __launch_bounds__(128) finalize_bwd_kernel(FinBwdArgs a) {
   __shared__ float sh[4];
@@ -870,14 +930,8 @@ __global__ void __launch_bounds__(128) finalize_bwd_kernel(FinBwdArgs a) {
   const float gc = a.gout[0] + a.lam_orig * a.gout[4];
   const float gs = a.gout[1] + g_soft;
   const float gx = a.gout[2] + a.text_lambda * g_soft;
-  const float coefc = gc * a.scal[SC_SCALE] * 0.5f * inv_b;
-  // diagonal entry of the CE logit gradient, (p_it_aa - 1) + (p_ti_aa - 1), in fp32 via expm1
-  const float LN2 = 0.6931471805599453f;
-  const float xd = a.scal[SC_SCALE_L2] * a.diag[i];
-  const float dm_it = expm1f(LN2 * (xd - a.lse_loc[0 * a.b + i]));
-  const float dm_ti = expm1f(LN2 * (xd - a.lse_loc[1 * a.b + i]));
-  const float dg_img = a.row_only ? dm_it : dm_it + dm_ti;
-  const float dg_txt = a.row_only ? dm_ti : dm_it + dm_ti;
+  const ClipDiag cd = clip_diag(a, i, gc, inv_b);
+  const float coefc = cd.coefc, dg_img = cd.dg_img, dg_txt = cd.dg_txt;
 
   float4 di[FB_MAXIT], dt[FB_MAXIT];  // d_image / d_text of this thread's features (D <= 2048)
   float4 tfeat[FB_MAXIT];             // text features (reused by the text-text term)
@@ -901,7 +955,7 @@ __global__ void __launch_bounds__(128) finalize_bwd_kernel(FinBwdArgs a) {
   if (tid == 0) {
     float d = 0.f;
     for (int s = 0; s < a.nds; ++s) d += a.ds1[s * a.b + i] + a.ds2[s * a.b + i];
-    ds_block += d - 2.f * a.diag[i];
+    ds_block += d + cd.ds_diag;
   }
 
   // ---- student KL (loss.py:358-383 backward): d z~ = (g / (b tau_s)) * acc3 ; chain through normalize
@@ -983,7 +1037,7 @@ __global__ void __launch_bounds__(128) finalize_bwd_kernel(FinBwdArgs a) {
   if (last_block_done(a.ticket)) {
     __shared__ double sum1[1];
     block_reduce_rows(a.dsrow, gridDim.x, 1, sum1);
-    const float gc = a.gout[0] + a.lam_orig * a.gout[4];
+    const float gc = a.weighted ? 1.f : a.gout[0] + a.lam_orig * a.gout[4];
     if (threadIdx.x == 0) a.d_scale[0] = static_cast<float>(sum1[0] * static_cast<double>(gc) * 0.5 / a.b);
   }
 }
@@ -1004,7 +1058,6 @@ __global__ void __launch_bounds__(256, 2) finalize_bwd_warp_kernel(FinBwdArgs a)
   const float gc = a.gout[0] + a.lam_orig * a.gout[4];
   const float gs = a.gout[1] + g_soft;
   const float gx = a.gout[2] + a.text_lambda * g_soft;
-  const float coefc = gc * a.scal[SC_SCALE] * 0.5f * inv_b;
   float ds_warp = 0.f;
   auto warp_sum = [](float v) {
 #pragma unroll
@@ -1014,11 +1067,8 @@ __global__ void __launch_bounds__(256, 2) finalize_bwd_warp_kernel(FinBwdArgs a)
   for (int i = blockIdx.x * 8 + warp; i < a.b; i += gridDim.x * 8) {
     const size_t gi = static_cast<size_t>(a.row0) + i;
     const __nv_bfloat16* rowp = a.gathered + gi * a.row_elems;
-    const float xd = a.scal[SC_SCALE_L2] * a.diag[i];
-    const float dm_it = expm1f(LN2 * (xd - a.lse_loc[0 * a.b + i]));
-    const float dm_ti = expm1f(LN2 * (xd - a.lse_loc[1 * a.b + i]));
-    const float dg_img = a.row_only ? dm_it : dm_it + dm_ti;
-    const float dg_txt = a.row_only ? dm_ti : dm_it + dm_ti;
+    const ClipDiag cd = clip_diag(a, i, gc, inv_b);
+    const float coefc = cd.coefc, dg_img = cd.dg_img, dg_txt = cd.dg_txt;
     float4 xs[NVZ];  // student term: d_student, or the share of d_image when the student IS the image feature
     float4 tf[NVD];  // text features
     float4 xt[NVD];  // text-text term's share of d_text
@@ -1110,7 +1160,7 @@ __global__ void __launch_bounds__(256, 2) finalize_bwd_warp_kernel(FinBwdArgs a)
     float d = 0.f;
     for (int s = lane; s < a.nds; s += 32) d += a.ds1[s * a.b + i] + a.ds2[s * a.b + i];
     d = warp_sum(d);
-    ds_warp += d - 2.f * a.diag[i];
+    ds_warp += d + cd.ds_diag;
   }
   // ---- d logit_scale = g_classic / (2b) * sum_i dsrow[i], finished by the last block (fixed order: deterministic)
   if (lane == 0) ds_sh[warp] = ds_warp;
@@ -1123,7 +1173,8 @@ __global__ void __launch_bounds__(256, 2) finalize_bwd_warp_kernel(FinBwdArgs a)
   if (last_block_done(a.ticket)) {
     __shared__ double sum1[1];
     block_reduce_rows(a.dsrow, gridDim.x, 1, sum1);
-    if (threadIdx.x == 0) a.d_scale[0] = static_cast<float>(sum1[0] * static_cast<double>(gc) * 0.5 / a.b);
+    if (threadIdx.x == 0)
+      a.d_scale[0] = static_cast<float>(sum1[0] * static_cast<double>(a.weighted ? 1.f : gc) * 0.5 / a.b);
   }
 }
 
@@ -1370,7 +1421,7 @@ extern "C" int dsoft_pack(const dsoft_plan_t* p, const void* image, int image_dt
   if ((rc = add(image, image_dt, ld_image, p->sh.D, p->offI))) return rc;
   if ((rc = add(text, text_dt, ld_text, p->sh.D, p->offT))) return rc;
   if (p->have_proj && (rc = add(student, student_dt, ld_student, p->sh.Dp, p->offZ))) return rc;
-  if (p->have_soft && dino && (rc = add(dino, dino_dt, ld_dino, p->sh.Dd, p->offD))) return rc;
+  if ((p->have_soft || p->weighted) && dino && (rc = add(dino, dino_dt, ld_dino, p->sh.Dd, p->offD))) return rc;
   bool vec8 = reinterpret_cast<uintptr_t>(base) % 16 == 0 && a.dst_ld % 8 == 0;
   for (int k = 0; k < a.nmat; ++k) {
     const PackSrc& m = a.m[k];
@@ -1488,9 +1539,274 @@ static void fill_clip_fwd(const dsoft_plan* p, FwdParams& P, int amap, int bmap,
   P.diag = diag;
 }
 
+// ------------------------------------------------------------------------------------------------
+// denominator-modulated ("weighted") CE branch, loss.py:416-471 + diagnostics loss.py:479-595 (world == 1)
+// ------------------------------------------------------------------------------------------------
+// Per direction (image rows x text columns; text rows x image columns when weight_text_symmetry):
+//   STAT tile pass -> wce_rows<0> (c_a, row std) -> wce_median (beta) -> LSE tile pass -> wce_rows<1> (lse~, A_a,
+//   row CE) -> DBG tile pass -> wce_rows<2> (diagnostic rows);  then wce_final assembles the loss and the dbg
+//   scalars.  Nothing of size B x B is stored; beta stays on the device (the reference's `.item()` syncs are gone).
+enum { WS_C = 0, WS_LSET = 1, WS_A = 2, WS_STD = 3 };       // state rows per direction: [dir * 4 + k][Bcol]
+enum { WR_CE_MOD = 0, WR_CE_BASE, WR_PC, WR_L1, WR_CORR, WR_SABS, WR_SSQ, WR_MAX, WR_POS, WR_DIAG, WR_N };
+enum { DBG_N = 32 };
+
+struct WceRowsArgs {
+  int b, np, dir;
+  const float* part;   // [k][np][b]
+  const float* lse;    // [b] log2 LSE of the unmodified logits of this direction
+  const float* diag;   // [b] raw diagonal dot products
+  const float* scal;
+  float* wstat;        // state rows of this direction [4][Bcol]
+  int Bcol;
+  float* wrows;        // [WR_N][b] of this direction
+  float cc;
+};
+
+template <int PHASE>
+__global__ void __launch_bounds__(256) wce_rows_kernel(WceRowsArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.b) return;
+  const float LN2 = 0.6931471805599453f;
+  const int st = a.np * a.b;
+  float* ws = a.wstat;
+  if constexpr (PHASE == 0) {
+    float c = 0.f;
+    double s1 = 0.0, s2 = 0.0;  // sums of x and x^2 in log2 units; fp64 for the E[x^2] - E[x]^2 cancellation
+    for (int k = 0; k < a.np; ++k) {
+      c += a.part[0 * st + k * a.b + i];
+      s1 += static_cast<double>(a.part[1 * st + k * a.b + i]);
+      s2 += static_cast<double>(a.part[2 * st + k * a.b + i]);
+    }
+    const double n = a.b;  // square logits: one column per row
+    const double var = (s2 - s1 * s1 / n) / (n - 1.0);  // torch.std: unbiased (loss.py:440)
+    ws[WS_C * a.Bcol + i] = c;
+    ws[WS_STD * a.Bcol + i] = static_cast<float>(sqrt(var > 0.0 ? var : 0.0)) * LN2;  // natural-log units
+  } else if constexpr (PHASE == 1) {
+    float m = M_FLOOR;
+    for (int k = 0; k < a.np; ++k) m = fmaxf(m, a.part[0 * st + k * a.b + i]);
+    float s = 0.f, si = 0.f;
+    for (int k = 0; k < a.np; ++k) {
+      const float sc = exp2f(a.part[0 * st + k * a.b + i] - m);
+      s += a.part[1 * st + k * a.b + i] * sc;
+      si += a.part[2 * st + k * a.b + i] * sc;
+    }
+    const float lset = m + log2f(s);
+    ws[WS_LSET * a.Bcol + i] = lset;
+    ws[WS_A * a.Bcol + i] = si / s;
+    const float xd = a.scal[SC_SCALE] * a.diag[i];
+    a.wrows[WR_CE_MOD * a.b + i] = LN2 * lset - xd;       // loss.py:447 / 463: CE row of the modified logits
+    a.wrows[WR_CE_BASE * a.b + i] = LN2 * a.lse[i] - xd;  // loss.py:541-542
+  } else {
+    float acc[11];
+    for (int q = 0; q < 11; ++q) {
+      float v = 0.f;
+      for (int k = 0; k < a.np; ++k)
+        v = (q == 9) ? fmaxf(v, a.part[q * st + k * a.b + i]) : v + a.part[q * st + k * a.b + i];
+      acc[q] = v;
+    }
+    const float n = static_cast<float>(a.b);
+    // rowwise Pearson correlation of r^ and (p~ - p), loss.py:528-536
+    const float cov = acc[6] - acc[2] * acc[4] / n;
+    const float vr = fmaxf(acc[3] - acc[2] * acc[2] / n, 0.f), vd = fmaxf(acc[5] - acc[4] * acc[4] / n, 0.f);
+    a.wrows[WR_PC * a.b + i] = fabsf(acc[0]);
+    a.wrows[WR_L1 * a.b + i] = acc[1];
+    a.wrows[WR_CORR * a.b + i] = cov / (sqrtf(vr) * sqrtf(vd) + 1e-9f);
+    a.wrows[WR_SABS * a.b + i] = acc[7];
+    a.wrows[WR_SSQ * a.b + i] = acc[8];
+    a.wrows[WR_MAX * a.b + i] = acc[9];
+    a.wrows[WR_POS * a.b + i] = acc[10];
+    a.wrows[WR_DIAG * a.b + i] = fabsf(fminf(fmaxf(-ws[WS_C * a.Bcol + i], -a.cc), a.cc));  // |r^_ii|, r_ii = 0
+  }
+}
+
+// beta = rho * max(median_row(std), 1e-6) / c_clip (loss.py:440-443).  torch.median returns the LOWER of the two
+// middle values: the element of rank (b - 1) / 2.  One block, four 8-bit radix-select passes over the bit
+// patterns (non-negative floats order like unsigned integers).
+__global__ void __launch_bounds__(1024) wce_median_kernel(const float* __restrict__ v, int b, float rho, float cc,
+                                                          float* __restrict__ scal, int dir) {
+  __shared__ unsigned hist[256];
+  __shared__ unsigned s_prefix, s_rank;
+  if (threadIdx.x == 0) { s_prefix = 0u; s_rank = static_cast<unsigned>((b - 1) / 2); }
+  __syncthreads();
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0u;
+    __syncthreads();
+    const unsigned prefix = s_prefix;
+    const unsigned mask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+    for (int i = threadIdx.x; i < b; i += blockDim.x) {
+      const unsigned key = __float_as_uint(v[i]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned rank = s_rank, bin = 0u;
+      for (; bin < 256u; ++bin) {
+        if (rank < hist[bin]) break;
+        rank -= hist[bin];
+      }
+      s_prefix = prefix | (bin << shift);
+      s_rank = rank;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float sigma = fmaxf(__uint_as_float(s_prefix), 1e-6f);
+    const float beta = rho * sigma / cc;
+    scal[SC_WBETA + dir] = beta;
+    scal[SC_WBETA2 + dir] = beta * 1.4426950408889634f;
+  }
+}
+
+struct WceFinalArgs {
+  int b, sym;
+  const float* wrows;  // [2][WR_N][b]
+  const float* lse;    // [5][b] (only the text direction's base CE needs it when !sym)
+  const float* diag;
+  const float* scal;
+  float rho, cc, lam_w;
+  float* losses;       // [6]: total (4) gets + lam_w * weighted, weighted -> (5)
+  float* dbg;          // [DBG_N] or null
+};
+
+// one block: deterministic fp64 reductions over the per-row results, then the scalars
+__global__ void __launch_bounds__(1024) wce_final_kernel(WceFinalArgs a) {
+  __shared__ double sh[32];
+  __shared__ double res[2][WR_N];
+  const float LN2 = 0.6931471805599453f;
+  for (int d = 0; d < 2; ++d) {
+    for (int k = 0; k < WR_N; ++k) {
+      double acc = 0.0;
+      const bool is_max = (k == WR_MAX || k == WR_DIAG);
+      const bool have = d == 0 || a.sym || k == WR_CE_BASE;
+      if (have) {
+        for (int i = threadIdx.x; i < a.b; i += blockDim.x) {
+          double v;
+          if (d == 1 && !a.sym) v = LN2 * a.lse[1 * a.b + i] - a.scal[SC_SCALE] * a.diag[i];  // plain text-direction CE
+          else v = a.wrows[(d * WR_N + k) * a.b + i];
+          acc = is_max ? fmax(acc, v) : acc + v;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double w = __shfl_xor_sync(0xffffffffu, acc, o);
+        acc = is_max ? fmax(acc, w) : acc + w;
+      }
+      if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double t = sh[0];
+        for (int w = 1; w < 32; ++w) t = is_max ? fmax(t, sh[w]) : t + sh[w];
+        res[d][k] = t;
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x != 0) return;
+  const double n = a.b, nn = n * n, off = nn - n;
+  const double ce_img_mod = res[0][WR_CE_MOD] / n, ce_img_base = res[0][WR_CE_BASE] / n;
+  const double ce_txt_base = res[1][WR_CE_BASE] / n;
+  const double ce_txt_mod = a.sym ? res[1][WR_CE_MOD] / n : ce_txt_base;
+  const float weighted = static_cast<float>(0.5 * (ce_img_mod + ce_txt_mod));  // loss.py:466
+  a.losses[5] = weighted;
+  a.losses[4] += a.lam_w * weighted;                                           // loss.py:473-477
+  if (!a.dbg) return;
+  float* g = a.dbg;
+  for (int k = 0; k < DBG_N; ++k) g[k] = 0.f;
+  for (int d = 0; d < (a.sym ? 2 : 1); ++d) {
+    const double beta = a.scal[SC_WBETA + d];
+    const double sabs = beta * res[d][WR_SABS], ssq = beta * beta * res[d][WR_SSQ];
+    const double var = (ssq - sabs * sabs / nn) / (nn - 1.0);  // std of |Delta| over all B^2 entries (diag = 0)
+    g[0 + d] = static_cast<float>(res[d][WR_PC] / n);          // pc_err
+    g[2 + d] = static_cast<float>(res[d][WR_DIAG]);            // diag_max
+    g[4 + 3 * d] = static_cast<float>(beta * res[d][WR_MAX]);  // delta max / mean / std
+    g[5 + 3 * d] = static_cast<float>(sabs / nn);
+    g[6 + 3 * d] = static_cast<float>(sqrt(var > 0.0 ? var : 0.0));
+    g[10 + d] = static_cast<float>(res[d][WR_L1] / n);         // l1_prob_shift
+    g[12 + d] = static_cast<float>(res[d][WR_CORR] / n);       // corr_rhat_dprob
+    g[18 + 2 * d] = static_cast<float>(res[d][WR_POS] / off);  // pos_frac, neg_frac
+    g[19 + 2 * d] = 1.f - g[18 + 2 * d];
+    g[22 + d] = static_cast<float>(beta);
+  }
+  g[14] = static_cast<float>(ce_img_base);
+  g[15] = static_cast<float>(ce_txt_base);
+  g[16] = static_cast<float>(ce_img_mod);
+  g[17] = static_cast<float>(ce_txt_mod);
+  g[24] = a.rho;
+  g[25] = a.cc;
+}
+
+template <typename K>
+static int launch_fwd_pair(K kernel, int rbs, int nsplit, cudaStream_t st, const TileMaps& tm, const FwdParams& P);
+template <typename K>
+static int set_smem(K kernel, int bytes);
+
+static void fill_wce(const dsoft_plan* p, FwdParams& P, int dir, float* S, float* part) {
+  memset(&P, 0, sizeof(P));
+  P.nprod = 2;
+  P.bn = 2 * BN;
+  P.a_map[0] = dir == 0 ? 0 : 1;  // CLIP logits: image rows x text columns / text rows x image columns
+  P.b_map[0] = dir == 0 ? 1 : 0;
+  P.a_map[1] = P.b_map[1] = 3;    // DINO cosine (symmetric: r^T = r, loss.py:453)
+  P.kchunks[0] = ceil_div(p->sh.D, BK);
+  P.kchunks[1] = ceil_div(p->sh.Dd, BK);
+  P.row0 = 0;
+  P.b = p->sh.b;
+  P.col0 = 0;
+  P.ncols = p->B;
+  P.ntiles = ceil_div(p->B, 2 * BN);
+  P.tiles_per_split = p->f_wce.tps;
+  P.npart = 2 * p->f_wce.nsplit;
+  P.scal = S + p->st_scal;
+  P.part = part;
+  P.ncolvec = 1;
+  P.colvec[0] = S + p->st_rinv_d;
+  P.wdir = dir;
+  P.wcc = p->sh.c_clip;
+}
+
+// forward of the weighted branch; runs after finalize_fwd_kernel (needs the CLIP row LSEs and the diagonal)
+static int weighted_forward(const dsoft_plan* p, const TileMaps& tm, float* S, float* X, const float* lse_local,
+                            float lam_w, float* losses, float* dbg, cudaStream_t st) {
+  const int b = p->sh.b, rbs = ceil_div(b, BM), ns = p->f_wce.nsplit;
+  int rc;
+  if ((rc = set_smem(dsoft_fwd_kernel<MODE_WCE_STAT, 2>, FWD_SMEM_BYTES))) return rc;
+  if ((rc = set_smem(dsoft_fwd_kernel<MODE_WCE_LSE, 2>, FWD_SMEM_BYTES))) return rc;
+  if ((rc = set_smem(dsoft_fwd_kernel<MODE_WCE_DBG, 2>, FWD_SMEM_BYTES))) return rc;
+  float* part = X + p->sc_wpart;
+  for (int d = 0; d < (p->wsym ? 2 : 1); ++d) {
+    float* ws = S + p->st_wstat + static_cast<size_t>(d) * 4 * p->Bcol;
+    FwdParams P;
+    fill_wce(p, P, d, S, part);
+    P.wrow[0] = lse_local + d * b;
+    P.wrow[1] = ws + WS_C * p->Bcol;
+    P.wrow[2] = ws + WS_LSET * p->Bcol;
+    WceRowsArgs ra;
+    ra.b = b; ra.np = 2 * ns; ra.dir = d; ra.part = part; ra.lse = lse_local + d * b; ra.diag = S + p->st_diag;
+    ra.scal = S + p->st_scal; ra.wstat = ws; ra.Bcol = p->Bcol; ra.wrows = X + p->sc_wrows + static_cast<size_t>(d) * WR_N * b;
+    ra.cc = p->sh.c_clip;
+    const int rg = ceil_div(b, 256);
+    if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_WCE_STAT, 2>, rbs, ns, st, tm, P))) return rc;
+    wce_rows_kernel<0><<<rg, 256, 0, st>>>(ra);
+    wce_median_kernel<<<1, 1024, 0, st>>>(ws + WS_STD * p->Bcol, b, p->sh.rho, p->sh.c_clip, S + p->st_scal, d);
+    if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_WCE_LSE, 2>, rbs, ns, st, tm, P))) return rc;
+    wce_rows_kernel<1><<<rg, 256, 0, st>>>(ra);
+    if (dbg) {
+      if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_WCE_DBG, 2>, rbs, ns, st, tm, P))) return rc;
+      wce_rows_kernel<2><<<rg, 256, 0, st>>>(ra);
+    }
+    CUDA_TRY(cudaGetLastError());
+  }
+  WceFinalArgs fa;
+  fa.b = b; fa.sym = p->wsym; fa.wrows = X + p->sc_wrows; fa.lse = lse_local; fa.diag = S + p->st_diag;
+  fa.scal = S + p->st_scal; fa.rho = p->sh.rho; fa.cc = p->sh.c_clip; fa.lam_w = lam_w; fa.losses = losses; fa.dbg = dbg;
+  wce_final_kernel<<<1, 1024, 0, st>>>(fa);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const float* logit_scale,
                              const float* lambdas, void* state, void* scratch, float* lse_local,
-                             float* losses, void* stream) {
+                             float* losses, float* dbg, void* stream) {
   if (!p || !gathered || !logit_scale || !lambdas || !state || !scratch || !lse_local || !losses)
     return fail(DSOFT_EINVAL, "null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1516,7 +1832,8 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
     ra.mat[0] = g + p->offT; ra.cols[0] = p->sh.D;  ra.out[0] = S + p->st_rinv_t; ra.rmin[0] = S + p->st_scal + SC_RMIN_T;
     ra.mat[1] = g + p->offZ; ra.cols[1] = p->Dz;    ra.out[1] = S + p->st_rinv_z; ra.rmin[1] = S + p->st_scal + SC_RMIN_Z;
     ra.mat[2] = g + p->offD; ra.cols[2] = p->sh.Dd; ra.out[2] = S + p->st_rinv_d; ra.rmin[2] = S + p->st_scal + SC_RMIN_D;
-    rinv_kernel<<<dim3(ceil_div(p->Bcol, 8 * RINV_ROWS_PER_WARP), p->have_soft ? 3 : 1), 256, 0, st>>>(ra);
+    rinv_kernel<<<dim3(ceil_div(p->Bcol, 8 * RINV_ROWS_PER_WARP), (p->have_soft || p->weighted) ? 3 : 1), 256, 0,
+                  st>>>(ra);
     CUDA_TRY(cudaGetLastError());
   }
 
@@ -1596,6 +1913,7 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
   fa.losses = losses;
   finalize_fwd_kernel<<<ceil_div(b, 128), 128, 0, st>>>(fa);
   CUDA_TRY(cudaGetLastError());
+  if (p->weighted) return weighted_forward(p, tm, S, X, lse_local, lambdas[3], losses, dbg, st);
   return 0;
 }
 
@@ -1653,7 +1971,8 @@ static int make_gstore_map(const dsoft_plan* p, CUtensorMap* map, const __half* 
 }
 
 static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* S, float* X, const float* lse_loc,
-                              const float* lsec, const __half* v16, cudaStream_t st) {
+                              const float* lsec, const __half* v16, const float* gout, const float* lambdas,
+                              cudaStream_t st) {
   const float* colfac = S + p->st_colfac;
   const int b = p->sh.b;
   const int rbs = ceil_div(b, BM);
@@ -1734,7 +2053,43 @@ static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* 
         return rc;
     }
   }
-  for (int d = 0; d < (p->clip_tr ? 1 : 2); ++d) {  // d = 0: image rows (dI = G . T), d = 1: text rows (dT = G . I)
+  if (p->weighted) {
+    // world == 1: ONE logit-gradient matrix carries  g_c * classic CE + g_w * weighted CE  of both directions
+    // (loss.py:416-471 backward); the two gradient GEMMs below are the classic ones
+    if ((rc = set_smem(dsoft_fwd_kernel<MODE_WCE_G, 2>, FWD_SMEM_BYTES))) return rc;
+    if ((rc = fk.lane(lane++, &ks))) return rc;
+    fill_wce(p, P, 0, S, nullptr);
+    const float* wi = S + p->st_wstat;
+    const float* wt = wi + static_cast<size_t>(4) * p->Bcol;
+    P.wrow[0] = lse_loc;
+    P.wrow[1] = wi + WS_C * p->Bcol;
+    P.wrow[2] = wi + WS_LSET * p->Bcol;
+    P.wrow[3] = wi + WS_A * p->Bcol;
+    P.ncolvec = 5;
+    P.colvec[1] = lsec + static_cast<size_t>(1) * p->Bcol;  // lse of the text direction, by column
+    P.colvec[2] = wt + WS_LSET * p->Bcol;                   // (only read when weight_text_symmetry)
+    P.colvec[3] = wt + WS_C * p->Bcol;
+    P.colvec[4] = wt + WS_A * p->Bcol;
+    P.wsym = p->wsym;
+    P.wgout = gout;
+    P.wlam[0] = lambdas[0];
+    P.wlam[1] = lambdas[3];
+    P.gout[0] = Gci;
+    P.g_pitch = p->pitch_c;
+    P.npart = 2 * p->f_wce.nsplit;
+    P.ds_part = X + p->sc_ds1;
+    if ((rc = make_gstore_map(p, &tm.g[0], Gci, p->pitch_c))) return rc;
+    tm.g[1] = tm.g[0];
+    {
+      ProfScope ps(PK_BWD_GCLIP, ks);
+      if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_WCE_G, 2>, rbs, p->f_wce.nsplit, ks, tm, P))) return rc;
+    }
+    {
+      ProfScope ps(PK_BWD_CLIP_I, ks);
+      if ((rc = launch_gy(p, Gci, p->pitch_c, v16, p->v_offT, p->sh.D, 0, p->g_clip, X + p->sc_acc1, ks))) return rc;
+    }
+  }
+  for (int d = 0; d < (p->weighted ? 0 : (p->clip_tr ? 1 : 2)); ++d) {  // d = 0: image rows (dI = G . T), d = 1: text rows
     if ((rc = fk.lane(lane++, &ks))) return rc;
     fill_clip_fwd(p, P, d == 0 ? 0 : 1, d == 0 ? 1 : 0, S + p->st_scal, nullptr, nullptr);
     P.lse_row[0] = lse_loc + d * b;
@@ -1761,7 +2116,8 @@ static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* 
   if (p->clip_tr) {
     // world == 1: G_text[j][i] = p_ti[j,i] + p_it[i,j] = G_image[i][j]: dT = G_image^T . I, no second G matrix;
     // the text rows' d(logit_scale) partials were folded into the image rows' (ds_both)
-    CUDA_TRY(cudaMemsetAsync(X + p->sc_ds2, 0, sizeof(float) * 2 * p->f_clip.nsplit * b, ks));
+    CUDA_TRY(cudaMemsetAsync(X + p->sc_ds2, 0,
+                             sizeof(float) * 2 * std::max(p->f_clip.nsplit, p->weighted ? p->f_wce.nsplit : 0) * b, ks));
     ProfScope ps(PK_BWD_CLIP_T, ks);
     if ((rc = launch_gy(p, Gci, p->pitch_c, v16, p->v_offI, p->sh.D, 0, p->g_clip_t, X + p->sc_acc2, ks, true)))
       return rc;
@@ -1775,6 +2131,8 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
   if (!p || !gathered || !state || !scratch || !lse_all || !gout || !lambdas || !d_image || !d_text || !d_scale)
     return fail(DSOFT_EINVAL, "null argument");
   if (p->have_proj && !d_student) return fail(DSOFT_EINVAL, "d_student is null but the plan has Dp > 0");
+  if (p->weighted && !p->gmat)
+    return fail(DSOFT_EINVAL, "the weighted CE branch needs the two-phase backward (DSOFT_F_GMAT)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // state is logically const for the caller; the relayouted LSE columns live in it
   float* S = const_cast<float*>(static_cast<const float*>(state));
@@ -1805,7 +2163,7 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
   };
 
   if (p->gmat) {
-    if ((rc = backward_two_phase(p, gathered, S, X, lse_loc, lsec, v16, st))) return rc;
+    if ((rc = backward_two_phase(p, gathered, S, X, lse_loc, lsec, v16, gout, lambdas, st))) return rc;
   } else {
   if ((rc = set_smem(dsoft_bwd_kernel<MODE_CLIP>, BWD_SMEM_BYTES))) return rc;
   if ((rc = set_smem(dsoft_bwd_kernel<MODE_SOFT>, BWD_SMEM_BYTES))) return rc;
@@ -1932,9 +2290,15 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
   fa.have_proj = p->have_proj;
   fa.row_only = p->row_only;
   fa.sym_scaled = p->gmat && p->clip_tr;
+  fa.weighted = p->weighted;
+  fa.wsym = p->wsym;
+  fa.wstat = S + p->st_wstat;
+  fa.Bcol = p->Bcol;
+  fa.lam_w = lambdas[3];
   fa.ns_c = p->gmat ? p->g_clip.nsplit : p->b_clip.nsplit;
   fa.ns_c2 = (p->gmat && p->clip_tr) ? p->g_clip_t.nsplit : fa.ns_c;
-  fa.nds = p->gmat ? 2 * p->f_clip.nsplit : 2 * p->b_clip.nsplit * chunk_cluster(p->nch_clip);
+  fa.nds = p->gmat ? 2 * (p->weighted ? p->f_wce.nsplit : p->f_clip.nsplit)
+                   : 2 * p->b_clip.nsplit * chunk_cluster(p->nch_clip);
   fa.ns_s = p->gmat ? p->g_stu.nsplit : p->b_stu.nsplit;
   fa.ns_x = p->gmat ? p->g_txt.nsplit : p->b_txt.nsplit;
   fa.gathered = static_cast<const __nv_bfloat16*>(gathered);

@@ -44,6 +44,11 @@ constexpr int MODE_SOFT = 1;
 constexpr int MODE_RAW = 2;  // bring-up: forward stores the raw tile, backward uses G = raw dot products
 constexpr int MODE_CLIP_G = 3;  // forward main loop, epilogue writes the fp16 logit-gradient tile (two-phase bwd)
 constexpr int MODE_SOFT_G = 4;
+// denominator-modulated ("weighted") CE branch, loss.py:416-471 + diagnostics 479-595: CLIP + DINO tiles
+constexpr int MODE_WCE_STAT = 5;
+constexpr int MODE_WCE_LSE = 6;
+constexpr int MODE_WCE_DBG = 7;
+constexpr int MODE_WCE_G = 8;
 
 // scalar block computed on device by prep_scalars_kernel (no host sync on logit_scale)
 enum {
@@ -62,7 +67,9 @@ enum {
   SC_TICKET_B = 13, // (int) same for finalize_bwd_kernel
   SC_C_CLIP = 14,   // reference exponent c of the factorised CLIP logit gradients (lse_prepare_kernel)
   SC_FAST_CLIP = 15,// 1.0: all CLIP log-sum-exps lie within 200 log2 units -> one exponential per pair
-  SC_COUNT = 16
+  SC_WBETA = 16,    // [2] beta = rho * median(row std) / c_clip of the weighted CE, image / text direction
+  SC_WBETA2 = 18,   // [2] beta * log2(e)
+  SC_COUNT = 32
 };
 
 struct TileMaps {
@@ -103,6 +110,15 @@ struct FwdParams {
   int g_pitch;              // columns of G (multiple of 64 >= ncols)
   int row_only;             // clip, exact form: gather_with_grad == False drops the column-side terms
   float* ds_part;           // clip: d(logit_scale) row partials [npart][b]
+  // ---- weighted-CE modes (MODE_WCE_*): world == 1
+  int ncolvec;              // per-column vectors staged per tile: colvec[0 .. ncolvec)
+  const float* colvec[6];   // [0] 1/||dino_j||; G mode: [1] lse_ti, [2] lse~ (text dir), [3] c' (text dir), [4] A'
+  const float* wrow[4];     // per row: [0] lse of the unmodified logits (log2), [1] c_a, [2] lse~ (log2), [3] A_a
+  int wdir;                 // 0: image rows x text columns, 1: text rows x image columns
+  int wsym;                 // weight_text_symmetry (loss.py:449-463)
+  float wcc;                // c_clip
+  const float* wgout;       // G mode: upstream gradients [6] (device)
+  float wlam[2];            // G mode: lambda_original, lambda_weighted
   int tri;                  // soft G, world == 1: the matrices are symmetric -> only the 256-column tiles from the
                             // row pair's own diagonal tile (index rb / 2) onwards are computed and stored, scaled
                             // symmetrically; the gradient GEMM reads the missing part from the transposed blocks
@@ -200,7 +216,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ FwdParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_1024(smem_raw);
-  constexpr bool kSoftMode = (MODE == MODE_SOFT || MODE == MODE_SOFT_G);
+  constexpr bool kWce = (MODE >= MODE_WCE_STAT && MODE <= MODE_WCE_G);
+  // "soft-like": 256-column tiles with several products per tile, staged per-column vectors, setmaxnreg
+  constexpr bool kSoftMode = (MODE == MODE_SOFT || MODE == MODE_SOFT_G || kWce);
   static_assert(!kSoftMode || CG == 2, "the soft modes are written for CTA pairs");
   // streaming mode: stages of (A box | B boxes); resident mode: 8 A boxes, then B-only stages
   const bool resident = P.resident != 0;
@@ -211,13 +229,14 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   const int stage_bytes = (resident ? 0 : TILE_BYTES) + brows * 128;
   // soft modes: 6 stages of 32 KiB (logit-gradient mode: 5); the 32 KiB behind them hold the staged per-column
   // vectors.  Logit-gradient modes keep 32 KiB (at 192 KiB; soft: at 160 KiB) for the G staging strips.
-  constexpr bool kGMode = (MODE == MODE_CLIP_G || MODE == MODE_SOFT_G);
-  const int nstages = MODE == MODE_SOFT_G ? 5 : (kSoftMode ? 6 :
+  constexpr bool kGMode = (MODE == MODE_CLIP_G || MODE == MODE_SOFT_G || MODE == MODE_WCE_G);
+  constexpr bool kSoftG = (MODE == MODE_SOFT_G || MODE == MODE_WCE_G);
+  const int nstages = kSoftG ? 5 : (kSoftMode ? 6 :
                       min(MODE == MODE_CLIP_G ? (resident ? 4 : 6) : 8, (resident ? 6 : 14) * TILE_BYTES / stage_bytes));
   // G staging: one 4 KiB strip (32 rows x 64 columns fp16, 128-byte swizzle) per epilogue warp.  A strip is written
   // with conflict-free 16-byte shared stores and leaves through ONE TMA tensor store; per-thread 32-byte global
   // stores (32 different lines per warp instruction) kept the L1TEX pipe at 78 % and the tensor pipe at 62 %.
-  uint8_t* gstage = smem + (MODE == MODE_SOFT_G ? 5 : 6) * 2 * TILE_BYTES;
+  uint8_t* gstage = smem + (kSoftG ? 5 : 6) * 2 * TILE_BYTES;
   const int nslots = TMEM_COLS / bn;  // 4 x 128 or 2 x 256 columns
   uint8_t* ring = resident ? smem + 8 * TILE_BYTES : smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F_STAGES * 2 * TILE_BYTES + 2 * TILE_BYTES);
@@ -309,14 +328,18 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
         mbar_wait(smem_u32(&col_empty[cb]), ((static_cast<uint32_t>(n / COL_BUFS)) & 1) ^ 1);
         if (elect_one()) {
           const uint32_t full = smem_u32(&col_full[cb]);
-          const int nvec = (MODE == MODE_SOFT_G ? 2 : 1) * P.nprod;
+          const int nvec = kWce ? P.ncolvec : (MODE == MODE_SOFT_G ? 2 : 1) * P.nprod;
           mbar_arrive_expect_tx(full, nvec * CT * 4);
           float* dst = colbuf + cb * COL_VECS * CT;
           const size_t c0 = static_cast<size_t>(P.col0) + static_cast<size_t>(t) * CT;
-          for (int p = 0; p < P.nprod; ++p) {
-            bulk_copy_g2s(smem_u32(dst + p * CT), P.rinv[p] + c0, CT * 4, full);
-            if constexpr (MODE == MODE_SOFT_G)
-              bulk_copy_g2s(smem_u32(dst + (3 + p) * CT), P.colfac[p] + c0, CT * 4, full);
+          if constexpr (kWce) {
+            for (int k = 0; k < P.ncolvec; ++k) bulk_copy_g2s(smem_u32(dst + k * CT), P.colvec[k] + c0, CT * 4, full);
+          } else {
+            for (int p = 0; p < P.nprod; ++p) {
+              bulk_copy_g2s(smem_u32(dst + p * CT), P.rinv[p] + c0, CT * 4, full);
+              if constexpr (MODE == MODE_SOFT_G)
+                bulk_copy_g2s(smem_u32(dst + (3 + p) * CT), P.colfac[p] + c0, CT * 4, full);
+            }
           }
         }
         __syncwarp();
@@ -735,6 +758,235 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
         mbar_arrive(smem_u32(&col_empty[cb]));
       }
       if (lane == 0) bulk_wait_group<0>();  // the stores have landed before the CTA may exit
+    } else if constexpr (kWce) {
+      // ---------------------------------------------------------------- denominator-modulated CE, loss.py:416-471
+      // Products per 256-column tile: [0] CLIP logits x (row operand = image rows, or text rows for the text
+      // direction), [1] DINO cosine -> dissimilarity r = 1 - clamp(cos), r_aa = 0 (loss.py:424-429).  One world-
+      // size-1 problem (the reference's branch is single-rank): global row == local row, col0 == 0.
+      //   STAT : c_a = sum_j p_aj r_aj with p = soft-max of the UNMODIFIED row (loss.py:434-435), and the row sums
+      //          of x and x^2 behind the row std of the logits (loss.py:440-441)
+      //   LSE  : log-sum-exp of x~ = x + beta clamp(r - c_a, +-c_clip) (diagonal unshifted, loss.py:445-447) and
+      //          A_a = sum_{j != a} p~_aj [ |r_aj - c_a| <= c_clip ] (the share of the row that feels d c_a)
+      //   DBG  : the row statistics behind the reference's diagnostics (loss.py:479-595)
+      //   G    : the fp16 logit gradient of  g_c * classic CE  +  g_w * weighted CE  for BOTH directions in one
+      //          matrix (rows = image, columns = text; the text direction's entry is the transposed one and reads
+      //          its row statistics per column):  d CE~_a / d x_ak = p~_ak - delta_ak - beta A_a p_ak (r_ak - c_a)
+      const int lic = min(li, P.b - 1);
+      const float s2 = P.scal[SC_SCALE_L2];
+      const float rda = P.colvec[0][min(gi, P.ncols - 1)];
+      const float cc = P.wcc;
+      const float beta2 = (MODE == MODE_WCE_STAT) ? 0.f : P.scal[SC_WBETA2 + P.wdir];
+      const float lse_a = (MODE == MODE_WCE_LSE) ? 0.f : P.wrow[0][lic];
+      const float c_a = (MODE == MODE_WCE_STAT) ? 0.f : P.wrow[1][lic];
+      const float lset_a = (MODE == MODE_WCE_DBG || MODE == MODE_WCE_G) ? P.wrow[2][lic] : 0.f;
+      const bool real_block = rb * BM < P.b;
+      const bool live_row = li < P.b;
+      float xq[128];  // this thread's 128 CLIP logits (log2 units), kept while the DINO tile arrives
+      // accumulators (meaning per mode, see the stores at the end)
+      float acc[11];
+#pragma unroll
+      for (int k = 0; k < 11; ++k) acc[k] = 0.f;
+      float mrun = M_FLOOR;
+      // G mode: upstream gradients and the text direction's knobs
+      float gcl = 0.f, gwt = 0.f, beta_i = 0.f, beta_t = 0.f, beta2_t = 0.f, aa_a = 0.f;
+      if constexpr (MODE == MODE_WCE_G) {
+        gcl = P.wgout[0] + P.wlam[0] * P.wgout[4];
+        gwt = P.wgout[5] + P.wlam[1] * P.wgout[4];
+        beta_i = P.scal[SC_WBETA + 0];
+        beta_t = P.scal[SC_WBETA + 1];
+        beta2_t = P.scal[SC_WBETA2 + 1];
+        aa_a = P.wrow[3][lic];
+      }
+      int it = 0;
+      for (int t = t0; t < t1; ++t, it += 2) {
+        const int jt0 = t * CT + half * 128;
+        const int cb = (t - t0) % COL_BUFS;
+        mbar_wait(smem_u32(&col_full[cb]), static_cast<uint32_t>((t - t0) / COL_BUFS) & 1);
+        const float* cv = colbuf + cb * COL_VECS * CT + half * 128;
+        {  // ---- CLIP tile -> xq
+          const int slot = it % 2;
+          mbar_wait(smem_u32(&s_full[slot]), static_cast<uint32_t>(it / 2) & 1);
+          tc_fence_after();
+          uint32_t rA[32], rB[32];
+          tmem_ld32_nowait(lane_addr + slot * CT + half * 128, rA);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t(&rcur)[32] = (c & 1) ? rB : rA;
+            uint32_t(&rnxt)[32] = (c & 1) ? rA : rB;
+            tmem_ld_wait(rcur);
+            if (c < 3) {
+              tmem_ld32_nowait(lane_addr + slot * CT + half * 128 + (c + 1) * 32, rnxt);
+            } else {
+              tc_fence_before();
+              release_slot(slot);
+            }
+#pragma unroll
+            for (int e = 0; e < 32; ++e) xq[c * 32 + e] = __uint_as_float(rcur[e]) * s2;
+          }
+        }
+        {  // ---- DINO tile -> r, then the mode's arithmetic per 32-column chunk
+          const int slot = (it + 1) % 2;
+          mbar_wait(smem_u32(&s_full[slot]), static_cast<uint32_t>((it + 1) / 2) & 1);
+          tc_fence_after();
+          uint32_t rA[32], rB[32];
+          tmem_ld32_nowait(lane_addr + slot * CT + half * 128, rA);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int jrel0 = jt0 + c * 32;
+            uint32_t(&rcur)[32] = (c & 1) ? rB : rA;
+            uint32_t(&rnxt)[32] = (c & 1) ? rA : rB;
+            tmem_ld_wait(rcur);
+            if (c < 3) {
+              tmem_ld32_nowait(lane_addr + slot * CT + half * 128 + (c + 1) * 32, rnxt);
+            } else {
+              tc_fence_before();
+              release_slot(slot);
+            }
+            const bool has_diag = gw0 < jrel0 + 32 && jrel0 < gw0 + 32;  // warp-uniform
+            const bool ragged = jrel0 + 32 > P.ncols;
+            const float4* rc = reinterpret_cast<const float4*>(cv + 0 * CT + c * 32);
+            float r[32];
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const float4 q4 = rc[e4];
+              const float rr[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int e = 4 * e4 + k;
+                const float cosv = __uint_as_float(rcur[e]) * rda * rr[k];
+                r[e] = 1.f - fminf(fmaxf(cosv, -1.f), 1.f);
+              }
+            }
+            if (has_diag) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e)
+                if (jrel0 + e == gi) r[e] = 0.f;
+            }
+            if constexpr (MODE == MODE_WCE_STAT) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                const float x = xq[c * 32 + e];
+                const bool live = !ragged || jrel0 + e < P.ncols;
+                const float p = live ? fast_exp2(x - lse_a) : 0.f;
+                acc[0] = fmaf(p, r[e], acc[0]);
+                acc[1 + (e & 1)] += live ? x : 0.f;          // two partial sums each: shorter dependency chains
+                acc[3 + (e & 1)] = fmaf(live ? x : 0.f, x, acc[3 + (e & 1)]);
+              }
+            } else if constexpr (MODE == MODE_WCE_LSE) {
+              float xt[32];
+              float cm = NEG_BIG;
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                const float z = r[e] - c_a;
+                const bool dg = has_diag && jrel0 + e == gi;
+                float x = xq[c * 32 + e] + (dg ? 0.f : beta2 * fminf(fmaxf(z, -cc), cc));
+                if (ragged && jrel0 + e >= P.ncols) x = NEG_BIG;
+                xt[e] = x;
+                cm = fmaxf(cm, x);
+              }
+              const float mnew = fmaxf(mrun, cm);
+              const float alpha = fast_exp2(mrun - mnew);
+              mrun = mnew;
+              float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                const float ex = fast_exp2(xt[e] - mnew);
+                const bool ind = fabsf(r[e] - c_a) <= cc && !(has_diag && jrel0 + e == gi);
+                s0 += ex;
+                s1 += ind ? ex : 0.f;
+              }
+              acc[0] = fmaf(acc[0], alpha, s0);
+              acc[1] = fmaf(acc[1], alpha, s1);
+            } else if constexpr (MODE == MODE_WCE_DBG) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                const bool dg = has_diag && jrel0 + e == gi;
+                const bool live = !ragged || jrel0 + e < P.ncols;
+                const float x = xq[c * 32 + e];
+                const float rh = fminf(fmaxf(r[e] - c_a, -cc), cc);
+                const float xm = x + (dg ? 0.f : beta2 * rh);
+                const float p = live ? fast_exp2(x - lse_a) : 0.f;
+                const float pt = live ? fast_exp2(xm - lset_a) : 0.f;
+                const float dp = pt - p;
+                const float rl = live ? rh : 0.f;
+                const float ro = dg ? 0.f : rl;  // off-diagonal share
+                acc[0] = fmaf(p, rl, acc[0]);       // sum p r^        (pc_err)
+                acc[1] += fabsf(dp);                // sum |dp|        (l1 shift)
+                acc[2] += rl;                       // sum r^
+                acc[3] = fmaf(rl, rl, acc[3]);      // sum r^^2
+                acc[4] += dp;                       // sum dp
+                acc[5] = fmaf(dp, dp, acc[5]);      // sum dp^2
+                acc[6] = fmaf(rl, dp, acc[6]);      // sum r^ dp
+                acc[7] += fabsf(ro);                // sum |r^| off-diagonal (delta mean)
+                acc[8] = fmaf(ro, ro, acc[8]);      // sum r^^2 off-diagonal (delta std)
+                acc[9] = fmaxf(acc[9], fabsf(ro));  // max |r^| off-diagonal (delta max)
+                acc[10] += (ro > 0.f) ? 1.f : 0.f;  // count r^ > 0 off-diagonal
+              }
+            } else {  // MODE_WCE_G
+              const float4* l1c = reinterpret_cast<const float4*>(cv + 1 * CT + c * 32);  // lse_ti by column
+              const float4* l2c = reinterpret_cast<const float4*>(cv + 2 * CT + c * 32);  // lse~ (text dir)
+              const float4* ccc = reinterpret_cast<const float4*>(cv + 3 * CT + c * 32);  // c' (text dir)
+              const float4* aac = reinterpret_cast<const float4*>(cv + 4 * CT + c * 32);  // A' (text dir)
+              const bool need_mask = has_diag || ragged || !real_block || rb * BM + q * 32 + 32 > P.b;
+              uint32_t w16[16];
+#pragma unroll
+              for (int e4 = 0; e4 < 8; ++e4) {
+                const float4 a4 = l1c[e4], b4 = l2c[e4], c4 = ccc[e4], d4 = aac[e4];
+                const float lti[4] = {a4.x, a4.y, a4.z, a4.w}, ltt[4] = {b4.x, b4.y, b4.z, b4.w};
+                const float cj[4] = {c4.x, c4.y, c4.z, c4.w}, aj[4] = {d4.x, d4.y, d4.z, d4.w};
+                float g4[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const int e = 4 * e4 + k;
+                  const float x = xq[c * 32 + e];
+                  const float za = r[e] - c_a;
+                  const float e1 = fast_exp2(x - lse_a);
+                  const float pt = fast_exp2(fmaf(beta2, fminf(fmaxf(za, -cc), cc), x) - lset_a);
+                  const float gimg = pt - beta_i * aa_a * e1 * za;
+                  const float e2 = fast_exp2(x - lti[k]);
+                  float gtxt = e2;
+                  if (P.wsym) {
+                    const float zj = r[e] - cj[k];
+                    const float ptj = fast_exp2(fmaf(beta2_t, fminf(fmaxf(zj, -cc), cc), x) - ltt[k]);
+                    gtxt = ptj - beta_t * aj[k] * e2 * zj;
+                  }
+                  float g = gcl * (e1 + e2) + gwt * (gimg + gtxt);
+                  if (need_mask && ((jrel0 + e == gi) || (jrel0 + e >= P.ncols) || !live_row)) g = 0.f;
+                  acc[0] = fmaf(g, x, acc[0]);  // d(logit_scale) row term in log2 units of x (off-diagonal part)
+                  g4[k] = g;
+                }
+                w16[2 * e4 + 0] = pack_f16x2(g4[0], g4[1]);
+                w16[2 * e4 + 1] = pack_f16x2(g4[2], g4[3]);
+              }
+              if (real_block && jrel0 + 32 <= P.g_pitch) {
+                if ((c & 1) == 0) stage_begin();
+                stage_put32(w16, c & 1);
+                if (c & 1) stage_store(&maps.g[0], (rb * (P.g_pitch >> 6) + (jrel0 >> 6)) * BM + q * 32);
+              }
+            }
+          }
+        }
+        mbar_arrive(smem_u32(&col_empty[cb]));
+      }
+      if constexpr (MODE == MODE_WCE_G) {
+        if (lane == 0) bulk_wait_group<0>();
+        if (li < P.b) P.ds_part[sp * P.b + li] = acc[0] / s2;  // back to raw dot-product units
+      } else if (li < P.b) {
+        const int o = sp * P.b + li;
+        const int st = P.npart * P.b;
+        if constexpr (MODE == MODE_WCE_STAT) {
+          P.part[0 * st + o] = acc[0];
+          P.part[1 * st + o] = acc[1] + acc[2];
+          P.part[2 * st + o] = acc[3] + acc[4];
+        } else if constexpr (MODE == MODE_WCE_LSE) {
+          P.part[0 * st + o] = mrun;
+          P.part[1 * st + o] = acc[0];
+          P.part[2 * st + o] = acc[1];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 11; ++k) P.part[k * st + o] = acc[k];
+        }
+      }
     } else {
       const float cq = P.rinv[0][gi] * P.scal[SC_ITT_L2];
       const float cp = P.rinv[1][gi] * P.scal[SC_ITS_L2];

@@ -18,8 +18,8 @@ Differences from the reference that are deliberate and documented in DESIGN.md:
     is rounded with a straight-through gradient); all soft-max / KL arithmetic is fp32;
   * at world_size > 1 the soft terms default to the *global* row block (``soft_scope="global"``);
     ``soft_scope="local"`` reproduces the reference's local b x b block;
-  * the weighted-CE branch (loss.py:416-471, lambda_weighted > 0; one rank only, off by default) runs as
-    fp32 PyTorch tensor ops next to the fused terms (fused kernels for it are the next step);
+  * the weighted-CE branch (loss.py:416-471, lambda_weighted > 0; one rank only, off by default) runs in the
+    same fused kernels (fp32 logits also under autocast, beta kept on the device instead of `.item()`);
   * Horovod is not supported (``use_horovod=True`` raises).
 """
 from __future__ import annotations
@@ -174,12 +174,13 @@ class CudaBackend:
     def _lam(lambdas):
         import ctypes as C
 
-        return (C.c_float * 3)(*[float(x) for x in lambdas])
+        return (C.c_float * 4)(*[float(x) for x in lambdas])
 
-    def forward(self, plan, gathered, logit_scale, lambdas, state, scratch, lse_local, losses):
+    def forward(self, plan, gathered, logit_scale, lambdas, state, scratch, lse_local, losses, dbg=None):
         _cabi.check(
             self._lib.dsoft_forward(plan.handle, _ptr(gathered), _ptr(logit_scale), self._lam(lambdas), _ptr(state),
-                                    _ptr(scratch), _ptr(lse_local), _ptr(losses), self._stream(gathered)),
+                                    _ptr(scratch), _ptr(lse_local), _ptr(losses), _ptr(dbg),
+                                    self._stream(gathered)),
             "dsoft_forward",
         )
 
@@ -247,13 +248,15 @@ def _gmat_fits_now(b, W, soft, text, soft_local, dev) -> bool:
 
 
 class _FnConfig:
-    __slots__ = ("backend", "world", "rank", "group", "flags", "teacher_temp", "text_temp", "lambdas")
+    __slots__ = ("backend", "world", "rank", "group", "flags", "teacher_temp", "text_temp", "lambdas", "rho",
+                 "c_clip")
 
 
 class _DinoSoftFn(torch.autograd.Function):
     """(image, text, logit_scale, student_raw, dino) ->
-    [classic_loss, soft_imgimg, soft_texttext, soft_loss, total_loss]  (loss composition loss.py:397, 473-477 is
-    done by the finalize kernel: ~12 tiny PyTorch kernels fewer per step)."""
+    [classic_loss, soft_imgimg, soft_texttext, soft_loss, total_loss, weighted_loss], dbg  (loss composition
+    loss.py:397, 466, 473-477 is done by the finalize kernels: ~12 tiny PyTorch kernels fewer per step; dbg is the
+    non-differentiable diagnostics array of the weighted branch, or an empty tensor)."""
 
     @staticmethod
     def forward(ctx, image, text, logit_scale, student, dino, cfg: _FnConfig):
@@ -262,23 +265,26 @@ class _DinoSoftFn(torch.autograd.Function):
         b, D = image.shape
         W, r = cfg.world, cfg.rank
         soft = bool(cfg.flags & _cabi.DSOFT_F_SOFT)
+        weighted = bool(cfg.flags & _cabi.DSOFT_F_WEIGHTED)
+        use_dino = soft or weighted
         needs_grad = any(ctx.needs_input_grad[:4])
         flags = cfg.flags
-        if needs_grad and _gmat_fits(b, W, soft, bool(flags & _cabi.DSOFT_F_TEXT),
-                                     bool(flags & _cabi.DSOFT_F_SOFT_LOCAL), dev):
+        # the weighted branch's backward exists in the two-phase form only
+        if needs_grad and (weighted or _gmat_fits(b, W, soft, bool(flags & _cabi.DSOFT_F_TEXT),
+                                                  bool(flags & _cabi.DSOFT_F_SOFT_LOCAL), dev)):
             flags |= _cabi.DSOFT_F_GMAT
         shape = _cabi.Shape(
             b=b, world=W, rank=r, D=D,
             Dp=(student.shape[1] if (student is not None and soft) else 0),
-            Dd=(dino.shape[1] if (dino is not None and soft) else 0),
-            flags=flags, teacher_temp=cfg.teacher_temp, text_temp=cfg.text_temp,
+            Dd=(dino.shape[1] if (dino is not None and use_dino) else 0),
+            flags=flags, teacher_temp=cfg.teacher_temp, text_temp=cfg.text_temp, rho=cfg.rho, c_clip=cfg.c_clip,
         )
         plan = be.plan(shape, dev) if dev.type == "cuda" else be.plan(shape)
         gathered = torch.empty((b * W, plan.row_elems), dtype=torch.bfloat16, device=dev)
         lazy_dino = isinstance(dino, DinoRows)
         be.pack(plan, image.detach(), text.detach(), None if student is None or not soft else student.detach(),
-                None if (dino is None or not soft or lazy_dino) else dino.detach(), gathered)
-        if lazy_dino and soft:
+                None if (dino is None or not use_dino or lazy_dino) else dino.detach(), gathered)
+        if lazy_dino and use_dino:
             # device feature store: the rows are gathered by index straight into the DINO columns of the packed
             # buffer (range check on the device), replacing train.py:250-280's CPU gather + H2D copy
             dino.store.gather_into_packed(dino, gathered, r * b, plan.dino_col)
@@ -288,9 +294,10 @@ class _DinoSoftFn(torch.autograd.Function):
         state = torch.empty(plan.state_numel, dtype=torch.float32, device=dev)
         scratch = torch.empty(plan.fwd_scratch_numel, dtype=torch.float32, device=dev)
         lse_all = torch.empty((W, 5, b), dtype=torch.float32, device=dev)
-        losses = torch.empty(5, dtype=torch.float32, device=dev)
+        losses = torch.empty(6, dtype=torch.float32, device=dev)
+        dbg = torch.empty(_cabi.DBG_N if weighted else 0, dtype=torch.float32, device=dev)
         ls = logit_scale.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
-        be.forward(plan, gathered, ls, cfg.lambdas, state, scratch, lse_all[r], losses)
+        be.forward(plan, gathered, ls, cfg.lambdas, state, scratch, lse_all[r], losses, dbg if weighted else None)
         if W > 1 and needs_grad:
             # column-side soft-max statistics of the other ranks' rows (5 floats per sample)
             dist.all_gather_into_tensor(lse_all.view(-1), lse_all[r].view(-1), group=cfg.group)
@@ -298,11 +305,12 @@ class _DinoSoftFn(torch.autograd.Function):
         ctx.plan, ctx.cfg = plan, cfg
         ctx.meta = (image.dtype, text.dtype, logit_scale.dtype, logit_scale.shape,
                     None if student is None else student.dtype, b, D, shape.Dp)
-        return losses
+        ctx.mark_non_differentiable(dbg)
+        return losses, dbg
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, gout):
+    def backward(ctx, gout, _gdbg=None):
         gathered, state, lse_all = ctx.saved_tensors
         plan, be = ctx.plan, ctx.cfg.backend
         idt, tdt, sdt, sshape, zdt, b, D, Dp = ctx.meta
@@ -318,13 +326,13 @@ class _DinoSoftFn(torch.autograd.Function):
             # the fp16 logit-gradient matrices fitted when this shape was first seen but do not now: the saved
             # forward state does not depend on the backward implementation, so run the fused backward instead
             s = plan.shape
-            if not (s.flags & _cabi.DSOFT_F_GMAT):
+            if not (s.flags & _cabi.DSOFT_F_GMAT) or (s.flags & _cabi.DSOFT_F_WEIGHTED):
                 raise
             for key in [k for k in _gmat_decisions if k[0] == s.b and k[1] == s.world]:
                 _gmat_decisions[key] = False
             plan = be.plan(_cabi.Shape(b=s.b, world=s.world, rank=s.rank, D=s.D, Dp=s.Dp, Dd=s.Dd,
                                        flags=s.flags & ~_cabi.DSOFT_F_GMAT, teacher_temp=s.teacher_temp,
-                                       text_temp=s.text_temp), dev)
+                                       text_temp=s.text_temp, rho=s.rho, c_clip=s.c_clip), dev)
             scratch = torch.empty(plan.scratch_numel, dtype=torch.float32, device=dev)
         be.backward(plan, gathered, state, scratch, lse_all, gout, ctx.cfg.lambdas, d_image, d_text, d_student, d_scale)
         g_student = None
@@ -336,86 +344,20 @@ class _DinoSoftFn(torch.autograd.Function):
 # --------------------------------------------------------------------------------------------------
 # denominator-modulated ("weighted") CE branch, loss.py:416-471 + diagnostics loss.py:479-595
 # --------------------------------------------------------------------------------------------------
-# Optional (lambda_weighted defaults to 0), single-rank only in the reference, and next in line for fused
-# kernels.  Until then it runs as plain fp32 PyTorch tensor ops on the inputs' device
-# (cuBLAS + element-wise kernels, [B, B] intermediates like the reference) next to the fused classic / soft
-# terms; autograd provides its backward.  Differences from the reference: fp32 logits also under autocast, and
-# beta stays a detached device scalar instead of `.item()` (no host synchronisation; same value).
-def _shift_logits(logits: torch.Tensor, dissim: torch.Tensor, rho: float, c_clip: float):
-    """logits + beta * clamp(r - E_p[r]) with a zero diagonal; p = soft-max of the UNMODIFIED rows (carries
-    gradient), beta = rho * median(row std) / c_clip (no gradient)."""
-    p_rows = torch.softmax(logits, dim=1)
-    r_hat = (dissim - (p_rows * dissim).sum(dim=1, keepdim=True)).clamp(min=-c_clip, max=c_clip)
-    with torch.no_grad():
-        beta = rho * torch.median(logits.float().std(dim=1)).clamp(min=1e-6) / c_clip
-    delta = (beta * r_hat).clone()
-    delta.diagonal().zero_()
-    return logits + delta, delta, r_hat, p_rows, beta
-
-
-def _row_corr_mean(a: torch.Tensor, b: torch.Tensor, eps: float = 1e-9) -> torch.Tensor:
-    a = a - a.mean(dim=1, keepdim=True)
-    b = b - b.mean(dim=1, keepdim=True)
-    den = a.pow(2).sum(dim=1).sqrt() * b.pow(2).sum(dim=1).sqrt() + eps
-    return ((a * b).sum(dim=1) / den).mean()
-
-
-def _weighted_ce_branch(image_features, text_features, logit_scale, dino_features, rho, c_clip, text_sym):
-    """Returns (weighted_loss, dbg).  dbg holds the reference's diagnostic keys as 0-dim tensors (formatting
-    one of them, as train.py:360-364 does every 300 steps, is what synchronises)."""
-    B = image_features.shape[0]
-    img, txt = image_features.float(), text_features.float()
-    logits_i = logit_scale.float() * (img @ txt.T)
-    logits_t = logits_i.T  # one rank: logits_per_text is the exact transpose (loss.py:272-273)
-    labels = torch.arange(B, device=img.device)
-    with torch.no_grad():
-        dn = F.normalize(dino_features.float(), dim=-1)
-        dissim = 1.0 - (dn @ dn.T).clamp(-1, 1)
-        dissim.diagonal().zero_()
-    tilde_i, delta_i, rhat_i, p_i, beta_i = _shift_logits(logits_i, dissim, rho, c_clip)
-    if text_sym:
-        tilde_t, delta_t, rhat_t, p_t, beta_t = _shift_logits(logits_t, dissim.T, rho, c_clip)
-    else:
-        tilde_t, delta_t, rhat_t, p_t, beta_t = logits_t, None, None, None, None
-    ce_i = F.cross_entropy(tilde_i, labels)
-    ce_t = F.cross_entropy(tilde_t, labels)
-    loss = 0.5 * (ce_i + ce_t)
-
-    with torch.no_grad():
-        zero = torch.zeros((), device=img.device)
-        off = float(B * B - B)
-
-        def side(delta, r_hat, p_base, tilde):
-            if delta is None:
-                return dict(pc=zero, dmax=zero, dmean=zero, dstd=zero, diag=zero, corr=zero, pos=zero)
-            p_mod = torch.softmax(tilde, dim=1)
-            d_abs = delta.abs()
-            pos = ((r_hat > 0).float().sum() - (r_hat.diagonal() > 0).float().sum()) / off
-            return dict(pc=(p_base * r_hat).sum(dim=1).abs().mean(), dmax=d_abs.max(), dmean=d_abs.mean(),
-                        dstd=d_abs.std(), diag=r_hat.diagonal().abs().max(),
-                        corr=_row_corr_mean(r_hat, p_mod - p_base), pos=pos)
-
-        si = side(delta_i, rhat_i, p_i.detach(), tilde_i.detach())
-        st = side(delta_t, None if rhat_t is None else rhat_t, None if p_t is None else p_t.detach(),
-                  tilde_t.detach())
-        p_t_base = torch.softmax(logits_t.detach(), dim=1)
-        dbg = {
-            "pc_err_img": si["pc"], "pc_err_txt": st["pc"],
-            "diag_max_img": si["diag"], "diag_max_txt": st["diag"],
-            "delta_img_max": si["dmax"], "delta_img_mean": si["dmean"], "delta_img_std": si["dstd"],
-            "delta_txt_max": st["dmax"], "delta_txt_mean": st["dmean"], "delta_txt_std": st["dstd"],
-            "l1_prob_shift_img": (torch.softmax(tilde_i.detach(), dim=1) - p_i.detach()).abs().sum(dim=1).mean(),
-            "l1_prob_shift_txt": (torch.softmax(tilde_t.detach(), dim=1) - p_t_base).abs().sum(dim=1).mean(),
-            "corr_rhat_dprob_img": si["corr"], "corr_rhat_dprob_txt": st["corr"],
-            "ce_img_base": F.cross_entropy(logits_i.detach(), labels),
-            "ce_txt_base": F.cross_entropy(logits_t.detach(), labels),
-            "ce_img_mod": ce_i.detach(), "ce_txt_mod": ce_t.detach(),
-            "pos_frac_img": si["pos"], "neg_frac_img": 1.0 - si["pos"],
-            "pos_frac_txt": st["pos"], "neg_frac_txt": (1.0 - st["pos"]) if text_sym else zero,
-            "beta_img": beta_i, "beta_txt": beta_t if text_sym else zero,
-            "rho": rho, "clip_c": c_clip,
-        }
-    return loss, dbg
+# Runs inside libdsoft.so (DSOFT_F_WEIGHTED): three tile passes per direction over the CLIP and DINO Gram tiles
+# (row statistics c_a = sum_j p r and the row std of the logits -> device-side median -> beta; log-sum-exp of the
+# shifted logits; diagnostics) and one logit-gradient pass in the backward.  Nothing of size B x B is stored and beta
+# never visits the host (the reference calls `.item()` twice per step).  Single-rank only, like the reference.
+DBG_KEYS = (  # index into the dbg array of dsoft_forward (include/dsoft.h)
+    ("pc_err_img", 0), ("pc_err_txt", 1), ("diag_max_img", 2), ("diag_max_txt", 3),
+    ("delta_img_max", 4), ("delta_img_mean", 5), ("delta_img_std", 6),
+    ("delta_txt_max", 7), ("delta_txt_mean", 8), ("delta_txt_std", 9),
+    ("l1_prob_shift_img", 10), ("l1_prob_shift_txt", 11),
+    ("corr_rhat_dprob_img", 12), ("corr_rhat_dprob_txt", 13),
+    ("ce_img_base", 14), ("ce_txt_base", 15), ("ce_img_mod", 16), ("ce_txt_mod", 17),
+    ("pos_frac_img", 18), ("neg_frac_img", 19), ("pos_frac_txt", 20), ("neg_frac_txt", 21),
+    ("beta_img", 22), ("beta_txt", 23),
+)
 
 
 def _normalize_out_dtype(x: torch.Tensor) -> torch.dtype:
@@ -595,6 +537,10 @@ class ClipLossWithDINOEnhancements(nn.Module):
                 flags |= _cabi.DSOFT_F_SOFT_LOCAL
         if self.world_size > 1 and not self.gather_with_grad:
             flags |= _cabi.DSOFT_F_ROW_ONLY
+        if weighted_on:
+            flags |= _cabi.DSOFT_F_WEIGHTED
+            if bool(g(args, "weight_text_symmetry", False)):
+                flags |= _cabi.DSOFT_F_WSYM
 
         lambda_original = float(g(args, "lambda_original", 1.0))
         text_lambda = float(g(args, "text_lambda", 0.2)) if text_on else 0.0
@@ -602,23 +548,23 @@ class ClipLossWithDINOEnhancements(nn.Module):
         cfg.backend = self._backend if self._backend is not None else _default_backend(device)
         cfg.world, cfg.rank, cfg.group = self.world_size, self.rank, self.process_group
         cfg.flags, cfg.teacher_temp, cfg.text_temp = flags, teacher_temp, text_temp
-        cfg.lambdas = (lambda_original, lambda_soft if soft_on else 0.0, text_lambda)
+        cfg.lambdas = (lambda_original, lambda_soft if soft_on else 0.0, text_lambda,
+                       lambda_weighted if weighted_on else 0.0)
+        cfg.rho, cfg.c_clip = float(g(args, "rho", 0.1)), float(g(args, "c_clip", 1.0))
 
-        terms = _DinoSoftFn.apply(
-            image_features, text_features, logit_scale, student, dino_features if soft_on else None, cfg
+        terms, dbg_arr = _DinoSoftFn.apply(
+            image_features, text_features, logit_scale, student,
+            dino_features if (soft_on or weighted_on) else None, cfg
         )
         classic_loss = terms[0]
         soft_loss = terms[3] if soft_on else torch.zeros((), device=device)
-        weighted_loss = torch.zeros((), device=device, dtype=classic_loss.dtype)
-        total_loss = terms[4]
+        weighted_loss = terms[5] if weighted_on else torch.zeros((), device=device, dtype=classic_loss.dtype)
+        total_loss = terms[4]  # loss.py:473-477, composed on the device
         dbg = {}
         if weighted_on:
-            if isinstance(dino_features, DinoRows):
-                dino_features = dino_features.materialize()
-            weighted_loss, dbg = _weighted_ce_branch(
-                image_features, text_features, logit_scale, dino_features, float(g(args, "rho", 0.1)),
-                float(g(args, "c_clip", 1.0)), bool(g(args, "weight_text_symmetry", False)))
-            total_loss = total_loss + lambda_weighted * weighted_loss  # loss.py:473-477
+            # 0-dim views of the device array: formatting one (train.py:360-364, every 300 steps) is what syncs
+            dbg = {k: dbg_arr[i] for k, i in DBG_KEYS}
+            dbg["rho"], dbg["clip_c"] = cfg.rho, cfg.c_clip
         if output_dict:
             return {
                 "total_loss": total_loss,

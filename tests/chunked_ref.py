@@ -158,3 +158,47 @@ def chunked_reference(img, txt, dino, scale, head=None, blocks=(), lambdas=(1.0,
         out["blocks"].append(dict(row0=b0, rows=nb, d_image=im.grad.detach(), d_text=tx.grad.detach(),
                                   d_student=None if hp is None else st.grad.detach()))
     return out
+
+
+def chunked_weighted_loss(img, txt, dino, scale, rho, c_clip, sym, slab=2048):
+    """Row-blocked fp64 evaluation of the denominator-modulated CE (loss.py:416-471), forward only:
+    0.5 * (CE(L_it + Delta_it) + CE(L_ti [+ Delta_ti]))."""
+    dt = torch.float64
+    dev = img.device
+    I, T = img.to(dt), txt.to(dt)
+    Dn = _norm(dino.to(dt))
+    s = float(scale)
+    B = I.shape[0]
+    diag = s * (I * T).sum(-1)
+
+    def one_direction(R, C, modulate):
+        lse = torch.empty(B, dtype=dt, device=dev)
+        cst = torch.empty(B, dtype=dt, device=dev)
+        std = torch.empty(B, dtype=dt, device=dev)
+        for r0 in range(0, B, slab):
+            r1 = min(r0 + slab, B)
+            idx = torch.arange(r0, r1, device=dev)
+            L = s * (R[r0:r1] @ C.T)
+            lse[r0:r1] = torch.logsumexp(L, dim=1)
+            if modulate:
+                r = 1.0 - (Dn[r0:r1] @ Dn.T).clamp(-1, 1)
+                r[idx - r0, idx] = 0.0
+                cst[r0:r1] = (torch.softmax(L, dim=1) * r).sum(1)
+                std[r0:r1] = L.std(dim=1)
+        if not modulate:
+            return (lse - diag).mean()
+        beta = rho * torch.median(std).clamp(min=1e-6) / c_clip
+        ce = torch.zeros((), dtype=dt, device=dev)
+        for r0 in range(0, B, slab):
+            r1 = min(r0 + slab, B)
+            idx = torch.arange(r0, r1, device=dev)
+            L = s * (R[r0:r1] @ C.T)
+            r = 1.0 - (Dn[r0:r1] @ Dn.T).clamp(-1, 1)
+            r[idx - r0, idx] = 0.0
+            delta = beta * (r - cst[r0:r1, None]).clamp(-c_clip, c_clip)
+            delta[idx - r0, idx] = 0.0
+            ce += (torch.logsumexp(L + delta, dim=1) - diag[r0:r1]).sum()
+        return ce / B
+
+    with torch.no_grad():
+        return float(0.5 * (one_direction(I, T, True) + one_direction(T, I, bool(sym))))

@@ -6,7 +6,15 @@ product never selects it: `ClipLossWithDINOEnhancements` resolves its backend to
 and raises on non-CUDA tensors; tests inject this object through the private `_backend` attribute."""
 import torch
 
+from weighted_ref import weighted_ce_branch
+
 F_SOFT, F_TEXT, F_SOFT_LOCAL, F_ROW_ONLY = 1, 2, 4, 8
+F_WEIGHTED, F_WSYM = 32, 64
+DBG_ORDER = ("pc_err_img", "pc_err_txt", "diag_max_img", "diag_max_txt", "delta_img_max", "delta_img_mean",
+             "delta_img_std", "delta_txt_max", "delta_txt_mean", "delta_txt_std", "l1_prob_shift_img",
+             "l1_prob_shift_txt", "corr_rhat_dprob_img", "corr_rhat_dprob_txt", "ce_img_base", "ce_txt_base",
+             "ce_img_mod", "ce_txt_mod", "pos_frac_img", "neg_frac_img", "pos_frac_txt", "neg_frac_txt", "beta_img",
+             "beta_txt")
 
 
 class _Plan:
@@ -24,11 +32,13 @@ class OracleBackend:
         p = _Plan()
         p.shape = shape
         p.soft = bool(shape.flags & F_SOFT)
+        p.weighted = bool(shape.flags & F_WEIGHTED)
         p.proj = p.soft and shape.Dp > 0
         p.offI, p.offT = 0, shape.D
         p.offZ = 2 * shape.D if p.proj else 0
         p.offD = 2 * shape.D + (shape.Dp if p.proj else 0)
-        p.row_elems = p.offD + (shape.Dd if p.soft else 0)
+        p.row_elems = p.offD + (shape.Dd if (p.soft or p.weighted) else 0)
+        p.dino_col = p.offD
         p.state_numel = 8
         p.scratch_numel = 8
         p.fwd_scratch_numel = 8
@@ -42,7 +52,7 @@ class OracleBackend:
         gathered[rows, plan.offT:plan.offT + s.D] = text.to(torch.bfloat16)
         if plan.proj:
             gathered[rows, plan.offZ:plan.offZ + s.Dp] = student.to(torch.bfloat16)
-        if plan.soft:
+        if plan.soft or plan.weighted:
             gathered[rows, plan.offD:plan.offD + s.Dd] = dino.to(torch.bfloat16)
         self.calls.append("pack")
 
@@ -52,7 +62,7 @@ class OracleBackend:
         img = g[:, plan.offI:plan.offI + s.D]
         txt = g[:, plan.offT:plan.offT + s.D]
         stu = g[:, plan.offZ:plan.offZ + s.Dp] if plan.proj else None
-        dino = g[:, plan.offD:plan.offD + s.Dd] if plan.soft else None
+        dino = g[:, plan.offD:plan.offD + s.Dd] if (plan.soft or plan.weighted) else None
         return img, txt, stu, dino
 
     def _cfg(self, plan):
@@ -64,14 +74,27 @@ class OracleBackend:
             world_size=s.world, local_loss=True, gather_with_grad=not (s.flags & F_ROW_ONLY),
             soft_scope="local" if (s.flags & F_SOFT_LOCAL) else "global")
 
-    def forward(self, plan, gathered, logit_scale, lambdas, state, scratch, lse_local, losses):
+    def _weighted(self, plan, img, txt, scale, dino):
+        s = plan.shape
+        return weighted_ce_branch(img, txt, scale, dino, float(s.rho), float(s.c_clip), bool(s.flags & F_WSYM))
+
+    def forward(self, plan, gathered, logit_scale, lambdas, state, scratch, lse_local, losses, dbg=None):
         img, txt, stu, dino = self._decode(plan, gathered)
-        out = self.oracle.rank_loss(img, txt, logit_scale.double()[0], dino, stu, self._cfg(plan), rank=plan.shape.rank)
-        lo, ls, tl = lambdas
+        out = self.oracle.rank_loss(img, txt, logit_scale.double()[0], dino if plan.soft else None, stu,
+                                    self._cfg(plan), rank=plan.shape.rank)
+        lo, ls, tl, lw = lambdas
         c, si, st = float(out["classic_loss"]), float(out["soft_img"]), float(out["soft_txt"])
         losses[0], losses[1], losses[2] = c, si, st
         losses[3] = si + tl * st
         losses[4] = lo * c + ls * (si + tl * st)
+        losses[5] = 0.0
+        if plan.weighted:
+            w, d = self._weighted(plan, img, txt, logit_scale.double()[0], dino)
+            losses[5] = float(w)
+            losses[4] = float(losses[4]) + lw * float(w)
+            if dbg is not None:
+                for i, k in enumerate(DBG_ORDER):
+                    dbg[i] = float(d[k])
         lse_local.zero_()
         state[0] = float(logit_scale[0])
         self.calls.append("forward")
@@ -86,14 +109,17 @@ class OracleBackend:
         if stu is not None:
             stu.requires_grad_(True)
         sc = torch.tensor(float(state[0]), dtype=torch.float64, requires_grad=True)
-        lo, ls, tl = lambdas
+        lo, ls, tl, lw = lambdas
         g5 = gout.double()
         gsoft = g5[3] + ls * g5[4]
-        g = torch.stack([g5[0] + lo * g5[4], g5[1] + gsoft, g5[2] + tl * gsoft])
+        g = torch.stack([g5[0] + lo * g5[4], g5[1] + gsoft, g5[2] + tl * gsoft, g5[5] + lw * g5[4]])
 
         def weighted(rank):
-            o = self.oracle.rank_loss(img, txt, sc, dino, stu, cfg, rank=rank)
-            return g[0] * o["classic_loss"] + g[1] * o["soft_img"] + g[2] * o["soft_txt"]
+            o = self.oracle.rank_loss(img, txt, sc, dino if plan.soft else None, stu, cfg, rank=rank)
+            t = g[0] * o["classic_loss"] + g[1] * o["soft_img"] + g[2] * o["soft_txt"]
+            if plan.weighted:
+                t = t + g[3] * self._weighted(plan, img, txt, sc, dino)[0]
+            return t
 
         own = weighted(s.rank)
         gs, = torch.autograd.grad(own, sc, retain_graph=True)

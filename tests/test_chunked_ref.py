@@ -33,3 +33,14 @@ def test_chunked_reference_matches_oracle(oracle, use_head, scale):
             want = ref[k][rows]
             err = (blk[k] - want).abs().max().item() / want.abs().max().item()
             assert err < 1e-9, (k, blk["row0"], err)
+
+
+@pytest.mark.parametrize("sym", [False, True])
+def test_chunked_weighted_loss_matches_oracle(oracle, sym):
+    from chunked_ref import chunked_weighted_loss
+
+    img, txt, dino = synth(3, 300, 32, 48)
+    cfg = oracle.OracleConfig(lambda_weighted=0.5, rho=0.2, c_clip=0.5, weight_text_symmetry=sym)
+    ref = oracle.loss_and_grads(img, txt, 30.0, dino, cfg)["ranks"][0]
+    assert chunked_weighted_loss(img, txt, dino, 30.0, 0.2, 0.5, sym, slab=64) == pytest.approx(
+        ref["weighted_loss"], rel=1e-9)

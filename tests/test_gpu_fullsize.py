@@ -6,7 +6,7 @@ last) at 1e-3 - plus size-independent properties (determinism, linearity, finite
 import pytest
 import torch
 
-from chunked_ref import chunked_reference
+from chunked_ref import chunked_reference, chunked_weighted_loss
 from gpu_util import head_params_of, make_args, rel_err, synth
 
 pytestmark = pytest.mark.gpu
@@ -151,3 +151,27 @@ def test_config4_dims_b8192_against_fp64(pkg, backward_path):
             linf, l2 = rel_err(got, blk[name])
             print(f"[config4] rows {blk['row0']}..: {name} linf={linf:.2e} l2={l2:.2e}")
             assert linf < 1e-3 and l2 < 1e-3, (blk["row0"], name, linf, l2)
+
+
+def test_weighted_branch_at_full_size(pkg):
+    """The weighted CE branch at B = 32768 (the reference needs ~10 live fp32 B x B matrices = 43 GB here): runs
+    inside the fused kernels without any B x B tensor, and its loss matches the row-blocked fp64 evaluation."""
+    img, txt, dino = synth(78, B, D, DD, device="cuda")
+    args = make_args(use_projection=False, lambda_weighted=0.5, rho=0.2, c_clip=0.5, weight_text_symmetry=True)
+    loss = pkg.ClipLossWithDINOEnhancements()
+    im = img.clone().requires_grad_(True)
+    tx = txt.clone().requires_grad_(True)
+    sc = torch.tensor(30.0, device="cuda", requires_grad=True)
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    out = loss(im, tx, sc, dino, args, output_dict=True)
+    out["total_loss"].backward()
+    torch.cuda.synchronize()
+    peak = torch.cuda.max_memory_allocated() - base
+    want = chunked_weighted_loss(img, txt, dino, 30.0, 0.2, 0.5, True)
+    got = float(out["weighted_loss"])
+    print(f"[fullsize weighted] got={got:.7f} ref={want:.7f} peak extra memory {peak / 2**30:.2f} GiB")
+    assert got == pytest.approx(want, rel=1e-4)
+    assert torch.isfinite(im.grad).all() and torch.isfinite(tx.grad).all() and torch.isfinite(sc.grad)
+    assert peak < 16 * 2**30  # fp16 logit-gradient matrices only (3 x 2 GiB + operands), no fp32 B x B tensors
+    assert float(out["dbg"]["beta_img"]) > 0 and float(out["dbg"]["pc_err_img"]) < 1e-3

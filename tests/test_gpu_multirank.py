@@ -20,7 +20,7 @@ from gpu_util import rel_err, synth
 pytestmark = pytest.mark.gpu
 
 LOSS_RTOL, GRAD_RTOL = 1e-4, 1e-3
-LAMBDAS = (1.0, 0.5, 0.5)  # lambda_original, lambda_soft, text_lambda
+LAMBDAS = (1.0, 0.5, 0.5, 0.0)  # lambda_original, lambda_soft, text_lambda, lambda_weighted
 TEACHER_TEMP, TEXT_TEMP = 0.15, 0.02
 
 
@@ -94,11 +94,11 @@ def cuda_ranks(pkg, img, txt, dino, student, scale, W, scope, gwg, gmat):
     for r, pl in enumerate(plans):
         st = torch.empty(pl.state_numel, dtype=torch.float32, device=dev)
         sc = torch.empty(pl.fwd_scratch_numel, dtype=torch.float32, device=dev)
-        lo = torch.empty(5, dtype=torch.float32, device=dev)
+        lo = torch.empty(6, dtype=torch.float32, device=dev)
         be.forward(pl, gathered, ls, LAMBDAS, st, sc, lse_all[r], lo)
         states.append(st)
         losses.append(lo)
-    gout = torch.tensor([0.0, 0.0, 0.0, 0.0, 1.0], dtype=torch.float32, device=dev)  # d total_loss = 1
+    gout = torch.tensor([0.0, 0.0, 0.0, 0.0, 1.0, 0.0], dtype=torch.float32, device=dev)  # d total_loss = 1
     out = []
     for r, pl in enumerate(plans):
         scratch = torch.empty(pl.scratch_numel, dtype=torch.float32, device=dev)

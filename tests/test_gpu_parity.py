@@ -113,12 +113,38 @@ def test_scale_100_linear_head(pkg, oracle):
                          make_args(use_projection=True, projection_type="linear", soft_dino_to_text=False))
 
 
+DBG_TOL = {  # relative tolerance per diagnostic (fp32 kernels vs the fp64 restatement in tests/weighted_ref.py)
+    "pos_frac_img": 2e-3, "neg_frac_img": 2e-3, "pos_frac_txt": 2e-3, "neg_frac_txt": 2e-3,
+    "corr_rhat_dprob_img": 2e-3, "corr_rhat_dprob_txt": 2e-3,
+}
+
+
 @pytest.mark.parametrize("sym", [False, True])
-def test_weighted_ce_branch(pkg, oracle, sym):
-    """lambda_weighted > 0 (loss.py:416-471): fused classic / soft terms plus the tensor-op weighted branch."""
-    check_against_oracle(pkg, oracle, 256, 128, 192, 30.0,
-                         make_args(use_projection=True, lambda_weighted=0.6, rho=0.2, c_clip=0.5,
-                                   weight_text_symmetry=sym), seed=11)
+@pytest.mark.parametrize("B,D,Dd,scale,proj,soft", [
+    (256, 128, 192, 30.0, True, True),      # everything on: classic + soft + weighted
+    (2048, 128, 192, 60.0, False, True),    # several column splits / row pairs
+    (200, 72, 136, 20.0, False, False),     # ragged, weighted without the soft term
+])
+def test_weighted_ce_branch(pkg, oracle, sym, B, D, Dd, scale, proj, soft):
+    """lambda_weighted > 0 (loss.py:416-471 + diagnostics 479-595) through the fused kernels (DSOFT_F_WEIGHTED)."""
+    from weighted_ref import weighted_ce_branch
+
+    args = make_args(use_projection=proj, lambda_weighted=0.6, rho=0.2, c_clip=0.5, weight_text_symmetry=sym,
+                     lambda_soft=0.5 if soft else 0.0, soft_mode="kl_teacher" if soft else "none")
+    out, ref = check_against_oracle(pkg, oracle, B, D, Dd, scale, args, seed=11)
+    assert float(out["weighted_loss"]) > 0.0
+    img, txt, dino = synth(11, B, D, Dd)
+    _, want = weighted_ce_branch(img.double(), txt.double(), torch.tensor(scale, dtype=torch.float64), dino.double(),
+                                 0.2, 0.5, sym)
+    assert set(out["dbg"]) == set(want)
+    for k, w in want.items():
+        got, w = float(out["dbg"][k]), float(w)
+        tol = DBG_TOL.get(k, 5e-4)
+        print(f"[weighted dbg] {k}: got={got:.6e} ref={w:.6e}")
+        if k.startswith("pc_err"):  # a cancellation residue (should be ~0): only its size is meaningful
+            assert abs(got) < 1e-4 and abs(w) < 1e-8, k
+        else:
+            assert got == pytest.approx(w, rel=tol, abs=1e-6), k
 
 
 def test_iid_gaussian_flat_teacher(pkg, oracle):
