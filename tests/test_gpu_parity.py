@@ -141,10 +141,8 @@ def test_weighted_ce_branch(pkg, oracle, sym, B, D, Dd, scale, proj, soft):
         got, w = float(out["dbg"][k]), float(w)
         tol = DBG_TOL.get(k, 5e-4)
         print(f"[weighted dbg] {k}: got={got:.6e} ref={w:.6e}")
-        if k.startswith("pc_err"):  # a cancellation residue (should be ~0): only its size is meaningful
-            assert abs(got) < 1e-4 and abs(w) < 1e-8, k
-        else:
-            assert got == pytest.approx(w, rel=tol, abs=1e-6), k
+        # pc_err is a cancellation residue (exactly 0 without the clamp): absolute floor of an fp32 row sum
+        assert got == pytest.approx(w, rel=tol, abs=2e-5 if k.startswith("pc_err") else 1e-6), k
 
 
 def test_iid_gaussian_flat_teacher(pkg, oracle):
