@@ -308,9 +308,15 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     // ------------------------------------------------------------------ TMA producer (warp-uniform loop)
     int stage = 0;
     uint32_t phase = 0;
+    // logit-gradient modes: the operands must survive the G store stream in L2
+    const uint64_t pol_keep = kGMode ? l2_policy_evict_last() : 0ull;
     auto load = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar_local, int c0, int c1) {
-      if constexpr (CG == 2) tma_load_2d_2sm(dst, m, mapa_shared(bar_local, 0), c0, c1);
-      else tma_load_2d(dst, m, bar_local, c0, c1);
+      if constexpr (CG == 2) {
+        if constexpr (kGMode) tma_load_2d_2sm_hint(dst, m, mapa_shared(bar_local, 0), c0, c1, pol_keep);
+        else tma_load_2d_2sm(dst, m, mapa_shared(bar_local, 0), c0, c1);
+      } else {
+        tma_load_2d(dst, m, bar_local, c0, c1);
+      }
     };
     if (resident && elect_one()) {
       const uint32_t af = smem_u32(a_full);
@@ -421,6 +427,7 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     float v[32];
     // ---- G staging (logit-gradient modes): this warp's strip, its swizzled row, and the TMA store of a finished
     // 64-column box.  Strip reuse: the issuing lane waits until its previous store has read the strip.
+    const uint64_t pol_stream = kGMode ? l2_policy_evict_first() : 0ull;  // G tiles: written once, read once later
     const uint32_t gs_base = smem_u32(gstage) + static_cast<uint32_t>(warp - EPI_WARP0) * 4096u;
     const uint32_t gs_row = gs_base + static_cast<uint32_t>(lane) * 128u;
     const int gsw = lane & 7;
@@ -438,7 +445,7 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_2d(gm, gs_base, 0, box_row);
+        tma_store_2d_hint(gm, gs_base, 0, box_row, pol_stream);
         bulk_commit_group();
       }
     };
