@@ -50,6 +50,9 @@ struct dsoft_plan {
   int B;           // global batch
   int Bcol;        // padded length of per-column fp32 vectors
   int have_soft, have_text, have_proj, soft_local, row_only;
+  int fwd_sym;         // world == 1 and fast_t: the soft forward computes the upper block triangle only
+  SplitPlan f_sym;     // its (triangular) column chunks
+  size_t sc_colpart, sc_colsum;
   int weighted, wsym;  // denominator-modulated CE branch (loss.py:416-471), world == 1 only
   SplitPlan f_wce;     // column split of its tile passes
   int Dz;          // student width (Dp or D)
@@ -200,6 +203,14 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   p->f_clip = choose_split(rbs, 1, ceil_div(p->B, 2 * BN), sms);  // forward CLIP kernel uses 256-column tiles
   p->f_soft = choose_split(rbs, 1, p->ntiles_s, sms);
   p->f_wce = choose_split(rbs, 1, ceil_div(p->B, 2 * BN), sms);
+  {
+    // symmetric forward: needs one rank (the row block is the whole square), the fixed teacher maximum, and more
+    // than one row pair (otherwise there is nothing to save); DSOFT_FWD_SYM=0 keeps the full-square kernel
+    const char* e = getenv("DSOFT_FWD_SYM");
+    p->fwd_sym = soft && sh->world == 1 && p->fast_t && rbs > 2 && !(e && e[0] == '0');
+    p->f_sym.tps = std::max(4, ceil_div(p->ntiles_s, 10));
+    p->f_sym.nsplit = ceil_div(p->ntiles_s, p->f_sym.tps);
+  }
   p->b_clip = choose_split(rbs, p->nch_clip, p->ntiles_g, sms);
   p->b_stu = choose_split(rbs, p->nch_stu, p->ntiles_s128, sms);
   p->b_txt = choose_split(rbs, p->nch_txt, p->ntiles_s128, sms);
@@ -234,7 +245,9 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   const size_t b = sh->b;
   p->sc_pc_it = take(2 * 2 * p->f_clip.nsplit * b);
   p->sc_pc_ti = take(2 * 2 * p->f_clip.nsplit * b);
-  p->sc_ps = take(soft ? 7 * 2 * p->f_soft.nsplit * b : 0);
+  p->sc_ps = take(soft ? 7 * 2 * std::max(p->f_soft.nsplit, p->fwd_sym ? p->f_sym.nsplit : 0) * b : 0);
+  p->sc_colpart = take(p->fwd_sym ? static_cast<size_t>(6) * (4 * rbs) * p->Bcol : 0);
+  p->sc_colsum = take(p->fwd_sym ? static_cast<size_t>(6) * p->Bcol : 0);
   p->sc_rowloss = take(3 * b);
   p->sc_wpart = take(p->weighted ? 11 * 2 * p->f_wce.nsplit * b : 0);
   p->sc_wrows = take(p->weighted ? 2 * 10 * b : 0);
@@ -301,6 +314,7 @@ extern "C" int dsoft_plan_kernel_flops(const dsoft_plan_t* p, double* algorithmi
   executed[3] = executed[4] = 2.0 * b * Bc * D * (chunk_groups(p->nch_clip) + 1.0);
   if (p->have_soft) {
     algorithmic[2] = executed[2] = 2.0 * b * Bs * (Dz + Dd + (p->have_text ? D : 0.0));
+    if (p->fwd_sym) executed[2] *= 0.5 * (1.0 + 256.0 / std::max(256.0, Bs));  // upper block triangle + diagonal tiles
     algorithmic[5] = 2.0 * b * Bs * Dz;
     executed[5] = 2.0 * b * Bs * (chunk_groups(p->nch_stu) * (Dz + Dd) + Dz);
   }
@@ -322,7 +336,8 @@ extern "C" int dsoft_plan_kernel_flops(const dsoft_plan_t* p, double* algorithmi
 
 extern "C" int dsoft_plan_launches_forward(const dsoft_plan_t* p) {
   if (!p) return 0;
-  return 1 /*pack*/ + 1 /*scalars*/ + 1 /*norms*/ + 2 /*clip x2*/ + (p->have_soft ? 1 : 0) + 1 /*finalize*/;
+  return 1 /*pack*/ + 1 /*scalars*/ + 1 /*norms*/ + 2 /*clip x2*/ + (p->have_soft ? 1 : 0) + (p->fwd_sym ? 1 : 0) +
+         1 /*finalize*/ + (p->weighted ? (p->wsym ? 2 : 1) * 7 + 1 : 0);
 }
 extern "C" int dsoft_plan_launches_backward(const dsoft_plan_t* p) {
   if (!p) return 0;
@@ -563,6 +578,8 @@ struct FinFwdArgs {
   const float* pc_it;  // [2][np_c][b]
   const float* pc_ti;
   const float* ps;     // [7][np_s][b]
+  const float* colsum; // symmetric forward: [6][Bcol] column-side sums (Zt, Aq, Ap, Ar, Zs, Ztt) by row, or null
+  int Bcol;
   const float* diag;
   const float* scal;
   float* lse;      // [5][b]
@@ -608,6 +625,14 @@ __device__ __forceinline__ void finalize_fwd_rows(const FinFwdArgs& a, float (&r
       zs += a.ps[5 * st + o];
       zx += a.ps[6 * st + o];
     }
+    if (a.colsum) {  // every partial of the symmetric forward is relative to the same fixed maximum
+      zt += a.colsum[0 * a.Bcol + i];
+      aq += a.colsum[1 * a.Bcol + i];
+      ap += a.colsum[2 * a.Bcol + i];
+      ar += a.colsum[3 * a.Bcol + i];
+      zs += a.colsum[4 * a.Bcol + i];
+      zx += a.colsum[5 * a.Bcol + i];
+    }
     l_t = m + log2f(zt);
     l_s = a.scal[SC_ITS_L2] + log2f(zs);
     // KL(q || p) = E_q[q2 - p2] - lse_t + lse_s   (log2 units -> nats), loss.py:380-383
@@ -622,6 +647,27 @@ __device__ __forceinline__ void finalize_fwd_rows(const FinFwdArgs& a, float (&r
   a.lse[4 * a.b + i] = l_x;
   rl[1] = kl_s;
   rl[2] = kl_x;
+}
+
+// Symmetric forward: out[k][j] = sum over the warps w < 8 * (j / 256) of colpart[k][w][j] - the row blocks left of
+// row j's own pair, four warps each - in a fixed order (deterministic).  grid (Bcol / 32, 6), block (32, 16).
+__global__ void __launch_bounds__(512) soft_colreduce_kernel(const float* __restrict__ colpart, int cp_rows, int pitch,
+                                                             int ncols, float* __restrict__ out) {
+  __shared__ float sh[16][33];
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  const int k = blockIdx.y;
+  const int wmax = min(cp_rows, 8 * (j >> 8));
+  float acc = 0.f;
+  if (j < ncols)
+    for (int w = threadIdx.y; w < wmax; w += 16) acc += colpart[(static_cast<size_t>(k) * cp_rows + w) * pitch + j];
+  sh[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 16; ++y) t += sh[y][threadIdx.x];
+    out[static_cast<size_t>(k) * pitch + j] = t;
+  }
 }
 
 __global__ void __launch_bounds__(128) finalize_fwd_kernel(FinFwdArgs a) {
@@ -1869,7 +1915,20 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
     P.rinv[2] = S + p->st_rinv_t;
     P.part = X + p->sc_ps;
     if ((rc = fk.lane(lane++, &ks))) return rc;
-    {
+    if (p->fwd_sym) {
+      // world == 1: upper block triangle only, the other half through column reductions (MODE_SOFT_SYM)
+      if ((rc = set_smem(dsoft_fwd_kernel<MODE_SOFT_SYM, 2>, FWD_SMEM_BYTES))) return rc;
+      P.tri = 1;
+      P.tiles_per_split = p->f_sym.tps;
+      P.npart = 2 * p->f_sym.nsplit;
+      P.colpart = X + p->sc_colpart;
+      P.cp_rows = 4 * rbs;
+      P.cp_pitch = p->Bcol;
+      ProfScope ps(PK_FWD_SOFT, ks);
+      if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_SOFT_SYM, 2>, rbs, p->f_sym.nsplit, ks, tm, P))) return rc;
+      soft_colreduce_kernel<<<dim3(p->Bcol / 32, 6), dim3(32, 16), 0, ks>>>(X + p->sc_colpart, 4 * rbs, p->Bcol, p->B,
+                                                                            X + p->sc_colsum);
+    } else {
       ProfScope ps(PK_FWD_SOFT, ks);
       if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_SOFT, 2>, rbs, p->f_soft.nsplit, ks, tm, P))) return rc;
     }
@@ -1896,12 +1955,14 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
   FinFwdArgs fa;
   fa.b = b;
   fa.np_c = 2 * p->f_clip.nsplit;
-  fa.np_s = 2 * p->f_soft.nsplit;
+  fa.np_s = 2 * (p->fwd_sym ? p->f_sym.nsplit : p->f_soft.nsplit);
   fa.have_soft = p->have_soft;
   fa.have_text = p->have_text;
   fa.pc_it = X + p->sc_pc_it;
   fa.pc_ti = X + p->sc_pc_ti;
   fa.ps = X + p->sc_ps;
+  fa.colsum = p->fwd_sym ? X + p->sc_colsum : nullptr;
+  fa.Bcol = p->Bcol;
   fa.diag = S + p->st_diag;
   fa.scal = S + p->st_scal;
   fa.lse = lse_local;

@@ -49,6 +49,7 @@ constexpr int MODE_WCE_STAT = 5;
 constexpr int MODE_WCE_LSE = 6;
 constexpr int MODE_WCE_DBG = 7;
 constexpr int MODE_WCE_G = 8;
+constexpr int MODE_SOFT_SYM = 9;  // forward soft statistics, world == 1: upper block triangle + column reductions
 
 // scalar block computed on device by prep_scalars_kernel (no host sync on logit_scale)
 enum {
@@ -118,6 +119,9 @@ struct FwdParams {
   int wsym;                 // weight_text_symmetry (loss.py:449-463)
   float wcc;                // c_clip
   const float* wgout;       // G mode: upstream gradients [6] (device)
+  // ---- symmetric forward (MODE_SOFT_SYM): column partials [6][cp_rows = 4 * row blocks][cp_pitch]
+  float* colpart;
+  int cp_rows, cp_pitch;
   float wlam[2];            // G mode: lambda_original, lambda_weighted
   int tri;                  // soft G, world == 1: the matrices are symmetric -> only the 256-column tiles from the
                             // row pair's own diagonal tile (index rb / 2) onwards are computed and stored, scaled
@@ -176,6 +180,24 @@ __device__ __forceinline__ void st_cs_v8(void* dst, const uint32_t (&w)[8]) {
                : "memory");
 }
 
+// Column sums over the 32 rows of a warp: every lane holds x[k] = the value of ITS row in column k; lane l returns
+// sum over the lanes of x[l].  Butterfly: a stage keeps the half of the columns that matches the lane's bit and
+// swaps the other half with the partner lane (31 shuffles; fixed order, so the result is deterministic).
+__device__ __forceinline__ float warp_colsum32(float (&x)[32], int lane) {
+#define DSOFT_CS_STAGE(O)                                               \
+  {                                                                     \
+    const bool up = (lane & O) != 0;                                    \
+    _Pragma("unroll") for (int i = 0; i < O; ++i) {                     \
+      const float send = up ? x[i] : x[i + O];                          \
+      const float keep = up ? x[i + O] : x[i];                          \
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);              \
+    }                                                                   \
+  }
+  DSOFT_CS_STAGE(16) DSOFT_CS_STAGE(8) DSOFT_CS_STAGE(4) DSOFT_CS_STAGE(2) DSOFT_CS_STAGE(1)
+#undef DSOFT_CS_STAGE
+  return x[0];
+}
+
 // element (local row li, column j) of a blocked fp16 logit-gradient matrix: K tiles of 64 columns, each
 // (row block, K tile) = one 16 KiB TMA box of the gradient GEMM's A operand
 __device__ __forceinline__ size_t g_index(int li, int j, int pitch) {
@@ -218,7 +240,7 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   uint8_t* smem = align_1024(smem_raw);
   constexpr bool kWce = (MODE >= MODE_WCE_STAT && MODE <= MODE_WCE_G);
   // "soft-like": 256-column tiles with several products per tile, staged per-column vectors, setmaxnreg
-  constexpr bool kSoftMode = (MODE == MODE_SOFT || MODE == MODE_SOFT_G || kWce);
+  constexpr bool kSoftMode = (MODE == MODE_SOFT || MODE == MODE_SOFT_G || MODE == MODE_SOFT_SYM || kWce);
   static_assert(!kSoftMode || CG == 2, "the soft modes are written for CTA pairs");
   // streaming mode: stages of (A box | B boxes); resident mode: 8 A boxes, then B-only stages
   const bool resident = P.resident != 0;
@@ -993,6 +1015,143 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < 11; ++k) P.part[k * st + o] = acc[k];
         }
+      }
+    } else if constexpr (MODE == MODE_SOFT_SYM) {
+      // ---------------------------------------------------------------- symmetric forward (world == 1)
+      // The teacher, student and text Gram matrices are symmetric, so a row pair only computes the tiles from its
+      // own diagonal tile onwards (P.tri).  A tile right of the diagonal also holds, transposed, the entries the
+      // rows of its COLUMN block need: every quantity is summed over the 32 rows of a warp per column (warp
+      // butterfly, warp_colsum32) and written as a column partial [k][rb * 4 + q][column]; soft_colreduce_kernel
+      // adds those to the row partials.  All exponentials use FIXED maxima (teacher: log2(e)/tau_t, valid because
+      // fast_t bounds it by 60; student / text: log2(e)/tau, reached on the diagonal), so row and column partials
+      // share one reference and no running maximum has to be reconciled.
+      const float mt2 = P.scal[SC_ITT_L2], ms2 = P.scal[SC_ITS_L2], mx2 = P.scal[SC_ITX_L2];
+      const float cq = P.rinv[0][gi] * mt2;
+      const float cp = P.rinv[1][gi] * ms2;
+      const bool has_text = P.nprod == 3;
+      const float cr = has_text ? P.rinv[2][gi] * mx2 : 0.f;
+      const bool live_row = li < P.b;  // rows past b (zero operands) must not reach the column sums
+      float zt = 0.f, aq = 0.f, ap = 0.f, ar = 0.f, zs = 0.f, zx = 0.f;
+      float w[128];  // teacher weights 2^(q - M_t) of this thread's 128 columns, kept across the three products
+      const size_t cp_stride = static_cast<size_t>(P.cp_rows) * P.cp_pitch;  // one quantity of the column partials
+      float* cp_row = P.colpart + static_cast<size_t>(rb * 4 + q) * P.cp_pitch;
+      int it = 0;
+      for (int t = t0; t < t1; ++t, it += P.nprod) {
+        const int jt0 = t * CT + half * 128;
+        const bool ragged = jt0 + 128 > P.ncols;
+        const bool offdiag = t > (rb >> 1);  // this tile also serves the rows of its column block
+        const int cb = (t - t0) % COL_BUFS;
+        mbar_wait(smem_u32(&col_full[cb]), static_cast<uint32_t>((t - t0) / COL_BUFS) & 1);
+        const float* cv = colbuf + cb * COL_VECS * CT + half * 128;
+        {  // ---- teacher
+          const int slot = (it + 0) % 2;
+          mbar_wait(smem_u32(&s_full[slot]), static_cast<uint32_t>((it + 0) / 2) & 1);
+          tc_fence_after();
+          uint32_t rA[32], rB[32];
+          tmem_ld32_nowait(lane_addr + slot * CT + half * 128, rA);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int jrel0 = jt0 + c * 32;
+            uint32_t(&rcur)[32] = (c & 1) ? rB : rA;
+            uint32_t(&rnxt)[32] = (c & 1) ? rA : rB;
+            tmem_ld_wait(rcur);
+            if (c < 3) {
+              tmem_ld32_nowait(lane_addr + slot * CT + half * 128 + (c + 1) * 32, rnxt);
+            } else {
+              tc_fence_before();
+              release_slot(slot);
+            }
+            const float4* rc = reinterpret_cast<const float4*>(cv + c * 32);
+            const bool need_mask = (gw0 < jrel0 + 32 && jrel0 < gw0 + 32) || (ragged && jrel0 + 32 > P.ncols) || !offdiag;
+            float wq[32];
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const float4 r = rc[e4];
+              const float rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int e = 4 * e4 + k;
+                const float q2 = __uint_as_float(rcur[e]) * cq * rr[k];
+                float we = live_row ? fast_exp2(q2 - mt2) : 0.f;
+                if (need_mask && (jrel0 + e >= P.ncols || jrel0 + e == gi)) we = 0.f;  // ragged; teacher diag masked
+                w[c * 32 + e] = we;
+                wq[e] = we * q2;
+                zt += we;
+                aq += wq[e];
+              }
+            }
+            if (offdiag) {  // warp-uniform
+              float x0[32];
+#pragma unroll
+              for (int e = 0; e < 32; ++e) x0[e] = w[c * 32 + e];
+              const float s0 = warp_colsum32(x0, lane);
+              const float s1 = warp_colsum32(wq, lane);
+              cp_row[0 * cp_stride + jrel0 + lane] = s0;
+              cp_row[1 * cp_stride + jrel0 + lane] = s1;
+            }
+          }
+        }
+        for (int p = 1; p < P.nprod; ++p) {  // ---- student (p = 1), text (p = 2)
+          const int slot = (it + p) % 2;
+          mbar_wait(smem_u32(&s_full[slot]), static_cast<uint32_t>((it + p) / 2) & 1);
+          tc_fence_after();
+          const float cs = (p == 1) ? cp : cr;
+          const float mfix = (p == 1) ? ms2 : mx2;
+          float b0 = 0.f, b1 = 0.f;
+          uint32_t rA[32], rB[32];
+          tmem_ld32_nowait(lane_addr + slot * CT + half * 128, rA);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int jrel0 = jt0 + c * 32;
+            uint32_t(&rcur)[32] = (c & 1) ? rB : rA;
+            uint32_t(&rnxt)[32] = (c & 1) ? rA : rB;
+            tmem_ld_wait(rcur);
+            if (c < 3) {
+              tmem_ld32_nowait(lane_addr + slot * CT + half * 128 + (c + 1) * 32, rnxt);
+            } else {
+              tc_fence_before();
+              release_slot(slot);
+            }
+            const float4* rc = reinterpret_cast<const float4*>(cv + p * CT + c * 32);
+            const bool rag = ragged && jrel0 + 32 > P.ncols;
+            float es[32], wp[32];
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const float4 r = rc[e4];
+              const float rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int e = 4 * e4 + k;
+                const float p2 = __uint_as_float(rcur[e]) * cs * rr[k];
+                float ex = live_row ? fast_exp2(p2 - mfix) : 0.f;
+                if (rag && jrel0 + e >= P.ncols) ex = 0.f;
+                es[e] = ex;
+                wp[e] = w[c * 32 + e] * p2;  // w is zero on masked entries
+                b0 += ex;
+                b1 += wp[e];
+              }
+            }
+            if (offdiag) {
+              const float s0 = warp_colsum32(es, lane);
+              const float s1 = warp_colsum32(wp, lane);
+              cp_row[(p == 1 ? 4 : 5) * cp_stride + jrel0 + lane] = s0;
+              cp_row[(p == 1 ? 2 : 3) * cp_stride + jrel0 + lane] = s1;
+            }
+          }
+          if (p == 1) { zs += b0; ap += b1; } else { zx += b0; ar += b1; }
+        }
+        mbar_arrive(smem_u32(&col_empty[cb]));
+      }
+      if (li < P.b) {  // same partial layout as MODE_SOFT; the maximum is the fixed one
+        const int o = sp * P.b + li;
+        const int st = P.npart * P.b;
+        P.part[0 * st + o] = mt2;
+        P.part[1 * st + o] = zt;
+        P.part[2 * st + o] = aq;
+        P.part[3 * st + o] = ap;
+        P.part[4 * st + o] = ar;
+        P.part[5 * st + o] = zs;
+        P.part[6 * st + o] = zx;
       }
     } else {
       const float cq = P.rinv[0][gi] * P.scal[SC_ITT_L2];
