@@ -110,15 +110,29 @@ static SplitPlan choose_split(int row_blocks, int nchunk, int ntiles, int num_sm
   return best;
 }
 
-// K split of a gradient GEMM: `tiles` CTA pairs per split; fill ~2 waves of pair slots when there are few.
-static SplitPlan choose_gy_split(int tiles, int ksteps, int num_sms) {
+// K split of a gradient GEMM: `tiles` CTA pairs per split on num_sms / 2 pair slots.  Cost model: whole waves of
+// pair slots x (K steps per CTA + a fixed prologue / drain overhead in K steps); e.g. 96 tiles (b = 8192, Dout = 768)
+// on 74 slots run as 2 waves unsplit (the second 30 % full) but as 4 full waves with a 3-way split.
+// Every extra split also costs one more [b x Dout] fp32 partial to write and to read back in finalize_bwd (~2.5 TB/s
+// there), expressed in K-step times of a CTA pair (512 clocks ~ 0.27 us).
+static SplitPlan choose_gy_split(int tiles, int ksteps, int num_sms, int b, int dout) {
+  const double split_penalty = static_cast<double>(b) * dout / 84375.0;
   const int slots = std::max(1, num_sms / 2);
-  int ns = 1;
-  if (tiles < 2 * slots) ns = std::max(1, (2 * slots) / std::max(1, tiles));
-  ns = std::min(ns, std::max(1, ksteps / 4));  // at least 4 K steps (256 columns) per split
-  ns = std::min(ns, 32);
+  const int max_ns = std::min(32, std::max(1, ksteps / 4));  // at least 4 K steps (256 columns) per split
+  int best = 1;
+  double best_cost = 1e300;
+  for (int ns = 1; ns <= max_ns; ++ns) {
+    const int tps = ceil_div(ksteps, ns);
+    const int ns_eff = ceil_div(ksteps, tps);
+    const long waves = (static_cast<long>(tiles) * ns_eff + slots - 1) / slots;
+    const double cost = static_cast<double>(waves) * (tps + 8.0) + split_penalty * (ns_eff - 1);
+    if (cost < 0.95 * best_cost) {  // more splits only for a clear gain (the model is coarse)
+      best_cost = cost;
+      best = ns_eff;
+    }
+  }
   SplitPlan sp;
-  sp.tps = ceil_div(ksteps, ns);
+  sp.tps = ceil_div(ksteps, best);
   sp.nsplit = ceil_div(ksteps, sp.tps);
   return sp;
 }
@@ -219,11 +233,11 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   p->pitch_s = ceil_div(p->s_ncols, 64) * 64;
   if (p->gmat) {
     const int pairs = ceil_div(rbs, 2);
-    p->g_clip = choose_gy_split(pairs * ceil_div(sh->D, GY_N), p->pitch_c / 64, sms);
-    p->g_stu = choose_gy_split(pairs * ceil_div(p->Dz, GY_N), p->pitch_s / 64, sms);
-    p->g_txt = choose_gy_split(pairs * ceil_div(sh->D, GY_N), p->pitch_s / 64, sms);
+    p->g_clip = choose_gy_split(pairs * ceil_div(sh->D, GY_N), p->pitch_c / 64, sms, sh->b, sh->D);
+    p->g_stu = choose_gy_split(pairs * ceil_div(p->Dz, GY_N), p->pitch_s / 64, sms, sh->b, p->Dz);
+    p->g_txt = choose_gy_split(pairs * ceil_div(sh->D, GY_N), p->pitch_s / 64, sms, sh->b, sh->D);
     p->clip_tr = sh->world == 1;
-    p->g_clip_t = choose_gy_split(pairs * ceil_div(sh->D, GY_N), rbs * 2, sms);
+    p->g_clip_t = choose_gy_split(pairs * ceil_div(sh->D, GY_N), rbs * 2, sms, sh->b, sh->D);
   }
 
   // ---- state (floats)
