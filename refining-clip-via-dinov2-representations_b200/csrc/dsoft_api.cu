@@ -646,6 +646,10 @@ __device__ __forceinline__ void finalize_fwd_rows(const FinFwdArgs& a, float (&r
       ar += a.colsum[3 * a.Bcol + i];
       zs += a.colsum[4 * a.Bcol + i];
       zx += a.colsum[5 * a.Bcol + i];
+      // the symmetric kernel accumulates sum w (q - M_t), sum w (p - M_s), sum w (r - M_x)
+      aq += a.scal[SC_ITT_L2] * zt;
+      ap += a.scal[SC_ITS_L2] * zt;
+      ar += a.scal[SC_ITX_L2] * zt;
     }
     l_t = m + log2f(zt);
     l_s = a.scal[SC_ITS_L2] + log2f(zs);

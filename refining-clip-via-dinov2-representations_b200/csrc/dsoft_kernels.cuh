@@ -1031,6 +1031,10 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       const bool has_text = P.nprod == 3;
       const float cr = has_text ? P.rinv[2][gi] * mx2 : 0.f;
       const bool live_row = li < P.b;  // rows past b (zero operands) must not reach the column sums
+      // exponent arguments come out of ONE fma: arg = dot * (row factor * column factor) - M, with M = -1e30 for a
+      // dead row (2^arg = 0 without a select).  The weighted sums are kept relative to the fixed maxima,
+      // sum w (q - M_t) etc.; finalize_fwd adds M * Zt back.
+      const float bias_t = live_row ? -mt2 : NEG_BIG;
       float zt = 0.f, aq = 0.f, ap = 0.f, ar = 0.f, zs = 0.f, zx = 0.f;
       float w[128];  // teacher weights 2^(q - M_t) of this thread's 128 columns, kept across the three products
       const size_t cp_stride = static_cast<size_t>(P.cp_rows) * P.cp_pitch;  // one quantity of the column partials
@@ -1071,11 +1075,11 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const int e = 4 * e4 + k;
-                const float q2 = __uint_as_float(rcur[e]) * cq * rr[k];
-                float we = live_row ? fast_exp2(q2 - mt2) : 0.f;
+                const float arg = fmaf(__uint_as_float(rcur[e]), cq * rr[k], bias_t);
+                float we = fast_exp2(arg);
                 if (need_mask && (jrel0 + e >= P.ncols || jrel0 + e == gi)) we = 0.f;  // ragged; teacher diag masked
                 w[c * 32 + e] = we;
-                wq[e] = we * q2;
+                wq[e] = we * arg;
                 zt += we;
                 aq += wq[e];
               }
@@ -1096,7 +1100,7 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
           mbar_wait(smem_u32(&s_full[slot]), static_cast<uint32_t>((it + p) / 2) & 1);
           tc_fence_after();
           const float cs = (p == 1) ? cp : cr;
-          const float mfix = (p == 1) ? ms2 : mx2;
+          const float bias_y = live_row ? -((p == 1) ? ms2 : mx2) : NEG_BIG;
           float b0 = 0.f, b1 = 0.f;
           uint32_t rA[32], rB[32];
           tmem_ld32_nowait(lane_addr + slot * CT + half * 128, rA);
@@ -1122,11 +1126,11 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const int e = 4 * e4 + k;
-                const float p2 = __uint_as_float(rcur[e]) * cs * rr[k];
-                float ex = live_row ? fast_exp2(p2 - mfix) : 0.f;
+                const float arg = fmaf(__uint_as_float(rcur[e]), cs * rr[k], bias_y);
+                float ex = fast_exp2(arg);
                 if (rag && jrel0 + e >= P.ncols) ex = 0.f;
                 es[e] = ex;
-                wp[e] = w[c * 32 + e] * p2;  // w is zero on masked entries
+                wp[e] = w[c * 32 + e] * arg;  // w is zero on masked entries and in dead rows
                 b0 += ex;
                 b1 += wp[e];
               }
