@@ -51,6 +51,8 @@ struct dsoft_plan {
   int Bcol;        // padded length of per-column fp32 vectors
   int have_soft, have_text, have_proj, soft_local, row_only;
   int fwd_sym;         // world == 1 and fast_t: the soft forward computes the upper block triangle only
+  int clip_sym;        // world == 1: one CLIP forward pass serves both directions (MODE_CLIP_SYM)
+  size_t sc_clipM, sc_clipS, sc_lse_ti, st_dbound;
   SplitPlan f_sym;     // its (triangular) column chunks
   size_t sc_colpart, sc_colsum;
   int weighted, wsym;  // denominator-modulated CE branch (loss.py:416-471), world == 1 only
@@ -225,6 +227,11 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
     p->f_sym.tps = std::max(4, ceil_div(p->ntiles_s, 10));
     p->f_sym.nsplit = ceil_div(p->ntiles_s, p->f_sym.tps);
   }
+  {
+    // one-pass CLIP forward: the row block must be the whole square (one rank); DSOFT_CLIP_SYM=0 keeps two passes
+    const char* e = getenv("DSOFT_CLIP_SYM");
+    p->clip_sym = sh->world == 1 && rbs > 2 && !(e && e[0] == '0');
+  }
   p->b_clip = choose_split(rbs, p->nch_clip, p->ntiles_g, sms);
   p->b_stu = choose_split(rbs, p->nch_stu, p->ntiles_s128, sms);
   p->b_txt = choose_split(rbs, p->nch_txt, p->ntiles_s128, sms);
@@ -248,6 +255,7 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   p->st_rinv_z = take(p->Bcol);
   p->st_rinv_d = take(p->Bcol);
   p->st_diag = take(sh->b);
+  p->st_dbound = take(p->Bcol);
   p->st_lsecols = take(static_cast<size_t>(5) * p->Bcol);
   p->st_colfac = take(static_cast<size_t>(5) * p->Bcol);
   p->st_lsestat = take(2 * 64);
@@ -257,11 +265,14 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   // ---- scratch (floats)
   o = 0;
   const size_t b = sh->b;
-  p->sc_pc_it = take(2 * 2 * p->f_clip.nsplit * b);
+  p->sc_pc_it = take(2 * (p->clip_sym ? 4 : 2) * p->f_clip.nsplit * b);
   p->sc_pc_ti = take(2 * 2 * p->f_clip.nsplit * b);
   p->sc_ps = take(soft ? 7 * 2 * std::max(p->f_soft.nsplit, p->fwd_sym ? p->f_sym.nsplit : 0) * b : 0);
   p->sc_colpart = take(p->fwd_sym ? static_cast<size_t>(6) * (4 * rbs) * p->Bcol : 0);
   p->sc_colsum = take(p->fwd_sym ? static_cast<size_t>(6) * p->Bcol : 0);
+  p->sc_clipM = take(p->clip_sym ? static_cast<size_t>(4 * rbs) * p->Bcol : 0);
+  p->sc_clipS = take(p->clip_sym ? static_cast<size_t>(4 * rbs) * p->Bcol : 0);
+  p->sc_lse_ti = take(p->clip_sym ? p->Bcol : 0);
   p->sc_rowloss = take(3 * b);
   p->sc_wpart = take(p->weighted ? 11 * 2 * p->f_wce.nsplit * b : 0);
   p->sc_wrows = take(p->weighted ? 2 * 10 * b : 0);
@@ -324,6 +335,10 @@ extern "C" int dsoft_plan_kernel_flops(const dsoft_plan_t* p, double* algorithmi
   // forward CLIP: the two directions are exact transposes -> one algorithmic product, two executed
   algorithmic[0] = algorithmic[1] = b * Bc * D;
   executed[0] = executed[1] = 2.0 * b * Bc * D;
+  if (p->clip_sym) {  // one pass: the product is computed once
+    algorithmic[0] = 2.0 * b * Bc * D;
+    algorithmic[1] = executed[1] = 0.0;
+  }
   algorithmic[3] = algorithmic[4] = 2.0 * b * Bc * D;
   executed[3] = executed[4] = 2.0 * b * Bc * D * (chunk_groups(p->nch_clip) + 1.0);
   if (p->have_soft) {
@@ -518,6 +533,8 @@ struct RinvArgs {
   float* rmin[3];
   int64_t ld;
   int rows, out_len;
+  const __nv_bfloat16* dot_mat;  // optional (matrix 0 only): dot_out[r] = <mat[0] row r, dot_mat row r>, the CLIP
+  float* dot_out;                // diagonal logit / scale = a lower bound of row r's and column r's log-sum-exp
 };
 constexpr int RINV_ROWS_PER_WARP = 4;
 __global__ void __launch_bounds__(256) rinv_kernel(RinvArgs a) {
@@ -530,20 +547,44 @@ __global__ void __launch_bounds__(256) rinv_kernel(RinvArgs a) {
   for (int q = 0; q < RINV_ROWS_PER_WARP; ++q) {
     const int r = (blockIdx.x * 8 + warp) * RINV_ROWS_PER_WARP + q;
     if (r >= a.out_len) break;
+    const bool want_dot = k == 0 && a.dot_out != nullptr;
     if (r >= a.rows) {
-      if (lane == 0) out[r] = 0.f;
+      if (lane == 0) {
+        out[r] = 0.f;
+        if (want_dot) a.dot_out[r] = 3.0e38f;  // padded columns never make a chunk look risky
+      }
       continue;
     }
     const uint4* p = reinterpret_cast<const uint4*>(a.mat[k] + r * a.ld);
-    float acc = 0.f;
-    for (int c = lane; c < ncol8; c += 32) {
-      const uint4 raw = __ldg(p + c);
-      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+    float acc = 0.f, dot = 0.f;
+    if (want_dot) {
+      const uint4* p2 = reinterpret_cast<const uint4*>(a.dot_mat + r * a.ld);
+      for (int c = lane; c < ncol8; c += 32) {
+        const uint4 raw = __ldg(p + c), raw2 = __ldg(p2 + c);
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w}, w2[4] = {raw2.x, raw2.y, raw2.z, raw2.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
-        acc = fmaf(f.x, f.x, acc);
-        acc = fmaf(f.y, f.y, acc);
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+          const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w2[j]));
+          acc = fmaf(f.x, f.x, acc);
+          acc = fmaf(f.y, f.y, acc);
+          dot = fmaf(f.x, g.x, dot);
+          dot = fmaf(f.y, g.y, dot);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      if (lane == 0) a.dot_out[r] = dot;
+    } else {
+      for (int c = lane; c < ncol8; c += 32) {
+        const uint4 raw = __ldg(p + c);
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+          acc = fmaf(f.x, f.x, acc);
+          acc = fmaf(f.y, f.y, acc);
+        }
       }
     }
 #pragma unroll
@@ -593,6 +634,7 @@ struct FinFwdArgs {
   const float* pc_ti;
   const float* ps;     // [7][np_s][b]
   const float* colsum; // symmetric forward: [6][Bcol] column-side sums (Zt, Aq, Ap, Ar, Zs, Ztt) by row, or null
+  const float* lse_ti; // one-pass CLIP forward: text -> image log-sum-exp by row (= column of I . T^T), or null
   int Bcol;
   const float* diag;
   const float* scal;
@@ -618,7 +660,7 @@ __device__ __forceinline__ void finalize_fwd_rows(const FinFwdArgs& a, float (&r
   if (i >= a.b) return;
   const float LN2 = 0.6931471805599453f;
   const float l_it = combine_lse2(a.pc_it, a.np_c, a.b, i);
-  const float l_ti = combine_lse2(a.pc_ti, a.np_c, a.b, i);
+  const float l_ti = a.lse_ti ? a.lse_ti[i] : combine_lse2(a.pc_ti, a.np_c, a.b, i);
   a.lse[0 * a.b + i] = l_it;
   a.lse[1 * a.b + i] = l_ti;
   // classic CE row term (loss.py:317-319): lse_it - L_ii + lse_ti - L_ii
@@ -685,6 +727,37 @@ __global__ void __launch_bounds__(512) soft_colreduce_kernel(const float* __rest
 #pragma unroll
     for (int y = 0; y < 16; ++y) t += sh[y][threadIdx.x];
     out[static_cast<size_t>(k) * pitch + j] = t;
+  }
+}
+
+// One-pass CLIP forward: out[j] = log2 sum_w colS[w][j] 2^(colM[w][j]) over all warp rows w (online maximum, fixed
+// order -> deterministic).  grid (Bcol / 32), block (32, 16).
+__global__ void __launch_bounds__(512) clip_colreduce_kernel(const float* __restrict__ colM,
+                                                             const float* __restrict__ colS, int cp_rows, int pitch,
+                                                             int ncols, float* __restrict__ out) {
+  __shared__ float shm[16][33], shs[16][33];
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  float m = M_FLOOR, s = 0.f;
+  if (j < ncols) {
+    for (int w = threadIdx.y; w < cp_rows; w += 16) {
+      const size_t o = static_cast<size_t>(w) * pitch + j;
+      const float mw = colM[o], sw = colS[o];
+      const float mn = fmaxf(m, mw);
+      s = s * exp2f(m - mn) + sw * exp2f(mw - mn);
+      m = mn;
+    }
+  }
+  shm[threadIdx.y][threadIdx.x] = m;
+  shs[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    float mm = M_FLOOR;
+#pragma unroll
+    for (int y = 0; y < 16; ++y) mm = fmaxf(mm, shm[y][threadIdx.x]);
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 16; ++y) t += shs[y][threadIdx.x] * exp2f(shm[y][threadIdx.x] - mm);
+    out[j] = mm + log2f(t);
   }
 }
 
@@ -1393,10 +1466,11 @@ struct Fork {
 // ------------------------------------------------------------------------------------------------
 // Forward tile kernels run as CTA pairs (cluster of 2 consecutive row blocks, cta_group::2 MMAs).
 template <typename K>
-static int launch_fwd_pair(K kernel, int rbs, int nsplit, cudaStream_t st, const TileMaps& tm, const FwdParams& P) {
+static int launch_fwd_pair(K kernel, int rbs, int nsplit, cudaStream_t st, const TileMaps& tm, const FwdParams& P,
+                           int threads = NUM_THREADS) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((rbs + 1) / 2 * 2, nsplit, 1);
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = FWD_SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1800,7 +1874,8 @@ __global__ void __launch_bounds__(1024) wce_final_kernel(WceFinalArgs a) {
 }
 
 template <typename K>
-static int launch_fwd_pair(K kernel, int rbs, int nsplit, cudaStream_t st, const TileMaps& tm, const FwdParams& P);
+static int launch_fwd_pair(K kernel, int rbs, int nsplit, cudaStream_t st, const TileMaps& tm, const FwdParams& P,
+                           int threads);
 template <typename K>
 static int set_smem(K kernel, int bytes);
 
@@ -1896,6 +1971,10 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
     ra.mat[0] = g + p->offT; ra.cols[0] = p->sh.D;  ra.out[0] = S + p->st_rinv_t; ra.rmin[0] = S + p->st_scal + SC_RMIN_T;
     ra.mat[1] = g + p->offZ; ra.cols[1] = p->Dz;    ra.out[1] = S + p->st_rinv_z; ra.rmin[1] = S + p->st_scal + SC_RMIN_Z;
     ra.mat[2] = g + p->offD; ra.cols[2] = p->sh.Dd; ra.out[2] = S + p->st_rinv_d; ra.rmin[2] = S + p->st_scal + SC_RMIN_D;
+    if (p->clip_sym) {  // diagonal dot products: lower bounds of the log-sum-exps for the one-pass CLIP forward
+      ra.dot_mat = g + p->offI;
+      ra.dot_out = S + p->st_dbound;
+    }
     rinv_kernel<<<dim3(ceil_div(p->Bcol, 8 * RINV_ROWS_PER_WARP), (p->have_soft || p->weighted) ? 3 : 1), 256, 0,
                   st>>>(ra);
     CUDA_TRY(cudaGetLastError());
@@ -1955,24 +2034,42 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
   // image -> text (loss.py:266/272) and text -> image (loss.py:267/273)
   fill_clip_fwd(p, P, 0, 1, S + p->st_scal, X + p->sc_pc_it, S + p->st_diag);
   if ((rc = fk.lane(lane++, &ks))) return rc;
-  {
+  if (p->clip_sym) {
+    // world == 1: text -> image is the transpose; one pass with per-warp column partials (MODE_CLIP_SYM)
+    if ((rc = set_smem(dsoft_fwd_kernel<MODE_CLIP_SYM, 2>, FWD_SMEM_BYTES))) return rc;
+    P.colM = X + p->sc_clipM;
+    P.colS = X + p->sc_clipS;
+    P.cp_rows = 4 * rbs;
+    P.cp_pitch = p->Bcol;
+    P.dbound = S + p->st_dbound;
     ProfScope ps(PK_FWD_CLIP_IT, ks);
-    if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_CLIP, 2>, rbs, p->f_clip.nsplit, ks, tm, P))) return rc;
+    P.npart = 4 * p->f_clip.nsplit;  // sixteen epilogue warps: four 64-column strips per split
+    if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_CLIP_SYM, 2>, rbs, p->f_clip.nsplit, ks, tm, P,
+                              fwd_threads(MODE_CLIP_SYM))))
+      return rc;
+    clip_colreduce_kernel<<<p->Bcol / 32, dim3(32, 16), 0, ks>>>(X + p->sc_clipM, X + p->sc_clipS, 4 * rbs, p->Bcol,
+                                                                  p->B, X + p->sc_lse_ti);
+    CUDA_TRY(cudaGetLastError());
+  } else {
+    {
+      ProfScope ps(PK_FWD_CLIP_IT, ks);
+      if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_CLIP, 2>, rbs, p->f_clip.nsplit, ks, tm, P))) return rc;
+    }
+    CUDA_TRY(cudaGetLastError());
+    // same diagonal as the image -> text launch (which may run concurrently): only that one stores it
+    fill_clip_fwd(p, P, 1, 0, S + p->st_scal, X + p->sc_pc_ti, nullptr);
+    if ((rc = fk.lane(lane++, &ks))) return rc;
+    {
+      ProfScope ps(PK_FWD_CLIP_TI, ks);
+      if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_CLIP, 2>, rbs, p->f_clip.nsplit, ks, tm, P))) return rc;
+    }
+    CUDA_TRY(cudaGetLastError());
   }
-  CUDA_TRY(cudaGetLastError());
-  // same diagonal as the image -> text launch (which may run concurrently): only that one stores it
-  fill_clip_fwd(p, P, 1, 0, S + p->st_scal, X + p->sc_pc_ti, nullptr);
-  if ((rc = fk.lane(lane++, &ks))) return rc;
-  {
-    ProfScope ps(PK_FWD_CLIP_TI, ks);
-    if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_CLIP, 2>, rbs, p->f_clip.nsplit, ks, tm, P))) return rc;
-  }
-  CUDA_TRY(cudaGetLastError());
   if ((rc = fk.join())) return rc;
 
   FinFwdArgs fa;
   fa.b = b;
-  fa.np_c = 2 * p->f_clip.nsplit;
+  fa.np_c = (p->clip_sym ? 4 : 2) * p->f_clip.nsplit;
   fa.np_s = 2 * (p->fwd_sym ? p->f_sym.nsplit : p->f_soft.nsplit);
   fa.have_soft = p->have_soft;
   fa.have_text = p->have_text;
@@ -1980,6 +2077,7 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
   fa.pc_ti = X + p->sc_pc_ti;
   fa.ps = X + p->sc_ps;
   fa.colsum = p->fwd_sym ? X + p->sc_colsum : nullptr;
+  fa.lse_ti = p->clip_sym ? X + p->sc_lse_ti : nullptr;
   fa.Bcol = p->Bcol;
   fa.diag = S + p->st_diag;
   fa.scal = S + p->st_scal;

@@ -50,6 +50,9 @@ constexpr int MODE_WCE_LSE = 6;
 constexpr int MODE_WCE_DBG = 7;
 constexpr int MODE_WCE_G = 8;
 constexpr int MODE_SOFT_SYM = 9;  // forward soft statistics, world == 1: upper block triangle + column reductions
+constexpr int MODE_CLIP_SYM = 10; // forward CLIP statistics of BOTH directions from one pass over I . T^T: row
+                                  // log-sum-exp partials as MODE_CLIP + per-warp column partials (the text -> image
+                                  // direction is the transpose: loss.py:267/273 recomputes it)
 
 // scalar block computed on device by prep_scalars_kernel (no host sync on logit_scale)
 enum {
@@ -122,6 +125,11 @@ struct FwdParams {
   // ---- symmetric forward (MODE_SOFT_SYM): column partials [6][cp_rows = 4 * row blocks][cp_pitch]
   float* colpart;
   int cp_rows, cp_pitch;
+  // ---- one-pass CLIP forward (MODE_CLIP_SYM): column partials (reference exponent, sum) [cp_rows][cp_pitch] each,
+  // and a lower bound of every row's / column's log-sum-exp: the raw diagonal dot product by global index
+  float* colM;
+  float* colS;
+  const float* dbound;
   float wlam[2];            // G mode: lambda_original, lambda_weighted
   int tri;                  // soft G, world == 1: the matrices are symmetric -> only the 256-column tiles from the
                             // row pair's own diagonal tile (index rb / 2) onwards are computed and stored, scaled
@@ -198,6 +206,22 @@ __device__ __forceinline__ float warp_colsum32(float (&x)[32], int lane) {
   return x[0];
 }
 
+// Column maxima over the 32 rows of a warp, same butterfly as warp_colsum32
+__device__ __forceinline__ float warp_colmax32(float (&x)[32], int lane) {
+#define DSOFT_CM_STAGE(O)                                               \
+  {                                                                     \
+    const bool up = (lane & O) != 0;                                    \
+    _Pragma("unroll") for (int i = 0; i < O; ++i) {                     \
+      const float send = up ? x[i] : x[i + O];                          \
+      const float keep = up ? x[i + O] : x[i];                          \
+      x[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, O));        \
+    }                                                                   \
+  }
+  DSOFT_CM_STAGE(16) DSOFT_CM_STAGE(8) DSOFT_CM_STAGE(4) DSOFT_CM_STAGE(2) DSOFT_CM_STAGE(1)
+#undef DSOFT_CM_STAGE
+  return x[0];
+}
+
 // element (local row li, column j) of a blocked fp16 logit-gradient matrix: K tiles of 64 columns, each
 // (row block, K tile) = one 16 KiB TMA box of the gradient GEMM's A operand
 __device__ __forceinline__ size_t g_index(int li, int j, int pitch) {
@@ -233,11 +257,21 @@ __device__ __forceinline__ void store_g32(__half* dst, const float (&g)[32]) {
 // soft epilogues keep the teacher strip of those 128 columns in registers across the student and text products
 // (w / E below); setmaxnreg moves the registers the producer / MMA / allocator warps do not need to the two
 // epilogue warpgroups (56 / 216 per thread).
+//
+// Epilogue warps.  Eight (two per TMEM lane quadrant, 128-column strips) everywhere except MODE_CLIP_SYM, whose
+// epilogue is a chain of short dependent steps (chunk maximum -> warp reduction -> exponentials -> 5-stage shuffle
+// butterfly): with two warps per scheduler it issued 23 % of the time and took 8200 clocks per tile against 5700 of
+// MMA time.  It runs SIXTEEN epilogue warps (four per quadrant, 64-column strips, 640 threads per CTA, <= 96
+// registers) so that four warps per scheduler hide each other's latencies.
+__host__ __device__ constexpr int fwd_epi_warps(int mode) { return mode == MODE_CLIP_SYM ? 16 : 8; }
+__host__ __device__ constexpr int fwd_threads(int mode) { return 32 * (EPI_WARP0 + fwd_epi_warps(mode)); }
+
 template <int MODE, int CG>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(fwd_threads(MODE), 1)
 dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ FwdParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_1024(smem_raw);
+  constexpr int kEpiThreads = 32 * fwd_epi_warps(MODE);
   constexpr bool kWce = (MODE >= MODE_WCE_STAT && MODE <= MODE_WCE_G);
   // "soft-like": 256-column tiles with several products per tile, staged per-column vectors, setmaxnreg
   constexpr bool kSoftMode = (MODE == MODE_SOFT || MODE == MODE_SOFT_G || MODE == MODE_SOFT_SYM || kWce);
@@ -305,7 +339,7 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     }
     for (int i = 0; i < F_SLOTS; ++i) {
       mbar_init(smem_u32(&s_full[i]), 1);
-      mbar_init(smem_u32(&s_empty[i]), CG * NUM_EPI_THREADS);
+      mbar_init(smem_u32(&s_empty[i]), CG * kEpiThreads);
     }
     mbar_init(smem_u32(a_full), 1);
     if constexpr (kSoftMode) {
@@ -548,6 +582,123 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       if (li < P.b) {
         P.part[(0 * P.npart + sp) * P.b + li] = m;
         P.part[(1 * P.npart + sp) * P.b + li] = sum;
+        if (have_dg && P.diag) P.diag[li] = dg;
+      }
+    } else if constexpr (MODE == MODE_CLIP_SYM) {
+      // ---------------------------------------------------------------- one-pass CLIP forward
+      // The text -> image logits are the transpose of the image -> text ones (loss.py:266-273), so one pass over
+      // x = s log2e (I . T^T) yields both soft-max denominators: row sums as in MODE_CLIP, and per column the sum
+      // over the 32 rows of this warp (warp_colsum32), written as a partial (reference exponent, sum) per
+      // (warp row, column); clip_colreduce_kernel combines the partials of all row blocks into the column LSEs.
+      // ONE exponential per pair serves both sums: e = 2^(x - R) with R = the maximum of the warp's 32 x 32 chunk.
+      // A term that is flushed to zero by the fp32 range (x < R - 126) is harmless as long as the log-sum-exp of
+      // its row and of its column is not far below R.  Both have an a-priori lower bound - the diagonal logit
+      // x_aa, from the dot products rinv_kernel computes next to the norms (P.dbound) - so the test
+      //   R - 80 <= min(bound of the warp's rows, bound of the chunk's columns)
+      // is warp-uniform and costs nothing; a chunk that fails it (logit scale near 100 next to a badly matched
+      // pair) takes the exact path: row sums against the row's own chunk maximum, column sums against per-column
+      // maxima (butterfly maximum, second exponential).
+      // Sixteen epilogue warps: warp w owns TMEM lanes 32 (w % 4) .. and the 64-column strip (w - 4) / 4 of the tile.
+      const int strip = (warp - EPI_WARP0) >> 2;
+      const int sp4 = split * 4 + strip;  // P.npart == 4 * nsplit
+      const float s2 = P.scal[SC_SCALE_L2];
+      const float as2 = fabsf(s2);
+      const bool live_row = li < P.b;
+      const bool real_block = rb * BM < P.b;
+      const bool tail_rows = rb * BM + q * 32 + 32 > P.b;  // warp-uniform: some rows of this warp are past b
+      const float row_lo = warp_min_f32(live_row ? P.dbound[gi] * s2 : 3.0e38f);
+      float m = M_FLOOR, sum = 0.f, dg = 0.f;
+      bool have_dg = false;
+      const size_t cp_off = static_cast<size_t>(rb * 4 + q) * P.cp_pitch;
+      float* cM = P.colM + cp_off;
+      float* cS = P.colS + cp_off;
+      // column bounds of the two chunks, fetched one tile ahead (one coalesced load per chunk and warp)
+      float bcur[2] = {0.f, 0.f}, bnxt[2] = {0.f, 0.f};
+      if (t0 < t1) {
+        bnxt[0] = __ldg(P.dbound + P.col0 + t0 * 256 + strip * 64 + lane);
+        bnxt[1] = __ldg(P.dbound + P.col0 + t0 * 256 + strip * 64 + 32 + lane);
+      }
+      int it = 0;
+      for (int t = t0; t < t1; ++t, ++it) {
+        const int slot = it % nslots;
+        const uint32_t use = static_cast<uint32_t>(it / nslots);
+        bcur[0] = bnxt[0];
+        bcur[1] = bnxt[1];
+        if (t + 1 < t1) {
+          bnxt[0] = __ldg(P.dbound + P.col0 + (t + 1) * 256 + strip * 64 + lane);
+          bnxt[1] = __ldg(P.dbound + P.col0 + (t + 1) * 256 + strip * 64 + 32 + lane);
+        }
+        mbar_wait(smem_u32(&s_full[slot]), use & 1);
+        tc_fence_after();
+        // one copy of the chunk code (no unrolling: the instruction cache matters more than the TMEM latency,
+        // which the four warps per scheduler hide); the slot goes back once the second chunk is in registers
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          const int jrel0 = t * 256 + strip * 64 + c * 32;
+          const int gj0 = P.col0 + jrel0;
+          tmem_ld32(lane_addr + slot * 256 + strip * 64 + c * 32, v);
+          if (c == 1) {
+            tc_fence_before();
+            release_slot(slot);
+          }
+          const float lo = fminf(row_lo, s2 * warp_min_f32(c ? bcur[1] : bcur[0]));
+          if (gi >= gj0 && gi < gj0 + 32) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (gj0 + e == gi) dg = v[e];
+            have_dg = true;
+          }
+          if (s2 < 0.f) {  // never in training (the model passes exp(logit_scale)); keeps x = v * as2 below
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = -v[e];
+          }
+          if (jrel0 + 32 > P.ncols || tail_rows) {  // ragged columns, rows past b: out of every sum (warp-uniform)
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (jrel0 + e >= P.ncols || !live_row) v[e] = NEG_BIG;
+          }
+          float cm[4] = {v[0], v[1], v[2], v[3]};
+#pragma unroll
+          for (int e = 4; e < 32; ++e) cm[e & 3] = fmaxf(cm[e & 3], v[e]);
+          // this row's chunk maximum in log2 units
+          const float mo = fmaxf(fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])) * as2, M_FLOOR);
+          const float mw = warp_max_f32(mo);
+          float ref = mw, csum, cmax = mw;
+          if (mw - 80.f <= lo) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              v[e] = fast_exp2(fmaf(v[e], as2, -mw));
+              acc[e & 3] += v[e];
+            }
+            csum = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+          } else {
+            ref = mo;
+            float x[32], acc = 0.f;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              x[e] = v[e] * as2;
+              acc += fast_exp2(x[e] - mo);
+              v[e] = x[e];
+            }
+            csum = acc;
+            cmax = fmaxf(warp_colmax32(x, lane), M_FLOOR);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = fast_exp2(v[e] - __shfl_sync(0xffffffffu, cmax, e));
+          }
+          const float mnew = fmaxf(m, ref);
+          sum = sum * fast_exp2(m - mnew) + csum * fast_exp2(ref - mnew);
+          m = mnew;
+          const float cs = warp_colsum32(v, lane);
+          if (real_block) {
+            cM[jrel0 + lane] = cmax;
+            cS[jrel0 + lane] = cs;
+          }
+        }
+      }
+      if (li < P.b) {
+        P.part[(0 * P.npart + sp4) * P.b + li] = m;
+        P.part[(1 * P.npart + sp4) * P.b + li] = sum;
         if (have_dg && P.diag) P.diag[li] = dg;
       }
     } else if constexpr (MODE == MODE_CLIP_G) {

@@ -445,6 +445,18 @@ __device__ __forceinline__ void setmaxnreg_dec() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
+// Warp-wide float maximum / minimum in one instruction (sm_100a: redux.sync on f32, result in a uniform register)
+__device__ __forceinline__ float warp_max_f32(float x) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float warp_min_f32(float x) {
+  float r;
+  asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 __device__ __forceinline__ float fast_log2(float x) {
   float y;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

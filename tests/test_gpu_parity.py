@@ -215,3 +215,41 @@ def test_temperature_and_scale_extremes(pkg, oracle, scale, teacher_temp, text_t
     check_against_oracle(pkg, oracle, 384, 128, 192, scale, args, seed=13)
     args = make_args(use_projection=False, teacher_temp=teacher_temp, text_student_temp=text_temp)
     check_against_oracle(pkg, oracle, 384, 128, 192, scale, args, seed=14, clustered=False)
+
+
+def test_clip_one_pass_risky_chunks(pkg, oracle):
+    """One-pass CLIP forward (MODE_CLIP_SYM): at scale 100 a 32 x 32 chunk that holds a near-duplicate pair (logit
+    ~ +144 in log2 units) next to rows / columns whose best logit is far lower cannot share one exponent reference;
+    those chunks must take the exact path (per-row and per-column maxima).  Anti-aligned and duplicate pairs are
+    planted at warp, tile and column-split boundaries."""
+    B, D, Dd = 1024, 128, 192
+    img, txt, dino = synth(21, B, D, Dd)
+    g = torch.Generator().manual_seed(5)
+    r = lambda x: x.to(torch.bfloat16).to(torch.float32)
+    for i in (0, 31, 32, 255, 256, 300, 511, 777, 1023):
+        txt[i] = r(-img[i])                      # matched pair with cosine -1: LSE lower bound far below the rest
+    for i in (1, 33, 257, 301, 640, 1022):
+        txt[i] = img[i]                          # duplicates: logit = scale
+        txt[(i + 7) % B] = r(torch.nn.functional.normalize(img[i] + 0.05 * torch.randn(D, generator=g), dim=-1))
+    check_against_oracle(pkg, oracle, B, D, Dd, 100.0, make_args(), inputs=(img, txt, dino))
+    check_against_oracle(pkg, oracle, B, D, Dd, 100.0, make_args(lambda_soft=0.0, soft_mode="none"),
+                         inputs=(img, txt, dino))
+
+
+def test_clip_one_pass_equals_two_pass(pkg, monkeypatch):
+    """Same losses and gradients whether the text -> image statistics come from the column partials of the one-pass
+    kernel or from the second (transposed) launch (DSOFT_CLIP_SYM=0)."""
+    from dinosoft_b200 import loss as loss_mod
+
+    img, txt, dino = synth(8, 1536, 512, 768)
+    res = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("DSOFT_CLIP_SYM", flag)
+        loss_mod._cuda_backend._plans.clear()     # the switch is read when a plan is created
+        _, out, gi, gt, gs = run_cuda(pkg, img, txt, dino, 40.0, make_args())
+        res.append((float(out["total_loss"]), float(out["classic_loss"]), gi.clone(), gt.clone(), float(gs)))
+    loss_mod._cuda_backend._plans.clear()
+    (t1, c1, gi1, gt1, s1), (t0, c0, gi0, gt0, s0) = res
+    assert c1 == pytest.approx(c0, rel=2e-6) and t1 == pytest.approx(t0, rel=2e-6)
+    assert rel_err(gi1, gi0)[0] < 1e-4 and rel_err(gt1, gt0)[0] < 1e-4
+    assert s1 == pytest.approx(s0, rel=1e-5, abs=1e-8)
