@@ -399,15 +399,16 @@ static EncodeTiledFn get_encode_fn() {
 
 // bf16 matrix [rows][cols] with row pitch `pitch_elems`; box = 64 columns x 128 rows, 128B swizzle.
 static int make_map(CUtensorMap* map, const void* base, int rows, int cols, size_t pitch_elems,
-                    CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, int box_rows = BM) {
+                    CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, int box_rows = BM, int box_cols = BK) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(DSOFT_ENODEV, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(pitch_elems) * 2};
-  cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   box_cols * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(DSOFT_ETMA, "cuTensorMapEncodeTiled failed (%d) base=%p rows=%d cols=%d pitch=%zu",
@@ -2142,9 +2143,10 @@ static int launch_gy(const dsoft_plan* p, const __half* G, int pitch, const __ha
 // tiles; phase 2: gradient GEMMs.  Three independent lanes on forked streams:
 //   soft (G kernel -> student GEMM -> text GEMM) | CLIP image rows (G -> GEMM) | CLIP text rows (G -> GEMM)
 // store map of a blocked fp16 G matrix: 64 columns x (row blocks * K tiles * 128) rows, box = 64 x 32, SW128
-static int make_gstore_map(const dsoft_plan* p, CUtensorMap* map, const __half* G, int pitch) {
+// box_cols = 64: one K tile x 32 rows (eight epilogue warps); 32: half a K tile (MODE_CLIP_G's sixteen warps)
+static int make_gstore_map(const dsoft_plan* p, CUtensorMap* map, const __half* G, int pitch, int box_cols = BK) {
   const int rbs = ceil_div(p->sh.b, BM);
-  return make_map(map, G, rbs * (pitch / BK) * BM, BK, BK, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 32);
+  return make_map(map, G, rbs * (pitch / BK) * BM, BK, BK, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 32, box_cols);
 }
 
 static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* S, float* X, const float* lse_loc,

@@ -262,8 +262,11 @@ __device__ __forceinline__ void store_g32(__half* dst, const float (&g)[32]) {
 // epilogue is a chain of short dependent steps (chunk maximum -> warp reduction -> exponentials -> 5-stage shuffle
 // butterfly): with two warps per scheduler it issued 23 % of the time and took 8200 clocks per tile against 5700 of
 // MMA time.  It runs SIXTEEN epilogue warps (four per quadrant, 64-column strips, 640 threads per CTA, <= 96
-// registers) so that four warps per scheduler hide each other's latencies.
-__host__ __device__ constexpr int fwd_epi_warps(int mode) { return mode == MODE_CLIP_SYM ? 16 : 8; }
+// registers) so that four warps per scheduler hide each other's latencies.  (Tried for MODE_CLIP_G as well, with
+// 32-column half-box G stores so that the staging strips still fit: 1.17 ms against 1.04 ms - dropped.)
+__host__ __device__ constexpr int fwd_epi_warps(int mode) {
+  return mode == MODE_CLIP_SYM ? 16 : 8;
+}
 __host__ __device__ constexpr int fwd_threads(int mode) { return 32 * (EPI_WARP0 + fwd_epi_warps(mode)); }
 
 template <int MODE, int CG>
