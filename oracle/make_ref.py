@@ -12,6 +12,11 @@ with the snapshot like a built .so.
 
 `load_reference()` returns the staged module or None; callers fall back to the oracle port and say so
 (`kind: "port"`).
+
+`stage_tree()` additionally stages the reference's two Python packages (`src/open_clip`, `src/open_clip_train`:
+pure Python + model-config JSON + the BPE vocabulary, 2.4 MB) as `oracle/_ref/src/` for the config-5 harness
+(`scripts/train_step_harness.py`: the reference's unmodified `create_model` / `create_loss` / `train_one_epoch`
+driven with a synthetic loader); `oracle/ref_tree.sha256` pins the files on the call path.
 """
 from __future__ import annotations
 
@@ -52,6 +57,35 @@ def stage(update: bool = False) -> str | None:
     return DST
 
 
+TREE_SRC = "/root/reference/src"
+TREE_DST = os.path.join(DST_DIR, "src")
+TREE_SUM = os.path.join(HERE, "ref_tree.sha256")
+TREE_PINNED = ["open_clip/loss.py", "open_clip/factory.py", "open_clip/model.py", "open_clip/transformer.py",
+               "open_clip_train/train.py", "open_clip_train/precision.py", "open_clip_train/distributed.py"]
+
+
+def stage_tree(update: bool = False) -> str | None:
+    """Copy src/open_clip and src/open_clip_train into oracle/_ref/src/ (when /root/reference exists) and verify
+    the pinned files.  Returns the staged `src` directory (to put on sys.path) or None."""
+    if os.path.isdir(TREE_SRC):
+        for pkg in ("open_clip", "open_clip_train"):
+            shutil.copytree(os.path.join(TREE_SRC, pkg), os.path.join(TREE_DST, pkg), dirs_exist_ok=True,
+                            ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
+        if update or not os.path.exists(TREE_SUM):
+            with open(TREE_SUM, "w") as f:
+                for rel in TREE_PINNED:
+                    f.write(_sha(os.path.join(TREE_DST, rel)) + "  src/" + rel + "\n")
+    if not os.path.isdir(os.path.join(TREE_DST, "open_clip_train")):
+        return None
+    if os.path.exists(TREE_SUM):
+        for line in open(TREE_SUM):
+            want, rel = line.split()
+            got = _sha(os.path.join(DST_DIR, rel))
+            if got != want:
+                raise RuntimeError(f"oracle/_ref/{rel} does not match oracle/ref_tree.sha256")
+    return TREE_DST
+
+
 def load_reference():
     """The staged reference module (`ClipLossWithDINOEnhancements` etc.), or None if it was never staged."""
     path = stage()
@@ -70,3 +104,4 @@ def load_reference():
 if __name__ == "__main__":
     p = stage(update="--update" in sys.argv)
     print("staged:", p, "sha256:", None if p is None else _sha(p))
+    print("staged tree:", stage_tree(update="--update" in sys.argv))

@@ -19,6 +19,7 @@ from .loss import (
     compute_student_tau,
     gather_features,
     install_into_open_clip,
+    uninstall_from_open_clip,
 )
 
 __version__ = "0.1.0"
@@ -28,6 +29,7 @@ __all__ = [
     "compute_student_tau",
     "gather_features",
     "install_into_open_clip",
+    "uninstall_from_open_clip",
     "build",
     "DinoFeatureStore",
     "DinoRows",

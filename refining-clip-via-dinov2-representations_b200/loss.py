@@ -585,6 +585,21 @@ def install_into_open_clip(open_clip_module=None):
 
     loss_mod = importlib.import_module("open_clip.loss") if open_clip_module is None else open_clip_module.loss
     factory_mod = importlib.import_module("open_clip.factory") if open_clip_module is None else open_clip_module.factory
+    if not hasattr(loss_mod, "_reference_ClipLossWithDINOEnhancements"):
+        loss_mod._reference_ClipLossWithDINOEnhancements = loss_mod.ClipLossWithDINOEnhancements
     loss_mod.ClipLossWithDINOEnhancements = ClipLossWithDINOEnhancements
     factory_mod.ClipLossWithDINOEnhancements = ClipLossWithDINOEnhancements
     return ClipLossWithDINOEnhancements
+
+
+def uninstall_from_open_clip(open_clip_module=None):
+    """Undo ``install_into_open_clip`` (A/B runs of the reference's loss and this one in one process)."""
+    import importlib
+
+    loss_mod = importlib.import_module("open_clip.loss") if open_clip_module is None else open_clip_module.loss
+    factory_mod = importlib.import_module("open_clip.factory") if open_clip_module is None else open_clip_module.factory
+    ref = getattr(loss_mod, "_reference_ClipLossWithDINOEnhancements", None)
+    if ref is not None:
+        loss_mod.ClipLossWithDINOEnhancements = ref
+        factory_mod.ClipLossWithDINOEnhancements = ref
+    return ref
