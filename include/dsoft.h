@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DSOFT_VERSION 200 /* 0.2.0 */
+#define DSOFT_VERSION 210 /* 0.2.1 */
 
 /* error codes */
 #define DSOFT_EINVAL (-1)  /* bad argument / unsupported shape            */
@@ -113,6 +113,17 @@ int dsoft_pack(const dsoft_plan_t* plan, const void* image_dev, int image_dtype,
                const void* text_dev, int text_dtype, int64_t ld_text, const void* student_dev,
                int student_dtype, int64_t ld_student, const void* dino_dev, int dino_dtype,
                int64_t ld_dino, void* gathered_dev, void* stream);
+
+/* Projection head, forward (replaces `self.image_to_dino_proj(image_features)` under train.py's bf16 autocast,
+ * loss.py:214-238 + 322-330): Linear(D -> Dp) when hidden_dim == 0 (w2/b2/hidden unused), else
+ * Linear(D -> hidden_dim) + ReLU + Linear(hidden_dim -> Dp).  Runs on the tcgen05 tile kernel with bias, ReLU and the
+ * bf16 rounding in the epilogue.  Input: the image columns of this rank's rows of `gathered` (written by dsoft_pack,
+ * which must be called with student_dev == NULL); output: the student columns of the same rows (no separate student
+ * tensor, no pack pass) and, for the MLP, hidden_dev [b][hidden_dim] bf16 (the ReLU output, needed by the caller's
+ * backward).  Weights: bf16, nn.Linear layout ([out][in], row-major); biases fp32 (may be NULL).  All dims multiples
+ * of 8, pointers 16-byte aligned.  LayerNorm / residual heads (loss.py:229-232, 331-343) stay with the caller. */
+int dsoft_head_forward(const dsoft_plan_t* plan, void* gathered_dev, const void* w1_dev, const float* b1_dev,
+                       const void* w2_dev, const float* b2_dev, int32_t hidden_dim, void* hidden_dev, void* stream);
 
 /* Column (in elements) of the DINO block inside a packed row: where dsoft_gather_rows must write when the caller
  * fills the DINO columns of `gathered` itself (dsoft_pack with dino_dev == NULL). */

@@ -1537,7 +1537,7 @@ extern "C" int dsoft_pack(const dsoft_plan_t* p, const void* image, int image_dt
                           int student_dt, int64_t ld_student, const void* dino, int dino_dt,
                           int64_t ld_dino, void* gathered, void* stream) {
   if (!p || !image || !text || !gathered) return fail(DSOFT_EINVAL, "null argument");
-  if (p->have_proj && !student) return fail(DSOFT_EINVAL, "plan has Dp > 0 but student pointer is null");
+  // student == NULL with Dp > 0: the caller fills the student columns itself (dsoft_head_forward);
   // dino == NULL with a soft term: the caller fills the DINO columns itself (dsoft_gather_rows)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* base =
@@ -1559,7 +1559,7 @@ extern "C" int dsoft_pack(const dsoft_plan_t* p, const void* image, int image_dt
   int rc;
   if ((rc = add(image, image_dt, ld_image, p->sh.D, p->offI))) return rc;
   if ((rc = add(text, text_dt, ld_text, p->sh.D, p->offT))) return rc;
-  if (p->have_proj && (rc = add(student, student_dt, ld_student, p->sh.Dp, p->offZ))) return rc;
+  if (p->have_proj && student && (rc = add(student, student_dt, ld_student, p->sh.Dp, p->offZ))) return rc;
   if ((p->have_soft || p->weighted) && dino && (rc = add(dino, dino_dt, ld_dino, p->sh.Dd, p->offD))) return rc;
   bool vec8 = reinterpret_cast<uintptr_t>(base) % 16 == 0 && a.dst_ld % 8 == 0;
   for (int k = 0; k < a.nmat; ++k) {
@@ -1942,6 +1942,71 @@ static int weighted_forward(const dsoft_plan* p, const TileMaps& tm, float* S, f
   wce_final_kernel<<<1, 1024, 0, st>>>(fa);
   CUDA_TRY(cudaGetLastError());
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// projection head, forward (loss.py:214-238, 322-347): Linear [-> ReLU -> Linear] on the tcgen05 tile kernel,
+// bias / ReLU / bf16 rounding in the epilogue, the last layer written into the student columns of `gathered`
+// ------------------------------------------------------------------------------------------------
+static int launch_linear(const dsoft_plan* p, const __nv_bfloat16* A, int a_rows, int64_t lda, int row0, int rows,
+                         int K, const __nv_bfloat16* Wt, int N, const float* bias, int relu, __nv_bfloat16* out,
+                         int64_t ld_out, cudaStream_t st) {
+  if (K % 8 || N % 8 || lda % 8 || ld_out % 8)
+    return fail(DSOFT_EINVAL, "head dims and row strides must be multiples of 8 (K=%d N=%d)", K, N);
+  if (reinterpret_cast<uintptr_t>(A) % 16 || reinterpret_cast<uintptr_t>(Wt) % 16 ||
+      reinterpret_cast<uintptr_t>(out) % 16 || (bias && reinterpret_cast<uintptr_t>(bias) % 16))
+    return fail(DSOFT_EINVAL, "head operands must be 16-byte aligned");
+  TileMaps tm;
+  int rc;
+  const CUtensorMapDataType bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  if ((rc = make_map(&tm.m[0], A, a_rows, K, static_cast<size_t>(lda), bf, 64))) return rc;
+  if ((rc = make_map(&tm.m[1], Wt, N, K, static_cast<size_t>(K), bf, 64))) return rc;
+  tm.m[2] = tm.m[3] = tm.g[0] = tm.g[1] = tm.m[0];
+  FwdParams P;
+  memset(&P, 0, sizeof(P));
+  P.nprod = 1;
+  P.a_map[0] = 0;
+  P.b_map[0] = 1;
+  P.kchunks[0] = ceil_div(K, BK);
+  P.resident = P.kchunks[0] <= 8;
+  P.bn = 2 * BN;
+  P.row0 = row0;
+  P.b = rows;
+  P.col0 = 0;
+  P.ncols = N;
+  P.ntiles = ceil_div(N, 2 * BN);
+  P.tiles_per_split = 1;
+  P.npart = 2 * P.ntiles;
+  P.lin_out = out;
+  P.lin_ld = static_cast<int>(ld_out);
+  P.lin_bias = bias;
+  P.lin_relu = relu;
+  if ((rc = set_smem(dsoft_fwd_kernel<MODE_LINEAR, 2>, FWD_SMEM_BYTES))) return rc;
+  (void)p;
+  return launch_fwd_pair(dsoft_fwd_kernel<MODE_LINEAR, 2>, ceil_div(rows, BM), P.ntiles, st, tm, P);
+}
+
+extern "C" int dsoft_head_forward(const dsoft_plan_t* p, void* gathered, const void* w1, const float* b1,
+                                  const void* w2, const float* b2, int32_t hidden_dim, void* hidden, void* stream) {
+  if (!p || !gathered || !w1) return fail(DSOFT_EINVAL, "null argument");
+  if (!p->have_proj) return fail(DSOFT_EINVAL, "the plan has no projected student (Dp == 0)");
+  const bool mlp = hidden_dim > 0;
+  if (mlp && (!w2 || !hidden)) return fail(DSOFT_EINVAL, "an MLP head needs w2 and the hidden buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* g = static_cast<__nv_bfloat16*>(gathered);
+  const int b = p->sh.b, row0 = p->sh.rank * b;
+  __nv_bfloat16* zout = g + static_cast<size_t>(row0) * p->row_elems + p->offZ;  // student columns, local rows
+  int rc;
+  if (!mlp)  // Linear(D -> Dp)
+    return launch_linear(p, g + p->offI, p->B, p->row_elems, row0, b, p->sh.D, static_cast<const __nv_bfloat16*>(w1),
+                         p->sh.Dp, b1, 0, zout, p->row_elems, st);
+  // Linear(D -> H) + ReLU -> hidden (kept for the backward), Linear(H -> Dp) -> student columns
+  __nv_bfloat16* h = static_cast<__nv_bfloat16*>(hidden);
+  if ((rc = launch_linear(p, g + p->offI, p->B, p->row_elems, row0, b, p->sh.D,
+                          static_cast<const __nv_bfloat16*>(w1), hidden_dim, b1, 1, h, hidden_dim, st)))
+    return rc;
+  return launch_linear(p, h, b, hidden_dim, 0, b, hidden_dim, static_cast<const __nv_bfloat16*>(w2), p->sh.Dp, b2, 0,
+                       zout, p->row_elems, st);
 }
 
 extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const float* logit_scale,

@@ -50,6 +50,7 @@ constexpr int MODE_WCE_LSE = 6;
 constexpr int MODE_WCE_DBG = 7;
 constexpr int MODE_WCE_G = 8;
 constexpr int MODE_SOFT_SYM = 9;  // forward soft statistics, world == 1: upper block triangle + column reductions
+constexpr int MODE_LINEAR = 11;   // projection head layer: out = act(A . W^T + bias) as bf16 (loss.py:214-238, 322-347)
 constexpr int MODE_CLIP_SYM = 10; // forward CLIP statistics of BOTH directions from one pass over I . T^T: row
                                   // log-sum-exp partials as MODE_CLIP + per-warp column partials (the text -> image
                                   // direction is the transpose: loss.py:267/273 recomputes it)
@@ -130,6 +131,11 @@ struct FwdParams {
   float* colM;
   float* colS;
   const float* dbound;
+  // ---- projection-head layer (MODE_LINEAR): out[li][j] = act(dot + bias[j]) -> bf16, j < ncols (multiple of 8)
+  __nv_bfloat16* lin_out;
+  int lin_ld;             // row stride of out in elements (multiple of 8)
+  const float* lin_bias;  // [ncols] or null
+  int lin_relu;
   float wlam[2];            // G mode: lambda_original, lambda_weighted
   int tri;                  // soft G, world == 1: the matrices are symmetric -> only the 256-column tiles from the
                             // row pair's own diagonal tile (index rb / 2) onwards are computed and stored, scaled
@@ -586,6 +592,53 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
         P.part[(0 * P.npart + sp) * P.b + li] = m;
         P.part[(1 * P.npart + sp) * P.b + li] = sum;
         if (have_dg && P.diag) P.diag[li] = dg;
+      }
+    } else if constexpr (MODE == MODE_LINEAR) {
+      // ---------------------------------------------------------------- projection-head layer
+      // Row operand = the samples (image rows of the packed buffer, or the hidden activations), column operand =
+      // the rows of the weight matrix [out features][K] (nn.Linear's layout is K-major already).  The epilogue adds
+      // the bias, applies the ReLU of the hidden layer and rounds to bf16 - the dtype torch.autocast gives the
+      // reference's nn.Linear outputs (train.py:285) and the dtype of the student operand of the Gram kernels:
+      // the second layer writes straight into the student columns of the packed buffer.
+      const bool relu = P.lin_relu != 0;
+      int it = 0;
+      for (int t = t0; t < t1; ++t, ++it) {
+        const int slot = it % nslots;
+        const uint32_t use = static_cast<uint32_t>(it / nslots);
+        mbar_wait(smem_u32(&s_full[slot]), use & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int jrel0 = t * 256 + half * 128 + c * 32;
+          tmem_ld32(lane_addr + slot * 256 + half * 128 + c * 32, v);
+          if (c == 3) {
+            tc_fence_before();
+            release_slot(slot);
+          }
+          if (li < P.b && jrel0 < P.ncols) {
+            __nv_bfloat16* orow = P.lin_out + static_cast<size_t>(li) * P.lin_ld + jrel0;
+#pragma unroll
+            for (int e8 = 0; e8 < 4; ++e8) {
+              if (jrel0 + e8 * 8 < P.ncols) {
+                float bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (P.lin_bias) {
+                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(P.lin_bias + jrel0 + e8 * 8));
+                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(P.lin_bias + jrel0 + e8 * 8 + 4));
+                  bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w;
+                  bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+                }
+                uint32_t w[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  float x0 = v[e8 * 8 + 2 * k] + bb[2 * k], x1 = v[e8 * 8 + 2 * k + 1] + bb[2 * k + 1];
+                  if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                  w[k] = pack_bf16x2(x0, x1);
+                }
+                *reinterpret_cast<uint4*>(orow + e8 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+              }
+            }
+          }
+        }
       }
     } else if constexpr (MODE == MODE_CLIP_SYM) {
       // ---------------------------------------------------------------- one-pass CLIP forward

@@ -170,6 +170,15 @@ class CudaBackend:
             "dsoft_pack",
         )
 
+    def head_forward(self, plan, gathered, w1, b1, w2, b2, hidden):
+        """Projection head on the tile kernels: image columns of `gathered` -> student columns (+ hidden)."""
+        _cabi.check(
+            self._lib.dsoft_head_forward(plan.handle, _ptr(gathered), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2),
+                                         0 if hidden is None else hidden.shape[1], _ptr(hidden),
+                                         self._stream(gathered)),
+            "dsoft_head_forward",
+        )
+
     @staticmethod
     def _lam(lambdas):
         import ctypes as C
@@ -249,7 +258,38 @@ def _gmat_fits_now(b, W, soft, text, soft_local, dev) -> bool:
 
 class _FnConfig:
     __slots__ = ("backend", "world", "rank", "group", "flags", "teacher_temp", "text_temp", "lambdas", "rho",
-                 "c_clip")
+                 "c_clip", "head_dp")
+
+
+# ---- fused projection head ----------------------------------------------------------------
+# Under bf16 autocast (how train.py:285 calls the loss) a plain Linear / Linear-ReLU-Linear head runs on the tile
+# kernels (dsoft_head_forward): bf16 operands, fp32 accumulation, bias + ReLU + bf16 rounding in the epilogue -
+# the arithmetic autocast gives nn.Linear - and its output lands in the student columns of the packed buffer, so
+# there is no student tensor, no cast and no pack pass.  The backward of the head (five small GEMMs) stays on
+# cuBLAS, issued directly from _DinoSoftFn.backward.  DSOFT_FUSED_HEAD=0 keeps the PyTorch head.
+FUSED_HEAD: Optional[bool] = None  # None: read DSOFT_FUSED_HEAD at every call (default on); True / False force it
+
+
+def _fusable_head(module, image: torch.Tensor):
+    """(w1, b1, w2, b2) of a head dsoft_head_forward can run, else None."""
+    on = FUSED_HEAD if FUSED_HEAD is not None else os.environ.get("DSOFT_FUSED_HEAD", "1") != "0"
+    if not on or module is None or image.device.type != "cuda":
+        return None
+    if not (torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16):
+        return None  # fp32 callers get fp32 nn.Linear arithmetic
+    if isinstance(module, nn.Linear):
+        lin = [module]
+    elif (isinstance(module, nn.Sequential) and len(module) == 3 and isinstance(module[0], nn.Linear)
+          and isinstance(module[1], nn.ReLU) and isinstance(module[2], nn.Linear)):
+        lin = [module[0], module[2]]
+    else:
+        return None  # LayerNorm / residual variants: PyTorch
+    for m in lin:
+        if m.bias is None or m.weight.device != image.device or m.in_features % 8 or m.out_features % 8:
+            return None
+    if len(lin) == 1:
+        return lin[0].weight, lin[0].bias, None, None
+    return lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias
 
 
 class _DinoSoftFn(torch.autograd.Function):
@@ -259,7 +299,7 @@ class _DinoSoftFn(torch.autograd.Function):
     non-differentiable diagnostics array of the weighted branch, or an empty tensor)."""
 
     @staticmethod
-    def forward(ctx, image, text, logit_scale, student, dino, cfg: _FnConfig):
+    def forward(ctx, image, text, logit_scale, student, dino, cfg: _FnConfig, w1=None, b1=None, w2=None, b2=None):
         be = cfg.backend
         dev = image.device
         b, D = image.shape
@@ -267,7 +307,8 @@ class _DinoSoftFn(torch.autograd.Function):
         soft = bool(cfg.flags & _cabi.DSOFT_F_SOFT)
         weighted = bool(cfg.flags & _cabi.DSOFT_F_WEIGHTED)
         use_dino = soft or weighted
-        needs_grad = any(ctx.needs_input_grad[:4])
+        needs_grad = any(ctx.needs_input_grad[:4]) or any(ctx.needs_input_grad[6:])
+        fused_head = w1 is not None  # the head runs inside (dsoft_head_forward); `student` is None
         flags = cfg.flags
         # the weighted branch's backward exists in the two-phase form only
         if needs_grad and (weighted or _gmat_fits(b, W, soft, bool(flags & _cabi.DSOFT_F_TEXT),
@@ -275,7 +316,8 @@ class _DinoSoftFn(torch.autograd.Function):
             flags |= _cabi.DSOFT_F_GMAT
         shape = _cabi.Shape(
             b=b, world=W, rank=r, D=D,
-            Dp=(student.shape[1] if (student is not None and soft) else 0),
+            Dp=((cfg.head_dp if fused_head else student.shape[1]) if ((student is not None or fused_head) and soft)
+                else 0),
             Dd=(dino.shape[1] if (dino is not None and use_dino) else 0),
             flags=flags, teacher_temp=cfg.teacher_temp, text_temp=cfg.text_temp, rho=cfg.rho, c_clip=cfg.c_clip,
         )
@@ -284,6 +326,14 @@ class _DinoSoftFn(torch.autograd.Function):
         lazy_dino = isinstance(dino, DinoRows)
         be.pack(plan, image.detach(), text.detach(), None if student is None or not soft else student.detach(),
                 None if (dino is None or not use_dino or lazy_dino) else dino.detach(), gathered)
+        hidden = w1b = w2b = None
+        if fused_head:
+            w1b = w1.detach().to(torch.bfloat16)
+            w2b = None if w2 is None else w2.detach().to(torch.bfloat16)
+            if w2 is not None:
+                hidden = torch.empty((b, w1.shape[0]), dtype=torch.bfloat16, device=dev)
+            be.head_forward(plan, gathered, w1b, b1.detach().float(), w2b,
+                            None if b2 is None else b2.detach().float(), hidden)
         if lazy_dino and use_dino:
             # device feature store: the rows are gathered by index straight into the DINO columns of the packed
             # buffer (range check on the device), replacing train.py:250-280's CPU gather + H2D copy
@@ -301,8 +351,9 @@ class _DinoSoftFn(torch.autograd.Function):
         if W > 1 and needs_grad:
             # column-side soft-max statistics of the other ranks' rows (5 floats per sample)
             dist.all_gather_into_tensor(lse_all.view(-1), lse_all[r].view(-1), group=cfg.group)
-        ctx.save_for_backward(gathered, state, lse_all)
+        ctx.save_for_backward(gathered, state, lse_all, hidden, w1b, w2b)
         ctx.plan, ctx.cfg = plan, cfg
+        ctx.fused_head = fused_head
         ctx.meta = (image.dtype, text.dtype, logit_scale.dtype, logit_scale.shape,
                     None if student is None else student.dtype, b, D, shape.Dp)
         ctx.mark_non_differentiable(dbg)
@@ -311,7 +362,7 @@ class _DinoSoftFn(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, gout, _gdbg=None):
-        gathered, state, lse_all = ctx.saved_tensors
+        gathered, state, lse_all, hidden, w1b, w2b = ctx.saved_tensors
         plan, be = ctx.plan, ctx.cfg.backend
         idt, tdt, sdt, sshape, zdt, b, D, Dp = ctx.meta
         dev = gathered.device
@@ -338,7 +389,23 @@ class _DinoSoftFn(torch.autograd.Function):
         g_student = None
         if zdt is not None:
             g_student = d_student.to(zdt) if d_student is not None else None
-        return (d_image.to(idt), d_text.to(tdt), d_scale.reshape(sshape).to(sdt), g_student, None, None)
+        g_head = (None, None, None, None)
+        if ctx.fused_head:
+            # head backward in the arithmetic autocast gives the reference (bf16 operands, fp32 accumulation), on
+            # cuBLAS: dZ -> (dW2, db2, dH) -> ReLU mask -> (dW1, db1, dX); dX joins d_image
+            s = plan.shape
+            r0 = s.rank * b
+            x = gathered[r0:r0 + b, :D]  # image columns of this rank's rows (strided view)
+            dz = d_student.to(torch.bfloat16)
+            if w2b is None:
+                g_head = ((dz.t() @ x).float(), d_student.sum(0), None, None)
+                d_image += (dz @ w1b).float()
+            else:
+                dh = torch.ops.aten.threshold_backward(dz @ w2b, hidden, 0.0)
+                g_head = ((dh.t() @ x).float(), dh.sum(0, dtype=torch.float32), (dz.t() @ hidden).float(),
+                          d_student.sum(0))
+                d_image += (dh @ w1b).float()
+        return (d_image.to(idt), d_text.to(tdt), d_scale.reshape(sshape).to(sdt), g_student, None, None) + g_head
 
 
 # --------------------------------------------------------------------------------------------------
@@ -504,12 +571,15 @@ class ClipLossWithDINOEnhancements(nn.Module):
 
         # ----- projection head (loss.py:322-347); stays in PyTorch/cuBLAS, its output is the student operand
         student = None
+        head = None
         if dino_features is not None and use_projection:
             self.init_proj(
                 embed_dim=image_features.size(-1), dino_dim=dino_features.size(-1), device=device,
                 projection_type=projection_type, layernorm=use_layernorm,
             )
-            if soft_on:
+            if soft_on and not residual_projection and self._backend is None:
+                head = _fusable_head(self.image_to_dino_proj, image_features)
+            if soft_on and head is None:
                 raw_proj = self.image_to_dino_proj(image_features)
                 student = raw_proj
                 if residual_projection and raw_proj.shape == image_features.shape:
@@ -551,10 +621,15 @@ class ClipLossWithDINOEnhancements(nn.Module):
         cfg.lambdas = (lambda_original, lambda_soft if soft_on else 0.0, text_lambda,
                        lambda_weighted if weighted_on else 0.0)
         cfg.rho, cfg.c_clip = float(g(args, "rho", 0.1)), float(g(args, "c_clip", 1.0))
+        cfg.head_dp = 0
+        head_args = (None, None, None, None)
+        if student is None and dino_features is not None and use_projection and soft_on and head is not None:
+            cfg.head_dp = (head[2] if head[2] is not None else head[0]).shape[0]
+            head_args = head
 
         terms, dbg_arr = _DinoSoftFn.apply(
             image_features, text_features, logit_scale, student,
-            dino_features if (soft_on or weighted_on) else None, cfg
+            dino_features if (soft_on or weighted_on) else None, cfg, *head_args
         )
         classic_loss = terms[0]
         soft_loss = terms[3] if soft_on else torch.zeros((), device=device)

@@ -100,7 +100,7 @@ def build(a, dev, rank, world):
         local_loss=True, gather_with_grad=True, rank=rank, world_size=world, horovod=False,
         # train_one_epoch (train.py:145-586)
         device=str(dev), precision=a.precision, accum_freq=1, skip_scheduler=True, grad_clip_norm=None,
-        batch_size=a.batch, log_every_n_steps=10 ** 9, local_rank=dev.index, use_mlflow=False, warmup=0,
+        batch_size=a.batch, log_every_n_steps=getattr(a, "log_every", 10 ** 9), local_rank=dev.index, use_mlflow=False, warmup=0,
         enable_warmup_dino_hyperparams=False, _precomputed_dino=table, _dino_on_device=False,
         distributed=world > 1, val_frequency=0, epochs=1, wandb=False, save_logs=False,
         # DINO-Soft knobs (params.py:58-203; thesis sweep values sweep_manual.sh:30-46)

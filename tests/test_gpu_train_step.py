@@ -25,7 +25,7 @@ def test_train_one_epoch_reference_loss_vs_dropin(pkg):
     runs = {}
     for which in ("reference", "ours"):
         a = types.SimpleNamespace(loss=which, model="ViT-B-32", batch=64, steps=3, precision="fp32", dino_dim=768,
-                                  image_size=224)
+                                  image_size=224, log_every=1)
         T, model, loss, opt, data, args = H.build(a, dev, 0, 1)
         assert type(loss).__module__.startswith("dinosoft_b200") == (which == "ours"), type(loss)
         logs = T.train_one_epoch(model, data, loss, 0, opt, None, None, None, None, None, args)
