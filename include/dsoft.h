@@ -125,6 +125,20 @@ int dsoft_pack(const dsoft_plan_t* plan, const void* image_dev, int image_dtype,
 int dsoft_head_forward(const dsoft_plan_t* plan, void* gathered_dev, const void* w1_dev, const float* b1_dev,
                        const void* w2_dev, const float* b2_dev, int32_t hidden_dim, void* hidden_dev, void* stream);
 
+/* CLIP-blind pair statistics (replaces the cs / ds matrices, masks and counts of
+ * src/open_clip_train/helpers.py:221-285, `_pair_stats`).  Over the pairs i < j of n L2-normalised rows:
+ *   counts_dev[2 k + 0] += #{cs_ij >= cmin[k]},  counts_dev[2 k + 1] += #{cs_ij >= cmin[k] and ds_ij <= dmax[k]}
+ * (k < n_thr <= 8; cmin / dmax are HOST arrays; counts_dev = NULL skips the counting) and every pair with
+ * cs_ij - ds_ij >= gap_floor is appended to cand_dev as 4 x 32 bit {int i, int j, float cs, float ds} (order
+ * unspecified; *cand_count_dev counts ALL qualifying pairs, only the first cand_cap are stored; cand_cap = 0 skips the
+ * collection).  The caller zeroes counts_dev and *cand_count_dev.  cs = clip_a . clip_b^T, ds = dino_a . dino_b^T,
+ * bf16 operands [n][k] row-major with fp32 accumulation: pass a == b for bf16 features, or the split pair
+ * a = [hi | lo | hi], b = [hi | hi | lo] (k = 3 d) for fp32 features at ~1e-5 cosine accuracy. */
+int dsoft_pair_stats(const void* clip_a_dev, const void* clip_b_dev, int32_t k_clip, const void* dino_a_dev,
+                     const void* dino_b_dev, int32_t k_dino, int32_t n, const float* cmin, const float* dmax,
+                     int32_t n_thr, unsigned long long* counts_dev, float gap_floor, void* cand_dev,
+                     uint32_t cand_cap, uint32_t* cand_count_dev, void* stream);
+
 /* Column (in elements) of the DINO block inside a packed row: where dsoft_gather_rows must write when the caller
  * fills the DINO columns of `gathered` itself (dsoft_pack with dino_dev == NULL). */
 size_t dsoft_plan_dino_col_offset(const dsoft_plan_t* plan);

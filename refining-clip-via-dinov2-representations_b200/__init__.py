@@ -6,6 +6,7 @@ Import as ``dinosoft_b200`` (see the shim at the repo root).  Contents:
                  compute_student_tau, install_into_open_clip
     feature_store.py  device-resident DINO feature store: bf16 table in HBM, gather kernel with on-device range
                  check writing straight into the packed operand buffer
+    pair_stats.py  CLIP-blind pair statistics on the Gram-tile kernel (helpers.py:221-285)
     _cabi.py     ctypes binding of libdsoft.so (include/dsoft.h)
     _build.py    nvcc recipe for csrc/ (sm_100a only)
     csrc/        hand-written tcgen05 / TMEM / TMA kernels + the C ABI
@@ -13,6 +14,7 @@ Import as ``dinosoft_b200`` (see the shim at the repo root).  Contents:
 from . import _build, _cabi
 from ._build import build
 from .feature_store import DinoFeatureStore, DinoRows, lookup as dino_lookup, to_device_table
+from .pair_stats import pair_stats
 from .loss import (
     ClipLossWithDINOEnhancements,
     CudaBackend,
@@ -35,4 +37,5 @@ __all__ = [
     "DinoRows",
     "to_device_table",
     "dino_lookup",
+    "pair_stats",
 ]

@@ -2009,6 +2009,62 @@ extern "C" int dsoft_head_forward(const dsoft_plan_t* p, void* gathered, const v
                        zout, p->row_elems, st);
 }
 
+// ------------------------------------------------------------------------------------------------
+// CLIP-blind pair statistics (open_clip_train/helpers.py:221-285, _pair_stats) on the Gram-tile kernel
+// ------------------------------------------------------------------------------------------------
+extern "C" int dsoft_pair_stats(const void* clip_a, const void* clip_b, int32_t k_clip, const void* dino_a,
+                                const void* dino_b, int32_t k_dino, int32_t n, const float* cmin, const float* dmax,
+                                int32_t n_thr, unsigned long long* counts, float gap_floor, void* cand,
+                                uint32_t cand_cap, uint32_t* cand_count, void* stream) {
+  if (!clip_a || !clip_b || !dino_a || !dino_b || !cand_count) return fail(DSOFT_EINVAL, "null argument");
+  if (n <= 1 || k_clip <= 0 || k_dino <= 0 || k_clip % 8 || k_dino % 8)
+    return fail(DSOFT_EINVAL, "need n > 1 and feature widths that are positive multiples of 8 (n=%d, %d, %d)", n,
+                k_clip, k_dino);
+  if (n_thr < 0 || n_thr > 8 || (n_thr > 0 && (!cmin || !dmax)))
+    return fail(DSOFT_EINVAL, "at most 8 threshold pairs (got %d)", n_thr);
+  if (cand_cap > 0 && !cand) return fail(DSOFT_EINVAL, "cand_cap > 0 needs a candidate buffer");
+  for (const void* q : {clip_a, clip_b, dino_a, dino_b})
+    if (reinterpret_cast<uintptr_t>(q) % 16) return fail(DSOFT_EINVAL, "operands must be 16-byte aligned");
+  int sms = 0, rc = query_num_sms(&sms);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TileMaps tm;
+  const CUtensorMapDataType bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  if ((rc = make_map(&tm.m[0], clip_a, n, k_clip, static_cast<size_t>(k_clip), bf, 64))) return rc;
+  if ((rc = make_map(&tm.m[1], clip_b, n, k_clip, static_cast<size_t>(k_clip), bf, 64))) return rc;
+  if ((rc = make_map(&tm.m[2], dino_a, n, k_dino, static_cast<size_t>(k_dino), bf, 64))) return rc;
+  if ((rc = make_map(&tm.m[3], dino_b, n, k_dino, static_cast<size_t>(k_dino), bf, 64))) return rc;
+  tm.g[0] = tm.g[1] = tm.m[0];
+  FwdParams P;
+  memset(&P, 0, sizeof(P));
+  P.nprod = 2;
+  P.a_map[0] = 0; P.b_map[0] = 1; P.kchunks[0] = ceil_div(k_clip, BK);
+  P.a_map[1] = 2; P.b_map[1] = 3; P.kchunks[1] = ceil_div(k_dino, BK);
+  P.bn = 2 * BN;
+  P.row0 = 0;
+  P.b = n;
+  P.col0 = 0;
+  P.ncols = n;
+  P.ntiles = ceil_div(n, 2 * BN);
+  P.tri = 1;  // upper block triangle: pairs i < j
+  P.tiles_per_split = std::max(4, ceil_div(P.ntiles, 10));
+  const int nsplit = ceil_div(P.ntiles, P.tiles_per_split);
+  P.npart = 2 * nsplit;
+  P.ncolvec = 0;
+  P.pr_nthr = counts ? n_thr : 0;
+  for (int k = 0; k < n_thr; ++k) {
+    P.pr_cmin[k] = cmin[k];
+    P.pr_dmax[k] = dmax[k];
+  }
+  P.pr_counts = (counts && n_thr > 0) ? counts : nullptr;
+  P.pr_gap_floor = cand_cap > 0 ? gap_floor : 3.0e38f;
+  P.pr_cand = static_cast<float4*>(cand);
+  P.pr_cand_cap = cand_cap;
+  P.pr_cand_count = cand_count;
+  if ((rc = set_smem(dsoft_fwd_kernel<MODE_PAIRS, 2>, FWD_SMEM_BYTES))) return rc;
+  return launch_fwd_pair(dsoft_fwd_kernel<MODE_PAIRS, 2>, ceil_div(n, BM), nsplit, st, tm, P);
+}
+
 extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const float* logit_scale,
                              const float* lambdas, void* state, void* scratch, float* lse_local,
                              float* losses, float* dbg, void* stream) {

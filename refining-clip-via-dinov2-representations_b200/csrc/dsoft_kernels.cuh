@@ -51,6 +51,8 @@ constexpr int MODE_WCE_DBG = 7;
 constexpr int MODE_WCE_G = 8;
 constexpr int MODE_SOFT_SYM = 9;  // forward soft statistics, world == 1: upper block triangle + column reductions
 constexpr int MODE_LINEAR = 11;   // projection head layer: out = act(A . W^T + bias) as bf16 (loss.py:214-238, 322-347)
+constexpr int MODE_PAIRS = 12;    // CLIP-blind pair statistics (open_clip_train/helpers.py:221-285): threshold counts
+                                  // and candidate pairs over the upper triangle of two Gram matrices
 constexpr int MODE_CLIP_SYM = 10; // forward CLIP statistics of BOTH directions from one pass over I . T^T: row
                                   // log-sum-exp partials as MODE_CLIP + per-warp column partials (the text -> image
                                   // direction is the transpose: loss.py:267/273 recomputes it)
@@ -131,6 +133,14 @@ struct FwdParams {
   float* colM;
   float* colS;
   const float* dbound;
+  // ---- pair statistics (MODE_PAIRS): products [0] CLIP Gram, [1] DINO Gram of L2-normalised rows, pairs i < j
+  int pr_nthr;                    // threshold pairs (<= 8)
+  float pr_cmin[8], pr_dmax[8];   // count cs >= cmin, and cs >= cmin && ds <= dmax
+  unsigned long long* pr_counts;  // [8][2] (clip-high, blind), or null: skip the counting
+  float pr_gap_floor;             // pairs with cs - ds >= floor are appended to pr_cand (i, j, cs, ds)
+  float4* pr_cand;
+  unsigned int pr_cand_cap;
+  unsigned int* pr_cand_count;    // total number of qualifying pairs (may exceed the capacity)
   // ---- projection-head layer (MODE_LINEAR): out[li][j] = act(dot + bias[j]) -> bf16, j < ncols (multiple of 8)
   __nv_bfloat16* lin_out;
   int lin_ld;             // row stride of out in elements (multiple of 8)
@@ -283,7 +293,8 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   constexpr int kEpiThreads = 32 * fwd_epi_warps(MODE);
   constexpr bool kWce = (MODE >= MODE_WCE_STAT && MODE <= MODE_WCE_G);
   // "soft-like": 256-column tiles with several products per tile, staged per-column vectors, setmaxnreg
-  constexpr bool kSoftMode = (MODE == MODE_SOFT || MODE == MODE_SOFT_G || MODE == MODE_SOFT_SYM || kWce);
+  constexpr bool kPairs = (MODE == MODE_PAIRS);  // two products per tile like the weighted-CE passes, no column vectors
+  constexpr bool kSoftMode = (MODE == MODE_SOFT || MODE == MODE_SOFT_G || MODE == MODE_SOFT_SYM || kWce || kPairs);
   static_assert(!kSoftMode || CG == 2, "the soft modes are written for CTA pairs");
   // streaming mode: stages of (A box | B boxes); resident mode: 8 A boxes, then B-only stages
   const bool resident = P.resident != 0;
@@ -399,11 +410,11 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
         mbar_wait(smem_u32(&col_empty[cb]), ((static_cast<uint32_t>(n / COL_BUFS)) & 1) ^ 1);
         if (elect_one()) {
           const uint32_t full = smem_u32(&col_full[cb]);
-          const int nvec = kWce ? P.ncolvec : (MODE == MODE_SOFT_G ? 2 : 1) * P.nprod;
+          const int nvec = (kWce || kPairs) ? P.ncolvec : (MODE == MODE_SOFT_G ? 2 : 1) * P.nprod;
           mbar_arrive_expect_tx(full, nvec * CT * 4);
           float* dst = colbuf + cb * COL_VECS * CT;
           const size_t c0 = static_cast<size_t>(P.col0) + static_cast<size_t>(t) * CT;
-          if constexpr (kWce) {
+          if constexpr (kWce || kPairs) {
             for (int k = 0; k < P.ncolvec; ++k) bulk_copy_g2s(smem_u32(dst + k * CT), P.colvec[k] + c0, CT * 4, full);
           } else {
             for (int p = 0; p < P.nprod; ++p) {
@@ -592,6 +603,101 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
         P.part[(0 * P.npart + sp) * P.b + li] = m;
         P.part[(1 * P.npart + sp) * P.b + li] = sum;
         if (have_dg && P.diag) P.diag[li] = dg;
+      }
+    } else if constexpr (kPairs) {
+      // ---------------------------------------------------------------- CLIP-blind pair statistics
+      // helpers.py:221-285 (_pair_stats): cs = Z Z^T, ds = D D^T for L2-normalised rows, over the pairs i < j:
+      // how many have cs >= cmin, how many of those have ds <= dmax ("blind": CLIP calls them similar, DINOv2 does
+      // not), and the pairs with the largest gap cs - ds.  Upper block triangle only (P.tri); the CLIP tile waits
+      // in registers for the DINO tile; counts are exact integers (warp sum -> one 64-bit atomic per warp at the
+      // end); candidates above the gap floor are appended through one warp-aggregated atomic per chunk.
+      float xq[128];
+      unsigned int chi[8], cbl[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) chi[k] = cbl[k] = 0u;
+      const bool live_row = li < P.b;
+      const bool counting = P.pr_counts != nullptr;
+      const float floor_gap = P.pr_gap_floor;
+      int it = 0;
+      for (int t = t0; t < t1; ++t, it += 2) {
+        const int jt0 = t * CT + half * 128;
+        const int cb = (t - t0) % COL_BUFS;
+        mbar_wait(smem_u32(&col_full[cb]), static_cast<uint32_t>((t - t0) / COL_BUFS) & 1);
+        {  // ---- CLIP Gram tile -> xq
+          const int slot = it % 2;
+          mbar_wait(smem_u32(&s_full[slot]), static_cast<uint32_t>(it / 2) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            tmem_ld32(lane_addr + slot * CT + half * 128 + c * 32, v);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) xq[c * 32 + e] = v[e];
+          }
+          tc_fence_before();
+          release_slot(slot);
+        }
+        {  // ---- DINO Gram tile
+          const int slot = (it + 1) % 2;
+          mbar_wait(smem_u32(&s_full[slot]), static_cast<uint32_t>((it + 1) / 2) & 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            const int jrel0 = jt0 + c * 32;
+            tmem_ld32(lane_addr + slot * CT + half * 128 + c * 32, v);
+            if (c == 3) {
+              tc_fence_before();
+              release_slot(slot);
+            }
+            // pairs i < j only; the whole chunk is out when its last column is not right of the warp's first row
+            if (jrel0 + 31 <= gw0 || jrel0 >= P.ncols) continue;  // warp-uniform
+            const bool edge = jrel0 <= gw0 + 31 || jrel0 + 32 > P.ncols || !live_row ||
+                              rb * BM + q * 32 + 32 > P.b;      // warp-uniform: some entries need the mask
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              // the chunk's CLIP values sit at a runtime offset of xq: select them with a static index
+              const float cs = (c == 0) ? xq[e] : (c == 1) ? xq[32 + e] : (c == 2) ? xq[64 + e] : xq[96 + e];
+              const float ds = v[e];
+              const bool ok = !edge || (jrel0 + e > gi && jrel0 + e < P.ncols && live_row);
+              if (counting) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  if (k < P.pr_nthr) {
+                    const bool hi = ok && cs >= P.pr_cmin[k];
+                    chi[k] += hi ? 1u : 0u;
+                    cbl[k] += (hi && ds <= P.pr_dmax[k]) ? 1u : 0u;
+                  }
+                }
+              }
+              const bool cand = ok && (cs - ds) >= floor_gap;
+              const unsigned int mask = __ballot_sync(0xffffffffu, cand);
+              if (mask) {
+                unsigned int base = 0;
+                const int leader = __ffs(mask) - 1;
+                if (lane == leader) base = atomicAdd(P.pr_cand_count, __popc(mask));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (cand) {
+                  const unsigned int idx = base + __popc(mask & ((1u << lane) - 1u));
+                  if (idx < P.pr_cand_cap)
+                    P.pr_cand[idx] = make_float4(__int_as_float(gi), __int_as_float(jrel0 + e), cs, ds);
+                }
+              }
+            }
+          }
+        }
+        mbar_arrive(smem_u32(&col_empty[cb]));
+      }
+      if (counting) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (k < P.pr_nthr) {
+            const unsigned int a = __reduce_add_sync(0xffffffffu, chi[k]);
+            const unsigned int bsum = __reduce_add_sync(0xffffffffu, cbl[k]);
+            if (lane == 0) {
+              if (a) atomicAdd(P.pr_counts + 2 * k + 0, static_cast<unsigned long long>(a));
+              if (bsum) atomicAdd(P.pr_counts + 2 * k + 1, static_cast<unsigned long long>(bsum));
+            }
+          }
+        }
       }
     } else if constexpr (MODE == MODE_LINEAR) {
       // ---------------------------------------------------------------- projection-head layer

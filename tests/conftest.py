@@ -40,4 +40,5 @@ def pkg():
 
 
 def golden_files():
-    return sorted(f for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+    """Fixtures of the loss path (w<world>_*.npz); other fixtures (pair_stats_*) have their own tests."""
+    return sorted(f for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f.startswith("w"))
