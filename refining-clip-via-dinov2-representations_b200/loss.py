@@ -664,6 +664,18 @@ def install_into_open_clip(open_clip_module=None):
         loss_mod._reference_ClipLossWithDINOEnhancements = loss_mod.ClipLossWithDINOEnhancements
     loss_mod.ClipLossWithDINOEnhancements = ClipLossWithDINOEnhancements
     factory_mod.ClipLossWithDINOEnhancements = ClipLossWithDINOEnhancements
+    if hasattr(loss_mod, "CyCLIPLoss"):  # the CyCLIP drop-in (factory.py:537-549; train.py:316 isinstance check)
+        from .cyclip import CyCLIPLoss
+
+        if not hasattr(loss_mod, "_reference_CyCLIPLoss"):
+            loss_mod._reference_CyCLIPLoss = loss_mod.CyCLIPLoss
+        loss_mod.CyCLIPLoss = CyCLIPLoss
+        factory_mod.CyCLIPLoss = CyCLIPLoss
+        import sys
+
+        train_mod = sys.modules.get("open_clip_train.train")  # train.py:16 binds the name at import, :316 isinstance
+        if train_mod is not None and hasattr(train_mod, "CyCLIPLoss"):
+            train_mod.CyCLIPLoss = CyCLIPLoss
     return ClipLossWithDINOEnhancements
 
 
@@ -677,4 +689,13 @@ def uninstall_from_open_clip(open_clip_module=None):
     if ref is not None:
         loss_mod.ClipLossWithDINOEnhancements = ref
         factory_mod.ClipLossWithDINOEnhancements = ref
+    cyc = getattr(loss_mod, "_reference_CyCLIPLoss", None)
+    if cyc is not None:
+        loss_mod.CyCLIPLoss = cyc
+        factory_mod.CyCLIPLoss = cyc
+        import sys
+
+        train_mod = sys.modules.get("open_clip_train.train")
+        if train_mod is not None and hasattr(train_mod, "CyCLIPLoss"):
+            train_mod.CyCLIPLoss = cyc
     return ref
