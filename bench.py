@@ -375,6 +375,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # --graph: forward and backward replay CUDA graphs (dinosoft_b200.make_graphed, the package's public helper for
+    # the launch-bound small-batch regime); the per-kernel pass below stays eager (it needs the host-side recorder)
+    eager_step = step
+    if args.graph:
+        gstep = pkg.make_graphed(loss, larg, img, txt, scale, dino, autocast_dtype=torch.bfloat16)
+
+        def step(im, tx, dn):  # noqa: F811
+            t, c, s = gstep(im, tx, scale, dn)
+            t.backward()
+            return {"total_loss": t, "classic_loss": c, "soft_loss": s}
+
     # ---- warm-up
     for _ in range(max(args.warmup, 3)):
         zero_grads()
@@ -405,7 +416,7 @@ def run_ours(args):
     p0.record()
     for _ in range(prof_steps):
         zero_grads()
-        step(img, txt, dino)
+        eager_step(img, txt, dino)
     p1.record()
     barrier()
     ms_serial = p0.elapsed_time(p1)
@@ -556,7 +567,7 @@ def run_ours(args):
             "metric": METRIC, "value": GLOBAL_B * args.steps / (ms / 1e3), "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": workload_config(world),
+            "config": dict(workload_config(world), graphed=bool(args.graph)),
             "backward_impl": ("two-phase: fp16 logit-gradient matrices + M=256xN=256 gradient GEMMs"
                               + (", symmetric shortcuts (world 1)" if world == 1 else "")
                               if plan.shape.flags & _cabi.DSOFT_F_GMAT else
@@ -610,6 +621,8 @@ def main():
     ap.add_argument("--clip-dim", type=int, default=512, help="CLIP embedding dim D (config 4: 768)")
     ap.add_argument("--dino-dim", type=int, default=768, help="DINOv2 feature dim (config 4: 1024)")
     ap.add_argument("--no-head", action="store_true", help="student = image features (no projection head)")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the loss forward / backward as CUDA graphs (dinosoft_b200.make_graphed)")
     args = ap.parse_args()
     GLOBAL_B, D_CLIP, D_DINO, USE_HEAD = args.batch, args.clip_dim, args.dino_dim, not args.no_head
     if args.impl == "reference":

@@ -8,6 +8,7 @@ Import as ``dinosoft_b200`` (see the shim at the repo root).  Contents:
                  check writing straight into the packed operand buffer
     cyclip.py    CyCLIPLoss drop-in (loss.py:813-905): CLIP term on the kernels, consistency terms through D x D
                  moment matrices
+    graphed.py   CUDA-graph capture of the loss forward + backward (launch-bound small batches)
     pair_stats.py  CLIP-blind pair statistics on the Gram-tile kernel (helpers.py:221-285)
     _cabi.py     ctypes binding of libdsoft.so (include/dsoft.h)
     _build.py    nvcc recipe for csrc/ (sm_100a only)
@@ -17,6 +18,7 @@ from . import _build, _cabi
 from ._build import build
 from .feature_store import DinoFeatureStore, DinoRows, lookup as dino_lookup, to_device_table
 from .cyclip import CyCLIPLoss
+from .graphed import make_graphed
 from .pair_stats import pair_stats
 from .loss import (
     ClipLossWithDINOEnhancements,
@@ -42,4 +44,5 @@ __all__ = [
     "dino_lookup",
     "pair_stats",
     "CyCLIPLoss",
+    "make_graphed",
 ]
