@@ -86,3 +86,31 @@ def test_two_gpu_parity(oracle, ctor, argd, gmat):
             print(f"[parity-w2] rank {r} {k}: linf={linf:.2e} l2={l2:.2e}")
             assert linf < 1e-3 and l2 < 1e-3, (r, k, linf, l2)
         assert o["d_scale"] == pytest.approx(want["d_logit_scale"], rel=1e-3, abs=1e-7)
+
+
+def test_eight_gpu_parity(oracle):
+    """BASELINE config 3's sharding (8 ranks, gather_with_grad + row-block local_loss, global soft scope) over
+    NCCL: every rank's loss terms and gradients against the oracle of the concatenated batch."""
+    if torch.cuda.device_count() < 8:
+        pytest.skip("needs 8 GPUs")
+    ctor = dict(local_loss=True, gather_with_grad=True, soft_scope="global")
+    argd = dict(use_projection=True)
+    B, D, Dd, scale, world = 2048, 128, 192, 30.0, 8
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), B, D, Dd, scale, argd, ctor, ret, "always"), nprocs=world, join=True)
+    args = make_args(**argd)
+    img, txt, dino = synth(21, B, D, Dd)
+    cfg = oracle_cfg(oracle, args, world_size=world, local_loss=True, gather_with_grad=True, soft_scope="global",
+                     round_student_bf16=True)
+    ref = oracle.loss_and_grads(img, txt, scale, dino, cfg, proj_params=ret[0]["head"],
+                                projection_type=args.projection_type)["ranks"]
+    for r in range(world):
+        o, want = ret[r], ref[r]
+        assert o["total"] == pytest.approx(want["total_loss"], rel=1e-4)
+        assert o["soft"] == pytest.approx(want["soft_loss"], rel=1e-4)
+        for k in ("d_image", "d_text"):
+            linf, l2 = rel_err(o[k], want[k])
+            print(f"[parity-w8] rank {r} {k}: linf={linf:.2e} l2={l2:.2e}")
+            assert linf < 1e-3 and l2 < 1e-3, (r, k, linf, l2)
+        assert o["d_scale"] == pytest.approx(want["d_logit_scale"], rel=1e-3, abs=1e-7)
