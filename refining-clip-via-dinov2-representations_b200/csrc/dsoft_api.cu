@@ -1975,15 +1975,18 @@ static int launch_linear(const dsoft_plan* p, const __nv_bfloat16* A, int a_rows
   P.col0 = 0;
   P.ncols = N;
   P.ntiles = ceil_div(N, 2 * BN);
-  P.tiles_per_split = 1;
-  P.npart = 2 * P.ntiles;
+  // enough row pairs to fill the machine: one CTA pair walks all N tiles of its rows (the row operand is loaded
+  // once and tile t's epilogue overlaps tile t+1's MMAs); few row pairs (small per-rank batches): one tile per CTA
+  const int pairs = ceil_div(ceil_div(rows, BM), 2);
+  P.tiles_per_split = (2 * pairs >= p->num_sms) ? P.ntiles : 1;
+  const int nsplit = ceil_div(P.ntiles, P.tiles_per_split);
+  P.npart = 2 * nsplit;
   P.lin_out = out;
   P.lin_ld = static_cast<int>(ld_out);
   P.lin_bias = bias;
   P.lin_relu = relu;
   if ((rc = set_smem(dsoft_fwd_kernel<MODE_LINEAR, 2>, FWD_SMEM_BYTES))) return rc;
-  (void)p;
-  return launch_fwd_pair(dsoft_fwd_kernel<MODE_LINEAR, 2>, ceil_div(rows, BM), P.ntiles, st, tm, P);
+  return launch_fwd_pair(dsoft_fwd_kernel<MODE_LINEAR, 2>, ceil_div(rows, BM), nsplit, st, tm, P);
 }
 
 extern "C" int dsoft_head_forward(const dsoft_plan_t* p, void* gathered, const void* w1, const float* b1,
