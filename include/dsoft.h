@@ -125,6 +125,28 @@ int dsoft_pack(const dsoft_plan_t* plan, const void* image_dev, int image_dtype,
 int dsoft_head_forward(const dsoft_plan_t* plan, void* gathered_dev, const void* w1_dev, const float* b1_dev,
                        const void* w2_dev, const float* b2_dev, int32_t hidden_dim, void* hidden_dev, void* stream);
 
+/* Symmetric soft tiles across ranks (world > 1, global soft scope, gather_with_grad, DSOFT_F_GMAT, local batch a
+ * multiple of 512; environment DSOFT_SYM_W=0 switches it off).  The teacher / student / text Gram matrices are
+ * symmetric, so each pair of row blocks is computed by ONE of its two ranks, and what belongs to the other rank's
+ * rows is exchanged by the caller - the reduce-scatter of the gathered-feature gradients that `gather_features`
+ * implies (loss.py:59-64, `_AllGather.backward`), restricted to the soft terms:
+ *   dsoft_forward_phase(.., 1)   tile kernels + column reductions
+ *   caller: the column sums [6][b] of every primed block k >= 1 go to rank (rank + k) % world, the received ones are
+ *           added to the first b columns (dsoft_plan_symw_info gives offsets and sizes)
+ *   dsoft_forward_phase(.., 2)   finalize (losses, log-sum-exps)
+ *   dsoft_backward_phase(.., 1)  logit-gradient kernels + gradient GEMMs, incl. the transposed products
+ *   caller: rows [(k-1) b, k b) of the transposed products go to rank (rank + k) % world, the received ones are added
+ *           to this rank's own partial sums (split 0)
+ *   dsoft_backward_phase(.., 2)  finalize (chain rule, outputs)
+ * dsoft_forward / dsoft_backward refuse such a plan.  Arguments as for dsoft_forward / dsoft_backward. */
+int dsoft_plan_symw_info(const dsoft_plan_t* plan, long long* out12, int n);
+int dsoft_forward_phase(const dsoft_plan_t* plan, const void* gathered_dev, const float* logit_scale_dev,
+                        const float* lambdas, void* state_dev, void* scratch_dev, float* lse_local_dev,
+                        float* losses_dev, float* dbg_dev, void* stream, int phase);
+int dsoft_backward_phase(const dsoft_plan_t* plan, const void* gathered_dev, const void* state_dev, void* scratch_dev,
+                         const float* lse_all_dev, const float* gout_dev, const float* lambdas, float* d_image_dev,
+                         float* d_text_dev, float* d_student_dev, float* d_scale_dev, void* stream, int phase);
+
 /* CLIP-blind pair statistics (replaces the cs / ds matrices, masks and counts of
  * src/open_clip_train/helpers.py:221-285, `_pair_stats`).  Over the pairs i < j of n L2-normalised rows:
  *   counts_dev[2 k + 0] += #{cs_ij >= cmin[k]},  counts_dev[2 k + 1] += #{cs_ij >= cmin[k] and ds_ij <= dmax[k]}

@@ -52,6 +52,15 @@ struct dsoft_plan {
   int have_soft, have_text, have_proj, soft_local, row_only;
   int fwd_sym;         // world == 1 and fast_t: the soft forward computes the upper block triangle only
   int clip_sym;        // world == 1: one CLIP forward pass serves both directions (MODE_CLIP_SYM)
+  // world > 1, global soft scope (DSOFT_SYM_W): the soft Gram matrices are symmetric, so every pair of row blocks
+  // is computed by ONE of its two ranks.  Rank r owns, in column coordinates relative to its own first row
+  // ("primed"), the blocks [0, W/2) - its diagonal block first - plus half of the contested block W/2 (ranks below
+  // W/2: all of its columns for the rows b/2.., the others: its first b/2 columns for all rows).  The column
+  // sums of the forward statistics and the transposed gradient products that belong to other ranks' rows leave
+  // through two exchanges driven by the caller (dsoft_forward_phase / dsoft_backward_phase).
+  int sym_w;
+  int sw_ncols_a, sw_rb_half;  // row blocks < sw_rb_half own the primed columns [.., sw_ncols_a), the rest s_ncols
+  size_t sc_accR3, sc_accR4;   // transposed products for other ranks' rows: [s_ncols - b][Dz] / [s_ncols - b][D]
   size_t sc_clipM, sc_clipS, sc_lse_ti, st_dbound;
   SplitPlan f_sym;     // its (triangular) column chunks
   size_t sc_colpart, sc_colsum;
@@ -210,6 +219,27 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   p->ntiles_g = ceil_div(p->B, BN);
   p->s_col0 = p->soft_local ? sh->rank * sh->b : 0;
   p->s_ncols = p->soft_local ? sh->b : p->B;
+  {
+    const char* e = getenv("DSOFT_SYM_W");
+    p->sym_w = soft && sh->world > 1 && !p->soft_local && !p->row_only && (sh->flags & DSOFT_F_GMAT) &&
+               1.4426950408889634 / sh->teacher_temp <= 60.0 && sh->b % 512 == 0 && !(e && e[0] == '0');
+    p->sw_ncols_a = 0;
+    p->sw_rb_half = 0;
+    if (p->sym_w) {
+      const int W = sh->world, r = sh->rank, b = sh->b;
+      const int nfull = (W % 2) ? (W + 1) / 2 : W / 2;
+      p->s_col0 = r * b;
+      p->s_ncols = p->sw_ncols_a = nfull * b;
+      if (W % 2 == 0) {
+        if (r < W / 2) {
+          p->s_ncols = (nfull + 1) * b;
+          p->sw_rb_half = (b / 2) / BM;
+        } else {
+          p->s_ncols = p->sw_ncols_a = nfull * b + b / 2;
+        }
+      }
+    }
+  }
   p->ntiles_s = ceil_div(p->s_ncols, 2 * BN);
   p->ntiles_s128 = ceil_div(p->s_ncols, BN);
   p->fast_t = soft && (1.4426950408889634 / sh->teacher_temp <= 60.0);
@@ -223,7 +253,8 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
     // symmetric forward: needs one rank (the row block is the whole square), the fixed teacher maximum, and more
     // than one row pair (otherwise there is nothing to save); DSOFT_FWD_SYM=0 keeps the full-square kernel
     const char* e = getenv("DSOFT_FWD_SYM");
-    p->fwd_sym = soft && sh->world == 1 && p->fast_t && rbs > 2 && !(e && e[0] == '0');
+    p->fwd_sym = soft && (sh->world == 1 || p->sym_w) && p->fast_t && rbs > 2 && !(e && e[0] == '0');
+    if (p->sym_w && !p->fwd_sym) p->sym_w = 0;  // (cannot happen: b % 512 == 0 gives rbs >= 4)
     p->f_sym.tps = std::max(4, ceil_div(p->ntiles_s, 10));
     p->f_sym.nsplit = ceil_div(p->ntiles_s, p->f_sym.tps);
   }
@@ -284,6 +315,8 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   p->sc_acc2 = take(ns_c * b * sh->D);
   p->sc_acc3 = take(soft ? ns_s * b * p->Dz : 0);
   p->sc_acc4 = take(p->have_text ? ns_x * b * sh->D : 0);
+  p->sc_accR3 = take(p->sym_w ? static_cast<size_t>(p->s_ncols - sh->b) * p->Dz : 0);
+  p->sc_accR4 = take(p->sym_w && p->have_text ? static_cast<size_t>(p->s_ncols - sh->b) * sh->D : 0);
   const size_t nds_g = 2 * std::max(p->f_clip.nsplit, p->weighted ? p->f_wce.nsplit : 0);
   p->sc_ds1 = take(p->gmat ? nds_g * b : 2 * X_MAXC * p->b_clip.nsplit * b);
   p->sc_ds2 = take(p->gmat ? nds_g * b : 2 * X_MAXC * p->b_clip.nsplit * b);
@@ -320,7 +353,7 @@ extern "C" size_t dsoft_plan_forward_scratch_bytes(const dsoft_plan_t* p) { retu
 extern "C" double dsoft_plan_algorithmic_flops(const dsoft_plan_t* p) {
   if (!p) return 0.0;
   // F_alg = 2 B^2 (3D + 2Dp + Dd [+ 2D]) for the whole job; this rank's share is 1/W.
-  const double b = p->sh.b, cols_c = p->B, cols_s = p->s_ncols;
+  const double b = p->sh.b, cols_c = p->B, cols_s = p->sym_w ? p->B : p->s_ncols;
   double f = 2.0 * b * cols_c * (3.0 * p->sh.D);
   if (p->have_soft) f += 2.0 * b * cols_s * (2.0 * p->Dz + p->sh.Dd);
   if (p->have_text) f += 2.0 * b * cols_s * (2.0 * p->sh.D);
@@ -330,7 +363,8 @@ extern "C" double dsoft_plan_algorithmic_flops(const dsoft_plan_t* p) {
 // the kernel really executes (recompute per 256-feature chunk included).  Both for this rank.
 extern "C" int dsoft_plan_kernel_flops(const dsoft_plan_t* p, double* algorithmic, double* executed, int n) {
   if (!p || !algorithmic || !executed || n < 7) return fail(DSOFT_EINVAL, "need 7 slots");
-  const double b = p->sh.b, Bc = p->B, Bs = p->s_ncols, D = p->sh.D, Dz = p->Dz, Dd = p->sh.Dd;
+  const double b = p->sh.b, Bc = p->B, Bs = p->sym_w ? p->B : p->s_ncols, D = p->sh.D, Dz = p->Dz, Dd = p->sh.Dd;
+  const double sw = p->sym_w ? 0.5 : 1.0;  // symmetric ownership across ranks: half of the soft tiles per rank
   for (int k = 0; k < n; ++k) algorithmic[k] = executed[k] = 0.0;
   // forward CLIP: the two directions are exact transposes -> one algorithmic product, two executed
   algorithmic[0] = algorithmic[1] = b * Bc * D;
@@ -357,8 +391,9 @@ extern "C" int dsoft_plan_kernel_flops(const dsoft_plan_t* p, double* algorithmi
     for (int k = 3; k < 7; ++k) executed[k] = algorithmic[k];
     if (n > 7) executed[7] = (p->clip_tr ? 1.0 : 2.0) * (2.0 * b * Bc * D);
     if (n > 8 && p->have_soft)  // world == 1: only the upper block triangle (plus the 256-wide diagonal blocks)
-      executed[8] = (p->clip_tr ? 0.5 * (1.0 + 256.0 / std::max(256.0, Bs)) : 1.0) * 2.0 * b * Bs *
+      executed[8] = ((p->clip_tr || p->sym_w) ? 0.5 * (1.0 + 256.0 / std::max(256.0, Bs)) : 1.0) * 2.0 * b * Bs *
                     (Dz + Dd + (p->have_text ? D : 0.0));
+    (void)sw;
   }
   return 0;
 }
@@ -712,15 +747,18 @@ __device__ __forceinline__ void finalize_fwd_rows(const FinFwdArgs& a, float (&r
 
 // Symmetric forward: out[k][j] = sum over the warps w < 8 * (j / 256) of colpart[k][w][j] - the row blocks left of
 // row j's own pair, four warps each - in a fixed order (deterministic).  grid (Bcol / 32, 6), block (32, 16).
+// (DSOFT_SYM_W: columns from ncols_a on were only visited by the warps from w_lo on.)
 __global__ void __launch_bounds__(512) soft_colreduce_kernel(const float* __restrict__ colpart, int cp_rows, int pitch,
-                                                             int ncols, float* __restrict__ out) {
+                                                             int ncols, float* __restrict__ out, int ncols_a, int w_lo) {
   __shared__ float sh[16][33];
   const int j = blockIdx.x * 32 + threadIdx.x;
   const int k = blockIdx.y;
   const int wmax = min(cp_rows, 8 * (j >> 8));
+  const int wmin = (j >= ncols_a) ? w_lo : 0;
   float acc = 0.f;
   if (j < ncols)
-    for (int w = threadIdx.y; w < wmax; w += 16) acc += colpart[(static_cast<size_t>(k) * cp_rows + w) * pitch + j];
+    for (int w = wmin + threadIdx.y; w < wmax; w += 16)
+      acc += colpart[(static_cast<size_t>(k) * cp_rows + w) * pitch + j];
   sh[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.y == 0) {
@@ -2068,9 +2106,30 @@ extern "C" int dsoft_pair_stats(const void* clip_a, const void* clip_b, int32_t 
   return launch_fwd_pair(dsoft_fwd_kernel<MODE_PAIRS, 2>, ceil_div(n, BM), nsplit, st, tm, P);
 }
 
+// phase 0: the whole forward; 1: everything up to the column-sum exchange of a DSOFT_SYM_W plan; 2: the rest
+static int forward_impl(const dsoft_plan_t* p, const void* gathered, const float* logit_scale,
+                        const float* lambdas, void* state, void* scratch, float* lse_local,
+                        float* losses, float* dbg, void* stream, int phase);
+
 extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const float* logit_scale,
                              const float* lambdas, void* state, void* scratch, float* lse_local,
                              float* losses, float* dbg, void* stream) {
+  if (p && p->sym_w)
+    return fail(DSOFT_EINVAL, "this plan shares the symmetric soft tiles across ranks (DSOFT_SYM_W): call "
+                              "dsoft_forward_phase(1), exchange the column sums, then dsoft_forward_phase(2)");
+  return forward_impl(p, gathered, logit_scale, lambdas, state, scratch, lse_local, losses, dbg, stream, 0);
+}
+
+extern "C" int dsoft_forward_phase(const dsoft_plan_t* p, const void* gathered, const float* logit_scale,
+                                   const float* lambdas, void* state, void* scratch, float* lse_local,
+                                   float* losses, float* dbg, void* stream, int phase) {
+  if (phase != 1 && phase != 2) return fail(DSOFT_EINVAL, "phase must be 1 or 2");
+  return forward_impl(p, gathered, logit_scale, lambdas, state, scratch, lse_local, losses, dbg, stream, phase);
+}
+
+static int forward_impl(const dsoft_plan_t* p, const void* gathered, const float* logit_scale,
+                        const float* lambdas, void* state, void* scratch, float* lse_local,
+                        float* losses, float* dbg, void* stream, int phase) {
   if (!p || !gathered || !logit_scale || !lambdas || !state || !scratch || !lse_local || !losses)
     return fail(DSOFT_EINVAL, "null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -2083,6 +2142,7 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
   int rc = make_maps(p, gathered, &tm, 64);  // 64-row boxes: each CTA of a pair stages half a column tile
   if (rc) return rc;
 
+  if (phase != 2) {
   prep_scalars_kernel<<<1, 32, 0, st>>>(logit_scale, p->have_soft ? p->sh.teacher_temp : 0.f,
                                         p->have_text ? p->sh.text_temp : 0.f, S + p->st_scal);
   CUDA_TRY(cudaGetLastError());
@@ -2146,10 +2206,17 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
       P.colpart = X + p->sc_colpart;
       P.cp_rows = 4 * rbs;
       P.cp_pitch = p->Bcol;
+      if (p->sym_w) {  // primed columns wrapping around the global batch, short rows (plan: sym_w)
+        P.wrap = p->B;
+        P.rb_half = p->sw_rb_half;
+        P.ntiles_a = p->sw_ncols_a / (2 * BN);
+      }
       ProfScope ps(PK_FWD_SOFT, ks);
       if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_SOFT_SYM, 2>, rbs, p->f_sym.nsplit, ks, tm, P))) return rc;
-      soft_colreduce_kernel<<<dim3(p->Bcol / 32, 6), dim3(32, 16), 0, ks>>>(X + p->sc_colpart, 4 * rbs, p->Bcol, p->B,
-                                                                            X + p->sc_colsum);
+      // column sums by PRIMED column: [0, b) are this rank's own rows, the rest belongs to the ranks behind it
+      soft_colreduce_kernel<<<dim3(p->Bcol / 32, 6), dim3(32, 16), 0, ks>>>(
+          X + p->sc_colpart, 4 * rbs, p->Bcol, p->s_ncols, X + p->sc_colsum, p->sym_w ? p->sw_ncols_a : p->s_ncols,
+          4 * p->sw_rb_half);
     } else {
       ProfScope ps(PK_FWD_SOFT, ks);
       if ((rc = launch_fwd_pair(dsoft_fwd_kernel<MODE_SOFT, 2>, rbs, p->f_soft.nsplit, ks, tm, P))) return rc;
@@ -2191,6 +2258,8 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
     CUDA_TRY(cudaGetLastError());
   }
   if ((rc = fk.join())) return rc;
+  }  // phase != 2
+  if (phase == 1) return 0;
 
   FinFwdArgs fa;
   fa.b = b;
@@ -2224,9 +2293,13 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
 // transposed = true (world == 1 only): acc[split][col][dout] = G^T . Y16, K runs over G's rows
 // tri (world == 1, symmetrically scaled soft G of which only the upper block triangle exists): blocks left of each
 // row pair's diagonal block are read transposed from the same matrix
+// DSOFT_SYM_W extras of a gradient GEMM launch (all zero otherwise; see GyParams)
+struct GySym {
+  int ywrap = 0, rb0 = 0, out_rows = 0, pair_half = 0, kend_a = 0, rb_a = 0, klo_b = 0;
+};
 static int launch_gy(const dsoft_plan* p, const __half* G, int pitch, const __half* v16, int voff, int dout,
                      int ycol0, const SplitPlan& sp, float* acc, cudaStream_t st, bool transposed = false,
-                     bool tri = false) {
+                     bool tri = false, const GySym* sym = nullptr) {
   CUtensorMap gmap, gmap64, vmap;
   int rc;
   // blocked G: 64 columns x (row blocks * K tiles * 128) rows, one 16 KiB box per (row block, K tile)
@@ -2236,6 +2309,7 @@ static int launch_gy(const dsoft_plan* p, const __half* G, int pitch, const __ha
   if ((rc = make_map(&gmap64, G, g_rows, BK, BK, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 64))) return rc;
   if ((rc = make_map(&vmap, v16 + voff, p->B, dout, p->v_row, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 64))) return rc;
   GyParams P;
+  memset(&P, 0, sizeof(P));
   P.b = p->sh.b;
   P.dout = dout;
   P.ksteps = transposed ? rbs * 2 : pitch / BK;
@@ -2245,7 +2319,19 @@ static int launch_gy(const dsoft_plan* p, const __half* G, int pitch, const __ha
   P.g_ktiles = pitch / BK;
   P.tri = tri ? 1 : 0;
   P.acc_part = acc;
-  const int pairs = ceil_div(rbs, 2);
+  int pairs = ceil_div(rbs, 2);
+  if (sym) {
+    P.ywrap = sym->ywrap;
+    P.rb0 = sym->rb0;
+    P.pair_half = sym->pair_half;
+    P.kend_a = sym->kend_a;
+    P.rb_a = sym->rb_a;
+    P.klo_b = sym->klo_b;
+    if (sym->out_rows) {  // transposed products for other ranks' rows: output rows = primed columns from 128 rb0 on
+      P.b = sym->out_rows;
+      pairs = ceil_div(sym->out_rows, 2 * BM);
+    }
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2, ceil_div(dout, GY_N), pairs * sp.nsplit);
   cfg.blockDim = dim3(NUM_THREADS);
@@ -2332,12 +2418,31 @@ static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* 
     // world == 1: the student / text / teacher matrices are symmetric, so G is: only the tiles from each row
     // pair's diagonal block onwards are computed (half the work), in column chunks small enough to balance the
     // triangular load; the gradient GEMMs read the other half through the transposed blocks
-    const bool tri = p->clip_tr;
+    // world > 1 with DSOFT_SYM_W: the same in primed column coordinates for the tiles this rank owns
+    const bool tri = p->clip_tr || p->sym_w;
     int nsplit = p->f_soft.nsplit;
     if (tri) {
       P.tri = 1;
       P.tiles_per_split = std::max(4, ceil_div(p->ntiles_s, 10));
       nsplit = ceil_div(p->ntiles_s, P.tiles_per_split);
+    }
+    GySym loc, rem;  // local rows' products / transposed products for the rows of the ranks behind this one
+    SplitPlan one;
+    if (p->sym_w) {
+      P.wrap = p->B;
+      P.rb_half = p->sw_rb_half;
+      P.ntiles_a = p->sw_ncols_a / (2 * BN);
+      loc.ywrap = p->B;
+      loc.pair_half = p->sw_rb_half / 2;
+      loc.kend_a = p->sw_ncols_a / BK;
+      rem.rb0 = b / BM;
+      rem.out_rows = p->s_ncols - b;
+      if (p->sw_rb_half) {  // the contested block's columns only exist in the rows from b/2 on
+        rem.rb_a = p->sw_ncols_a / BM;
+        rem.klo_b = (b / 2) / BK;
+      }
+      one.nsplit = 1;
+      one.tps = rbs * 2;
     }
     {
       ProfScope ps(PK_BWD_GSOFT, ks);
@@ -2346,13 +2451,19 @@ static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* 
     {
       ProfScope ps(PK_BWD_STU, ks);
       if ((rc = launch_gy(p, Gs, p->pitch_s, v16, p->v_offZn, p->Dz, p->s_col0, p->g_stu, X + p->sc_acc3, ks, false,
-                          tri)))
+                          tri, p->sym_w ? &loc : nullptr)))
+        return rc;
+      if (p->sym_w && (rc = launch_gy(p, Gs, p->pitch_s, v16, p->v_offZn, p->Dz, p->sh.rank * b, one,
+                                      X + p->sc_accR3, ks, true, false, &rem)))
         return rc;
     }
     if (p->have_text) {
       ProfScope ps(PK_BWD_TXT, ks);
       if ((rc = launch_gy(p, Gx, p->pitch_s, v16, p->v_offTn, p->sh.D, p->s_col0, p->g_txt, X + p->sc_acc4, ks, false,
-                          tri)))
+                          tri, p->sym_w ? &loc : nullptr)))
+        return rc;
+      if (p->sym_w && (rc = launch_gy(p, Gx, p->pitch_s, v16, p->v_offTn, p->sh.D, p->sh.rank * b, one,
+                                      X + p->sc_accR4, ks, true, false, &rem)))
         return rc;
     }
   }
@@ -2428,9 +2539,59 @@ static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* 
   return fk.join();
 }
 
+// phase 0: the whole backward; 1: everything up to the exchange of the transposed products of a DSOFT_SYM_W plan
+// (logit-gradient kernels + gradient GEMMs); 2: the finalize kernel
+static int backward_impl(const dsoft_plan_t* p, const void* gathered, const void* state, void* scratch,
+                         const float* lse_all, const float* gout, const float* lambdas, float* d_image,
+                         float* d_text, float* d_student, float* d_scale, void* stream, int phase);
+
 extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const void* state, void* scratch,
                               const float* lse_all, const float* gout, const float* lambdas, float* d_image,
                               float* d_text, float* d_student, float* d_scale, void* stream) {
+  if (p && p->sym_w)
+    return fail(DSOFT_EINVAL, "this plan shares the symmetric soft tiles across ranks (DSOFT_SYM_W): call "
+                              "dsoft_backward_phase(1), exchange the transposed products, then dsoft_backward_phase(2)");
+  return backward_impl(p, gathered, state, scratch, lse_all, gout, lambdas, d_image, d_text, d_student, d_scale,
+                       stream, 0);
+}
+
+extern "C" int dsoft_backward_phase(const dsoft_plan_t* p, const void* gathered, const void* state, void* scratch,
+                                    const float* lse_all, const float* gout, const float* lambdas, float* d_image,
+                                    float* d_text, float* d_student, float* d_scale, void* stream, int phase) {
+  if (phase != 1 && phase != 2) return fail(DSOFT_EINVAL, "phase must be 1 or 2");
+  return backward_impl(p, gathered, state, scratch, lse_all, gout, lambdas, d_image, d_text, d_student, d_scale,
+                       stream, phase);
+}
+
+// Layout of the two exchanges of a DSOFT_SYM_W plan, in floats / rows (out[12]):
+//  [0] 1 if the plan uses them            [1] b                          [2] Bcol (pitch of the column sums)
+//  [3] offset of the column sums [6][Bcol] in the FORWARD scratch (primed columns; [0, b) = this rank's rows)
+//  [4] primed columns this rank computes (s_ncols): the blocks 1 .. belong to ranks rank+1, rank+2, ...
+//  [5] offset of the student products for other ranks' rows [s_ncols - b][Dz] in the BACKWARD scratch, [6] Dz
+//  [7] the same for the text term [s_ncols - b][D], [8] D (0: no text term)
+//  [9] offset of this rank's own student partial sums (split 0: [b][Dz]), [10] of the text ones ([b][D])
+//  [11] number of K splits of those partial sums (received products are added to split 0)
+extern "C" int dsoft_plan_symw_info(const dsoft_plan_t* p, long long* out, int n) {
+  if (!p || !out || n < 12) return fail(DSOFT_EINVAL, "need 12 slots");
+  for (int k = 0; k < n; ++k) out[k] = 0;
+  out[0] = p->sym_w;
+  out[1] = p->sh.b;
+  out[2] = p->Bcol;
+  out[3] = static_cast<long long>(p->sc_colsum);
+  out[4] = p->s_ncols;
+  out[5] = static_cast<long long>(p->sc_accR3);
+  out[6] = p->Dz;
+  out[7] = static_cast<long long>(p->sc_accR4);
+  out[8] = p->have_text ? p->sh.D : 0;
+  out[9] = static_cast<long long>(p->sc_acc3);
+  out[10] = static_cast<long long>(p->sc_acc4);
+  out[11] = p->gmat ? p->g_stu.nsplit : 1;
+  return 0;
+}
+
+static int backward_impl(const dsoft_plan_t* p, const void* gathered, const void* state, void* scratch,
+                         const float* lse_all, const float* gout, const float* lambdas, float* d_image,
+                         float* d_text, float* d_student, float* d_scale, void* stream, int phase) {
   if (!p || !gathered || !state || !scratch || !lse_all || !gout || !lambdas || !d_image || !d_text || !d_scale)
     return fail(DSOFT_EINVAL, "null argument");
   if (p->have_proj && !d_student) return fail(DSOFT_EINVAL, "d_student is null but the plan has Dp > 0");
@@ -2447,13 +2608,14 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
   if (rc) return rc;
 
   float* lsec = S + p->st_lsecols;
+  const float* lse_loc = lse_all + static_cast<size_t>(p->sh.rank) * 5 * b;
+  if (phase != 2) {
   lse_stats_kernel<<<LSE_NB, 256, 0, st>>>(lse_all, p->sh.world, b, S + p->st_lsestat);
   CUDA_TRY(cudaGetLastError());
   lse_relayout_kernel<<<ceil_div(5 * p->Bcol, 1024), 256, 0, st>>>(
       lse_all, p->sh.world, b, p->Bcol, S + p->st_scal, S + p->st_lsestat, p->fast_t, p->row_only,
       p->row_only && !p->soft_local, lsec, S + p->st_colfac);
   CUDA_TRY(cudaGetLastError());
-  const float* lse_loc = lse_all + static_cast<size_t>(p->sh.rank) * 5 * b;
   __half* v16 = reinterpret_cast<__half*>(X + p->sc_v16);
   make_v16_kernel<<<ceil_div(p->B, 8), 256, 0, st>>>(
       static_cast<const __nv_bfloat16*>(gathered), p->row_elems, p->B, p->sh.D, p->Dz, p->offI, p->offT,
@@ -2577,6 +2739,8 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
 
   if ((rc = fk.join())) return rc;
   }  // !p->gmat
+  }  // phase != 2
+  if (phase == 1) return 0;
 
   FinBwdArgs fa;
   memset(&fa, 0, sizeof(fa));
@@ -2592,7 +2756,7 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
   fa.have_text = p->have_text;
   fa.have_proj = p->have_proj;
   fa.row_only = p->row_only;
-  fa.sym_scaled = p->gmat && p->clip_tr;
+  fa.sym_scaled = p->gmat && (p->clip_tr || p->sym_w);
   fa.weighted = p->weighted;
   fa.wsym = p->wsym;
   fa.wstat = S + p->st_wstat;

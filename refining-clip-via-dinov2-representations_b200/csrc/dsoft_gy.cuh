@@ -43,6 +43,11 @@ struct GyParams {
   int tri;              // symmetric G of which only the blocks from each row pair's 256-column diagonal block
                         // onwards exist: K steps below 4 * pair read the transposed blocks instead (AT-style)
   float* acc_part;      // [nsplit][b][dout] fp32
+  // ---- symmetric soft matrices across ranks (DSOFT_SYM_W; all zero otherwise)
+  int ywrap;            // rows of Y16 wrap around the global batch: row = (ycol0 + 64 k) mod ywrap
+  int rb0;              // AT: first G column block (128 columns) of the output; output row 0 = column 128 rb0
+  int pair_half, kend_a;  // normal launch: row pairs < pair_half stop at K step kend_a (their G tiles end there)
+  int rb_a, klo_b;        // AT: output blocks >= rb_a only sum over the G rows from K step klo_b on
 };
 
 template <bool AT>
@@ -65,9 +70,11 @@ dsoft_gy_kernel(const __grid_constant__ CUtensorMap gmap, const __grid_constant_
   const int nt = blockIdx.y;
   const int pair = blockIdx.z / P.nsplit;
   const int split = blockIdx.z % P.nsplit;
-  const int rb = pair * 2 + prank;
-  const int k0 = split * P.steps_per_split;
-  const int k1 = min(k0 + P.steps_per_split, P.ksteps);
+  const int rb = (AT ? P.rb0 : 0) + pair * 2 + prank;  // AT: G column block; else: row block
+  int k0 = split * P.steps_per_split;
+  int k1 = min(k0 + P.steps_per_split, P.ksteps);
+  if (!AT && pair < P.pair_half) k1 = min(k1, P.kend_a);
+  if (AT && P.rb0 + pair * 2 >= P.rb_a && P.rb_a > 0) k0 = max(k0, P.klo_b);
   const int f0 = nt * GY_N + prank * (GY_N / 2);  // first feature staged by this CTA
 
   if (warp == 0 && lane == 0) {
@@ -105,8 +112,9 @@ dsoft_gy_kernel(const __grid_constant__ CUtensorMap gmap, const __grid_constant_
         } else {
           tma_load_2d_2sm(dst, &gmap, full_leader, 0, (rb * P.g_ktiles + k) * BM);
         }
-        tma_load_2d_2sm(dst + TILE_BYTES, &vmap, full_leader, f0, P.ycol0 + k * BK);
-        tma_load_2d_2sm(dst + TILE_BYTES + TILE_BYTES / 2, &vmap, full_leader, f0 + BK, P.ycol0 + k * BK);
+        const int yrow = P.ywrap ? (P.ycol0 + k * BK) % P.ywrap : P.ycol0 + k * BK;
+        tma_load_2d_2sm(dst + TILE_BYTES, &vmap, full_leader, f0, yrow);
+        tma_load_2d_2sm(dst + TILE_BYTES + TILE_BYTES / 2, &vmap, full_leader, f0 + BK, yrow);
       }
       __syncwarp();
       if (++stage == GY_STAGES) { stage = 0; phase ^= 1; }
@@ -141,7 +149,7 @@ dsoft_gy_kernel(const __grid_constant__ CUtensorMap gmap, const __grid_constant_
   } else if (warp >= EPI_WARP0) {
     const int q = warp & 3;
     const int half = (warp - EPI_WARP0) >> 2;
-    const int li = rb * BM + q * 32 + lane;
+    const int li = (pair * 2 + prank) * BM + q * 32 + lane;  // output row (AT: relative to column 128 rb0)
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     float v[32];
     const bool any = k1 > k0;

@@ -152,6 +152,11 @@ struct FwdParams {
                             // symmetrically; the gradient GEMM reads the missing part from the transposed blocks
   int ds_both;              // clip, world == 1: one launch serves both directions (the text rows' matrix is the
                             // transpose), so the row partial also takes the column-side term
+  // ---- symmetric soft kernels across ranks (world > 1, DSOFT_SYM_W): column coordinates are "primed" - relative
+  // to this rank's first row, so that its diagonal block comes first - and wrap around the global batch
+  int wrap;                 // 0, or B: global column of primed tile t = (col0 + t * 256) mod wrap  (col0 == row0)
+  int rb_half, ntiles_a;    // row blocks rb < rb_half own the primed tiles [diagonal, ntiles_a) only, the others
+                            // [diagonal, ntiles): the contested half block of the rank pair (r, r + W/2)
 };
 
 struct BwdParams {
@@ -341,9 +346,12 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   int t0 = split * P.tiles_per_split;
   int t1 = min(t0 + P.tiles_per_split, P.ntiles);
   if (P.tri) {
-    t1 = P.ntiles - split * P.tiles_per_split;
+    const int tend = (rb < P.rb_half) ? P.ntiles_a : P.ntiles;  // both CTAs of a pair lie in the same half
+    t1 = tend - split * P.tiles_per_split;
     t0 = max(t1 - P.tiles_per_split, rb >> 1);  // may be >= t1: nothing to do
   }
+  // global column of the first column of (primed) tile t; without wrap the two coincide up to col0
+  auto gcol = [&](int t) { return P.wrap ? (P.col0 + t * P.bn) % P.wrap : P.col0 + t * P.bn; };
   const int prank = (CG == 2) ? (rb & 1) : 0;  // rank in the pair (== cluster rank)
   const bool leader = prank == 0;
 
@@ -413,7 +421,7 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
           const int nvec = (kWce || kPairs) ? P.ncolvec : (MODE == MODE_SOFT_G ? 2 : 1) * P.nprod;
           mbar_arrive_expect_tx(full, nvec * CT * 4);
           float* dst = colbuf + cb * COL_VECS * CT;
-          const size_t c0 = static_cast<size_t>(P.col0) + static_cast<size_t>(t) * CT;
+          const size_t c0 = static_cast<size_t>(gcol(t));  // CT == bn == 256 in the soft modes
           if constexpr (kWce || kPairs) {
             for (int k = 0; k < P.ncolvec; ++k) bulk_copy_g2s(smem_u32(dst + k * CT), P.colvec[k] + c0, CT * 4, full);
           } else {
@@ -442,7 +450,7 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
               bdst += TILE_BYTES;
             }
             for (int i = 0; i < brows / boxr; ++i)
-              load(bdst + i * box_bytes, bm, full, kc * BK, P.col0 + t * bn + prank * brows + i * boxr);
+              load(bdst + i * box_bytes, bm, full, kc * BK, gcol(t) + prank * brows + i * boxr);
           }
           __syncwarp();
           if (++stage == nstages) { stage = 0; phase ^= 1; }
@@ -1379,7 +1387,9 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
               release_slot(slot);
             }
             const float4* rc = reinterpret_cast<const float4*>(cv + c * 32);
-            const bool need_mask = (gw0 < jrel0 + 32 && jrel0 < gw0 + 32) || (ragged && jrel0 + 32 > P.ncols) || !offdiag;
+            // primed columns: the diagonal is where the column equals the LOCAL row (== the global one at world 1)
+            const int lw0 = rb * BM + q * 32;
+            const bool need_mask = (lw0 < jrel0 + 32 && jrel0 < lw0 + 32) || (ragged && jrel0 + 32 > P.ncols) || !offdiag;
             float wq[32];
 #pragma unroll
             for (int e4 = 0; e4 < 8; ++e4) {
@@ -1390,7 +1400,7 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
                 const int e = 4 * e4 + k;
                 const float arg = fmaf(__uint_as_float(rcur[e]), cq * rr[k], bias_t);
                 float we = fast_exp2(arg);
-                if (need_mask && (jrel0 + e >= P.ncols || jrel0 + e == gi)) we = 0.f;  // ragged; teacher diag masked
+                if (need_mask && (jrel0 + e >= P.ncols || jrel0 + e == li)) we = 0.f;  // ragged; teacher diag masked
                 w[c * 32 + e] = we;
                 wq[e] = we * arg;
                 zt += we;

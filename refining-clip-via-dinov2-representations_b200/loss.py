@@ -101,7 +101,73 @@ _DTYPES = {torch.float32: _cabi.DT_F32, torch.bfloat16: _cabi.DT_BF16, torch.flo
 
 class _Plan:
     __slots__ = ("handle", "row_elems", "state_numel", "scratch_numel", "fwd_scratch_numel", "flops",
-                 "launches_fwd", "launches_bwd", "shape", "dino_col")
+                 "launches_fwd", "launches_bwd", "shape", "dino_col", "symw")
+
+
+class _SymW:
+    """Exchange layout of a plan that shares the symmetric soft tiles across ranks (dsoft_plan_symw_info).
+
+    Primed block k (columns [k b, (k+1) b) relative to this rank's first row) holds what this rank computed for the
+    rows of rank (rank + k) % W; the last block may be half a block (see include/dsoft.h)."""
+
+    def __init__(self, info, W, rank):
+        (_, self.b, self.Bcol, self.off_colsum, self.ncols, self.off_r3, self.Dz, self.off_r4, self.Dx, self.off_a3,
+         self.off_a4, self.nsplit) = [int(x) for x in info]
+        self.W, self.rank = W, rank
+        b = self.b
+        # (peer, primed block, rows) this rank sends / receives
+        self.sends = [((rank + k) % W, k, min(b, self.ncols - k * b)) for k in range(1, -(-self.ncols // b))]
+        self.recvs = []
+        for k in range(1, W):
+            s = (rank - k) % W
+            if W % 2:
+                rows = b if k <= (W - 1) // 2 else 0
+            elif k < W // 2:
+                rows = b
+            elif k == W // 2:
+                rows = b if s < W // 2 else b // 2  # the contested block: see the plan's ownership rule
+            else:
+                rows = 0
+            if rows:
+                self.recvs.append((s, k, rows))
+
+    # ---- views into the scratch buffers
+    def colsum(self, fwd_scratch):
+        return fwd_scratch[self.off_colsum:self.off_colsum + 6 * self.Bcol].view(6, self.Bcol)
+
+    def remote(self, scratch, which):
+        off, d = (self.off_r3, self.Dz) if which == 0 else (self.off_r4, self.Dx)
+        n = self.ncols - self.b
+        return scratch[off:off + n * d].view(n, d)
+
+    def own(self, scratch, which):
+        off, d = (self.off_a3, self.Dz) if which == 0 else (self.off_a4, self.Dx)
+        return scratch[off:off + self.b * d].view(self.b, d)
+
+    # ---- the two exchanges over NCCL
+    def exchange_forward(self, fwd_scratch, group):
+        cs = self.colsum(fwd_scratch)
+        send = torch.zeros((self.W, 6, self.b), dtype=torch.float32, device=cs.device)
+        for peer, k, rows in self.sends:
+            send[peer, :, :rows] = cs[:, k * self.b:k * self.b + rows]
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=group)
+        cs[:, :self.b] += recv.sum(0)
+
+    def exchange_backward(self, scratch, group):
+        ops, landed = [], []
+        for which in ((0, 1) if self.Dx else (0,)):
+            rem, own = self.remote(scratch, which), self.own(scratch, which)
+            for peer, k, rows in self.sends:
+                ops.append(dist.P2POp(dist.isend, rem[(k - 1) * self.b:(k - 1) * self.b + rows], peer, group))
+            for peer, k, rows in self.recvs:
+                buf = torch.empty((rows, rem.shape[1]), dtype=torch.float32, device=rem.device)
+                ops.append(dist.P2POp(dist.irecv, buf, peer, group))
+                landed.append((own, rows, buf))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        for own, rows, buf in landed:
+            own[:rows] += buf
 
 
 def _rowmajor(x: torch.Tensor) -> torch.Tensor:
@@ -145,6 +211,9 @@ class CudaBackend:
             p.launches_fwd = int(self._lib.dsoft_plan_launches_forward(h))
             p.launches_bwd = int(self._lib.dsoft_plan_launches_backward(h))
             p.dino_col = int(self._lib.dsoft_plan_dino_col_offset(h))
+            info = (C.c_longlong * 12)()
+            _cabi.check(self._lib.dsoft_plan_symw_info(h, info, 12), "dsoft_plan_symw_info")
+            p.symw = _SymW(list(info), shape.world, shape.rank) if info[0] else None
             p.shape = shape
             self._plans[key] = p
         return p
@@ -185,21 +254,24 @@ class CudaBackend:
 
         return (C.c_float * 4)(*[float(x) for x in lambdas])
 
-    def forward(self, plan, gathered, logit_scale, lambdas, state, scratch, lse_local, losses, dbg=None):
-        _cabi.check(
-            self._lib.dsoft_forward(plan.handle, _ptr(gathered), _ptr(logit_scale), self._lam(lambdas), _ptr(state),
-                                    _ptr(scratch), _ptr(lse_local), _ptr(losses), _ptr(dbg),
-                                    self._stream(gathered)),
-            "dsoft_forward",
-        )
+    def forward(self, plan, gathered, logit_scale, lambdas, state, scratch, lse_local, losses, dbg=None, phase=0):
+        """phase 0: whole forward; 1 / 2: before / after the column-sum exchange of a plan with `symw`."""
+        a = (plan.handle, _ptr(gathered), _ptr(logit_scale), self._lam(lambdas), _ptr(state), _ptr(scratch),
+             _ptr(lse_local), _ptr(losses), _ptr(dbg), self._stream(gathered))
+        if phase == 0:
+            _cabi.check(self._lib.dsoft_forward(*a), "dsoft_forward")
+        else:
+            _cabi.check(self._lib.dsoft_forward_phase(*a, phase), "dsoft_forward_phase")
 
-    def backward(self, plan, gathered, state, scratch, lse_all, gout, lambdas, d_image, d_text, d_student, d_scale):
-        _cabi.check(
-            self._lib.dsoft_backward(plan.handle, _ptr(gathered), _ptr(state), _ptr(scratch), _ptr(lse_all),
-                                     _ptr(gout), self._lam(lambdas), _ptr(d_image), _ptr(d_text), _ptr(d_student),
-                                     _ptr(d_scale), self._stream(gathered)),
-            "dsoft_backward",
-        )
+    def backward(self, plan, gathered, state, scratch, lse_all, gout, lambdas, d_image, d_text, d_student, d_scale,
+                 phase=0):
+        """phase 0: whole backward; 1 / 2: before / after the exchange of the transposed products (`symw`)."""
+        a = (plan.handle, _ptr(gathered), _ptr(state), _ptr(scratch), _ptr(lse_all), _ptr(gout), self._lam(lambdas),
+             _ptr(d_image), _ptr(d_text), _ptr(d_student), _ptr(d_scale), self._stream(gathered))
+        if phase == 0:
+            _cabi.check(self._lib.dsoft_backward(*a), "dsoft_backward")
+        else:
+            _cabi.check(self._lib.dsoft_backward_phase(*a, phase), "dsoft_backward_phase")
 
 
 _cuda_backend: Optional[CudaBackend] = None
@@ -347,7 +419,14 @@ class _DinoSoftFn(torch.autograd.Function):
         losses = torch.empty(6, dtype=torch.float32, device=dev)
         dbg = torch.empty(_cabi.DBG_N if weighted else 0, dtype=torch.float32, device=dev)
         ls = logit_scale.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
-        be.forward(plan, gathered, ls, cfg.lambdas, state, scratch, lse_all[r], losses, dbg if weighted else None)
+        if getattr(plan, "symw", None) is not None:
+            # symmetric soft tiles across ranks: the column sums this rank computed for other ranks' rows travel
+            # between the tile kernels and the finalize kernel (6 floats per row and owner)
+            be.forward(plan, gathered, ls, cfg.lambdas, state, scratch, lse_all[r], losses, None, phase=1)
+            plan.symw.exchange_forward(scratch, cfg.group)
+            be.forward(plan, gathered, ls, cfg.lambdas, state, scratch, lse_all[r], losses, None, phase=2)
+        else:
+            be.forward(plan, gathered, ls, cfg.lambdas, state, scratch, lse_all[r], losses, dbg if weighted else None)
         if W > 1 and needs_grad:
             # column-side soft-max statistics of the other ranks' rows (5 floats per sample)
             dist.all_gather_into_tensor(lse_all.view(-1), lse_all[r].view(-1), group=cfg.group)
@@ -385,7 +464,15 @@ class _DinoSoftFn(torch.autograd.Function):
                                        flags=s.flags & ~_cabi.DSOFT_F_GMAT, teacher_temp=s.teacher_temp,
                                        text_temp=s.text_temp, rho=s.rho, c_clip=s.c_clip), dev)
             scratch = torch.empty(plan.scratch_numel, dtype=torch.float32, device=dev)
-        be.backward(plan, gathered, state, scratch, lse_all, gout, ctx.cfg.lambdas, d_image, d_text, d_student, d_scale)
+        args = (plan, gathered, state, scratch, lse_all, gout, ctx.cfg.lambdas, d_image, d_text, d_student, d_scale)
+        if getattr(plan, "symw", None) is not None:
+            # ... and the transposed gradient products (the reduce-scatter of `_AllGather.backward`, loss.py:59-64,
+            # restricted to the soft terms and to the half of the blocks the other rank did not compute itself)
+            be.backward(*args, phase=1)
+            plan.symw.exchange_backward(scratch, ctx.cfg.group)
+            be.backward(*args, phase=2)
+        else:
+            be.backward(*args)
         g_student = None
         if zdt is not None:
             g_student = d_student.to(zdt) if d_student is not None else None
