@@ -130,14 +130,19 @@ int dsoft_head_forward(const dsoft_plan_t* plan, void* gathered_dev, const void*
  * symmetric, so each pair of row blocks is computed by ONE of its two ranks, and what belongs to the other rank's
  * rows is exchanged by the caller - the reduce-scatter of the gathered-feature gradients that `gather_features`
  * implies (loss.py:59-64, `_AllGather.backward`), restricted to the soft terms:
- *   dsoft_forward_phase(.., 1)   tile kernels + column reductions
+ *   dsoft_forward_phase(.., 1)   operand statistics, soft tile kernel + column reductions
  *   caller: the column sums [6][b] of every primed block k >= 1 go to rank (rank + k) % world, the received ones are
  *           added to the first b columns (dsoft_plan_symw_info gives offsets and sizes)
- *   dsoft_forward_phase(.., 2)   finalize (losses, log-sum-exps)
- *   dsoft_backward_phase(.., 1)  logit-gradient kernels + gradient GEMMs, incl. the transposed products
+ *   dsoft_forward_phase(.., 3)   CLIP tile kernels; touches nothing the exchange touches, so the caller runs the
+ *                                exchange on a second stream next to it
+ *   dsoft_forward_phase(.., 2)   finalize (losses, log-sum-exps): after phase 3 and the exchange
+ *   dsoft_backward_phase(.., 1)  statistics relayout, fp16 operands, soft logit-gradient kernel + its gradient GEMMs,
+ *                                incl. the transposed products
  *   caller: rows [(k-1) b, k b) of the transposed products go to rank (rank + k) % world, the received ones are added
  *           to this rank's own partial sums (split 0)
- *   dsoft_backward_phase(.., 2)  finalize (chain rule, outputs)
+ *   dsoft_backward_phase(.., 3)  CLIP logit-gradient kernels + gradient GEMMs (next to the exchange, as above)
+ *   dsoft_backward_phase(.., 2)  finalize (chain rule, outputs): after phase 3 and the exchange
+ * Every call of one pass takes the same arguments; phases 1 and 3 go to the same stream in that order.
  * dsoft_forward / dsoft_backward refuse such a plan.  Arguments as for dsoft_forward / dsoft_backward. */
 int dsoft_plan_symw_info(const dsoft_plan_t* plan, long long* out12, int n);
 int dsoft_forward_phase(const dsoft_plan_t* plan, const void* gathered_dev, const float* logit_scale_dev,

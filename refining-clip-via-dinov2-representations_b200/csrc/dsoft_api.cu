@@ -2106,7 +2106,8 @@ extern "C" int dsoft_pair_stats(const void* clip_a, const void* clip_b, int32_t 
   return launch_fwd_pair(dsoft_fwd_kernel<MODE_PAIRS, 2>, ceil_div(n, BM), nsplit, st, tm, P);
 }
 
-// phase 0: the whole forward; 1: everything up to the column-sum exchange of a DSOFT_SYM_W plan; 2: the rest
+// phase 0: the whole forward; of a DSOFT_SYM_W plan: 1 = the soft part up to the column-sum exchange, 3 = the CLIP
+// part (independent of the exchange), 2 = finalize
 static int forward_impl(const dsoft_plan_t* p, const void* gathered, const float* logit_scale,
                         const float* lambdas, void* state, void* scratch, float* lse_local,
                         float* losses, float* dbg, void* stream, int phase);
@@ -2116,14 +2117,14 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
                              float* losses, float* dbg, void* stream) {
   if (p && p->sym_w)
     return fail(DSOFT_EINVAL, "this plan shares the symmetric soft tiles across ranks (DSOFT_SYM_W): call "
-                              "dsoft_forward_phase(1), exchange the column sums, then dsoft_forward_phase(2)");
+                              "dsoft_forward_phase 1, 3 (next to the column-sum exchange), 2");
   return forward_impl(p, gathered, logit_scale, lambdas, state, scratch, lse_local, losses, dbg, stream, 0);
 }
 
 extern "C" int dsoft_forward_phase(const dsoft_plan_t* p, const void* gathered, const float* logit_scale,
                                    const float* lambdas, void* state, void* scratch, float* lse_local,
                                    float* losses, float* dbg, void* stream, int phase) {
-  if (phase != 1 && phase != 2) return fail(DSOFT_EINVAL, "phase must be 1 or 2");
+  if (phase < 1 || phase > 3) return fail(DSOFT_EINVAL, "phase must be 1, 3 or 2");
   return forward_impl(p, gathered, logit_scale, lambdas, state, scratch, lse_local, losses, dbg, stream, phase);
 }
 
@@ -2142,7 +2143,11 @@ static int forward_impl(const dsoft_plan_t* p, const void* gathered, const float
   int rc = make_maps(p, gathered, &tm, 64);  // 64-row boxes: each CTA of a pair stages half a column tile
   if (rc) return rc;
 
+  // phases of a DSOFT_SYM_W plan: 1 = operand statistics + soft tile kernel + column reduction, 3 = CLIP kernels
+  // (the caller's column-sum exchange runs next to them), 2 = finalize; 0 = everything
+  const bool do_soft = phase == 0 || phase == 1, do_clip = phase == 0 || phase == 3;
   if (phase != 2) {
+  if (do_soft) {
   prep_scalars_kernel<<<1, 32, 0, st>>>(logit_scale, p->have_soft ? p->sh.teacher_temp : 0.f,
                                         p->have_text ? p->sh.text_temp : 0.f, S + p->st_scal);
   CUDA_TRY(cudaGetLastError());
@@ -2164,6 +2169,7 @@ static int forward_impl(const dsoft_plan_t* p, const void* gathered, const float
                   st>>>(ra);
     CUDA_TRY(cudaGetLastError());
   }
+  }  // do_soft: scalars + norms
 
   if ((rc = set_smem(dsoft_fwd_kernel<MODE_CLIP, 2>, FWD_SMEM_BYTES))) return rc;
   if ((rc = set_smem(dsoft_fwd_kernel<MODE_SOFT, 2>, FWD_SMEM_BYTES))) return rc;
@@ -2174,7 +2180,7 @@ static int forward_impl(const dsoft_plan_t* p, const void* gathered, const float
   cudaStream_t ks = st;
   int lane = 0;
   FwdParams P;
-  if (p->have_soft) {
+  if (p->have_soft && do_soft) {
     memset(&P, 0, sizeof(P));
     P.nprod = p->have_text ? 3 : 2;
     P.bn = 2 * BN;
@@ -2224,6 +2230,7 @@ static int forward_impl(const dsoft_plan_t* p, const void* gathered, const float
     CUDA_TRY(cudaGetLastError());
   }
   // image -> text (loss.py:266/272) and text -> image (loss.py:267/273)
+  if (do_clip) {
   fill_clip_fwd(p, P, 0, 1, S + p->st_scal, X + p->sc_pc_it, S + p->st_diag);
   if ((rc = fk.lane(lane++, &ks))) return rc;
   if (p->clip_sym) {
@@ -2257,9 +2264,10 @@ static int forward_impl(const dsoft_plan_t* p, const void* gathered, const float
     }
     CUDA_TRY(cudaGetLastError());
   }
+  }  // do_clip
   if ((rc = fk.join())) return rc;
   }  // phase != 2
-  if (phase == 1) return 0;
+  if (phase == 1 || phase == 3) return 0;
 
   FinFwdArgs fa;
   fa.b = b;
@@ -2361,7 +2369,7 @@ static int make_gstore_map(const dsoft_plan* p, CUtensorMap* map, const __half* 
 
 static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* S, float* X, const float* lse_loc,
                               const float* lsec, const __half* v16, const float* gout, const float* lambdas,
-                              cudaStream_t st) {
+                              cudaStream_t st, bool do_soft = true, bool do_clip = true) {
   const float* colfac = S + p->st_colfac;
   const int b = p->sh.b;
   const int rbs = ceil_div(b, BM);
@@ -2381,7 +2389,7 @@ static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* 
   cudaStream_t ks = st;
   int lane = 0;
   FwdParams P;
-  if (p->have_soft) {
+  if (p->have_soft && do_soft) {
     if ((rc = fk.lane(lane++, &ks))) return rc;
     memset(&P, 0, sizeof(P));
     P.nprod = p->have_text ? 3 : 2;
@@ -2467,6 +2475,7 @@ static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* 
         return rc;
     }
   }
+  if (!do_clip) return fk.join();
   if (p->weighted) {
     // world == 1: ONE logit-gradient matrix carries  g_c * classic CE + g_w * weighted CE  of both directions
     // (loss.py:416-471 backward); the two gradient GEMMs below are the classic ones
@@ -2539,8 +2548,8 @@ static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* 
   return fk.join();
 }
 
-// phase 0: the whole backward; 1: everything up to the exchange of the transposed products of a DSOFT_SYM_W plan
-// (logit-gradient kernels + gradient GEMMs); 2: the finalize kernel
+// phase 0: the whole backward; of a DSOFT_SYM_W plan: 1 = the soft part up to the exchange of the transposed products
+// (logit-gradient kernel + gradient GEMMs), 3 = the CLIP part (independent of the exchange), 2 = the finalize kernel
 static int backward_impl(const dsoft_plan_t* p, const void* gathered, const void* state, void* scratch,
                          const float* lse_all, const float* gout, const float* lambdas, float* d_image,
                          float* d_text, float* d_student, float* d_scale, void* stream, int phase);
@@ -2550,7 +2559,7 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
                               float* d_text, float* d_student, float* d_scale, void* stream) {
   if (p && p->sym_w)
     return fail(DSOFT_EINVAL, "this plan shares the symmetric soft tiles across ranks (DSOFT_SYM_W): call "
-                              "dsoft_backward_phase(1), exchange the transposed products, then dsoft_backward_phase(2)");
+                              "dsoft_backward_phase 1, 3 (next to the exchange of the transposed products), 2");
   return backward_impl(p, gathered, state, scratch, lse_all, gout, lambdas, d_image, d_text, d_student, d_scale,
                        stream, 0);
 }
@@ -2558,7 +2567,7 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
 extern "C" int dsoft_backward_phase(const dsoft_plan_t* p, const void* gathered, const void* state, void* scratch,
                                     const float* lse_all, const float* gout, const float* lambdas, float* d_image,
                                     float* d_text, float* d_student, float* d_scale, void* stream, int phase) {
-  if (phase != 1 && phase != 2) return fail(DSOFT_EINVAL, "phase must be 1 or 2");
+  if (phase < 1 || phase > 3) return fail(DSOFT_EINVAL, "phase must be 1, 3 or 2");
   return backward_impl(p, gathered, state, scratch, lse_all, gout, lambdas, d_image, d_text, d_student, d_scale,
                        stream, phase);
 }
@@ -2609,26 +2618,32 @@ static int backward_impl(const dsoft_plan_t* p, const void* gathered, const void
 
   float* lsec = S + p->st_lsecols;
   const float* lse_loc = lse_all + static_cast<size_t>(p->sh.rank) * 5 * b;
+  // phases of a DSOFT_SYM_W plan: 1 = statistics relayout + fp16 operands + soft lane (G kernel, GEMMs incl. the
+  // transposed products), 3 = CLIP lanes (the caller's exchange of the transposed products runs next to them),
+  // 2 = finalize; 0 = everything
   if (phase != 2) {
+  __half* v16 = reinterpret_cast<__half*>(X + p->sc_v16);
+  if (phase != 3) {
   lse_stats_kernel<<<LSE_NB, 256, 0, st>>>(lse_all, p->sh.world, b, S + p->st_lsestat);
   CUDA_TRY(cudaGetLastError());
   lse_relayout_kernel<<<ceil_div(5 * p->Bcol, 1024), 256, 0, st>>>(
       lse_all, p->sh.world, b, p->Bcol, S + p->st_scal, S + p->st_lsestat, p->fast_t, p->row_only,
       p->row_only && !p->soft_local, lsec, S + p->st_colfac);
   CUDA_TRY(cudaGetLastError());
-  __half* v16 = reinterpret_cast<__half*>(X + p->sc_v16);
   make_v16_kernel<<<ceil_div(p->B, 8), 256, 0, st>>>(
       static_cast<const __nv_bfloat16*>(gathered), p->row_elems, p->B, p->sh.D, p->Dz, p->offI, p->offT,
       p->offZ, p->have_soft, p->have_text, S + p->st_rinv_z, S + p->st_rinv_t, v16, p->v_row, p->v_offT, p->v_offI,
       p->v_offZn, p->v_offTn);
   CUDA_TRY(cudaGetLastError());
+  }  // phase != 3
   CUtensorMap vmap;
   auto vmap_for = [&](int voff, int cols) {
     return make_map(&vmap, v16 + voff, p->B, cols, p->v_row, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 64);
   };
 
   if (p->gmat) {
-    if ((rc = backward_two_phase(p, gathered, S, X, lse_loc, lsec, v16, gout, lambdas, st))) return rc;
+    if ((rc = backward_two_phase(p, gathered, S, X, lse_loc, lsec, v16, gout, lambdas, st, phase != 3, phase != 1)))
+      return rc;
   } else {
   if ((rc = set_smem(dsoft_bwd_kernel<MODE_CLIP>, BWD_SMEM_BYTES))) return rc;
   if ((rc = set_smem(dsoft_bwd_kernel<MODE_SOFT>, BWD_SMEM_BYTES))) return rc;
@@ -2740,7 +2755,7 @@ static int backward_impl(const dsoft_plan_t* p, const void* gathered, const void
   if ((rc = fk.join())) return rc;
   }  // !p->gmat
   }  // phase != 2
-  if (phase == 1) return 0;
+  if (phase == 1 || phase == 3) return 0;
 
   FinBwdArgs fa;
   memset(&fa, 0, sizeof(fa));

@@ -24,6 +24,7 @@ Differences from the reference that are deliberate and documented in DESIGN.md:
 """
 from __future__ import annotations
 
+import contextlib
 import os
 from typing import Optional
 
@@ -144,6 +145,28 @@ class _SymW:
         off, d = (self.off_a3, self.Dz) if which == 0 else (self.off_a4, self.Dx)
         return scratch[off:off + self.b * d].view(self.b, d)
 
+    # ---- the exchanges run on a second stream, next to the CLIP kernels of phase 3 (DSOFT_SYMW_OVERLAP=0: in line)
+    _side = {}
+
+    @contextlib.contextmanager
+    def beside(self, dev):
+        """Code under this context is ordered after everything queued on the current stream so far and runs on the
+        exchange stream; `rejoin` orders the current stream after it."""
+        if dev.type != "cuda" or os.environ.get("DSOFT_SYMW_OVERLAP", "1") == "0":
+            yield
+            return
+        side = _SymW._side.get(dev.index)
+        if side is None:
+            side = _SymW._side[dev.index] = torch.cuda.Stream(dev, priority=-1)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            yield
+
+    def rejoin(self, dev):
+        side = _SymW._side.get(dev.index) if dev.type == "cuda" else None
+        if side is not None:
+            torch.cuda.current_stream(dev).wait_stream(side)
+
     # ---- the two exchanges over NCCL
     def exchange_forward(self, fwd_scratch, group):
         cs = self.colsum(fwd_scratch)
@@ -255,7 +278,7 @@ class CudaBackend:
         return (C.c_float * 4)(*[float(x) for x in lambdas])
 
     def forward(self, plan, gathered, logit_scale, lambdas, state, scratch, lse_local, losses, dbg=None, phase=0):
-        """phase 0: whole forward; 1 / 2: before / after the column-sum exchange of a plan with `symw`."""
+        """phase 0: whole forward; a plan with `symw`: 1 soft part, 3 CLIP part (next to the column-sum exchange), 2 finalize."""
         a = (plan.handle, _ptr(gathered), _ptr(logit_scale), self._lam(lambdas), _ptr(state), _ptr(scratch),
              _ptr(lse_local), _ptr(losses), _ptr(dbg), self._stream(gathered))
         if phase == 0:
@@ -265,7 +288,8 @@ class CudaBackend:
 
     def backward(self, plan, gathered, state, scratch, lse_all, gout, lambdas, d_image, d_text, d_student, d_scale,
                  phase=0):
-        """phase 0: whole backward; 1 / 2: before / after the exchange of the transposed products (`symw`)."""
+        """phase 0: whole backward; a plan with `symw`: 1 soft part, 3 CLIP part (next to the exchange of the transposed
+        products), 2 finalize."""
         a = (plan.handle, _ptr(gathered), _ptr(state), _ptr(scratch), _ptr(lse_all), _ptr(gout), self._lam(lambdas),
              _ptr(d_image), _ptr(d_text), _ptr(d_student), _ptr(d_scale), self._stream(gathered))
         if phase == 0:
@@ -421,10 +445,14 @@ class _DinoSoftFn(torch.autograd.Function):
         ls = logit_scale.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
         if getattr(plan, "symw", None) is not None:
             # symmetric soft tiles across ranks: the column sums this rank computed for other ranks' rows travel
-            # between the tile kernels and the finalize kernel (6 floats per row and owner)
-            be.forward(plan, gathered, ls, cfg.lambdas, state, scratch, lse_all[r], losses, None, phase=1)
-            plan.symw.exchange_forward(scratch, cfg.group)
-            be.forward(plan, gathered, ls, cfg.lambdas, state, scratch, lse_all[r], losses, None, phase=2)
+            # (6 floats per row and owner) while the CLIP tile kernels run; the finalize kernel needs both
+            fargs = (plan, gathered, ls, cfg.lambdas, state, scratch, lse_all[r], losses, None)
+            be.forward(*fargs, phase=1)
+            with plan.symw.beside(dev):
+                plan.symw.exchange_forward(scratch, cfg.group)
+            be.forward(*fargs, phase=3)
+            plan.symw.rejoin(dev)
+            be.forward(*fargs, phase=2)
         else:
             be.forward(plan, gathered, ls, cfg.lambdas, state, scratch, lse_all[r], losses, dbg if weighted else None)
         if W > 1 and needs_grad:
@@ -467,9 +495,13 @@ class _DinoSoftFn(torch.autograd.Function):
         args = (plan, gathered, state, scratch, lse_all, gout, ctx.cfg.lambdas, d_image, d_text, d_student, d_scale)
         if getattr(plan, "symw", None) is not None:
             # ... and the transposed gradient products (the reduce-scatter of `_AllGather.backward`, loss.py:59-64,
-            # restricted to the soft terms and to the half of the blocks the other rank did not compute itself)
+            # restricted to the soft terms and to the half of the blocks the other rank did not compute itself),
+            # next to the CLIP logit-gradient kernels and gradient GEMMs
             be.backward(*args, phase=1)
-            plan.symw.exchange_backward(scratch, ctx.cfg.group)
+            with plan.symw.beside(dev):
+                plan.symw.exchange_backward(scratch, ctx.cfg.group)
+            be.backward(*args, phase=3)
+            plan.symw.rejoin(dev)
             be.backward(*args, phase=2)
         else:
             be.backward(*args)

@@ -95,7 +95,7 @@ def test_eight_gpu_parity(oracle):
         pytest.skip("needs 8 GPUs")
     ctor = dict(local_loss=True, gather_with_grad=True, soft_scope="global")
     argd = dict(use_projection=True)
-    B, D, Dd, scale, world = 2048, 128, 192, 30.0, 8
+    B, D, Dd, scale, world = 4096, 128, 192, 30.0, 8  # b = 512: the symmetric soft tiles are shared across ranks
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), B, D, Dd, scale, argd, ctor, ret, "always"), nprocs=world, join=True)

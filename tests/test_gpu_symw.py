@@ -1,6 +1,7 @@
 """Symmetric soft tiles across ranks (DSOFT_SYM_W, include/dsoft.h): every pair of row blocks of the teacher /
 student / text Gram matrices is computed by ONE of its two ranks; column sums (forward) and transposed gradient
-products (backward) for the other rank's rows are exchanged between two phases of the C calls.
+products (backward) for the other rank's rows are exchanged between the phases of the C calls (1 soft part, 3 CLIP
+part - independent of the exchange -, 2 finalize).
 
 All ranks of a W-rank job are played on ONE GPU through the C ABI, the two exchanges being done by hand exactly as
 `_SymW.exchange_forward / exchange_backward` do over NCCL (same layout object).  Every rank is compared with the
@@ -40,6 +41,7 @@ def cuda_ranks_symw(pkg, img, txt, dino, student, scale, W):
     losses = [torch.empty(6, dtype=torch.float32, device=dev) for _ in plans]
     for r, pl in enumerate(plans):
         be.forward(pl, gathered, ls, LAMBDAS, states[r], fscr[r], lse_all[r], losses[r], phase=1)
+        be.forward(pl, gathered, ls, LAMBDAS, states[r], fscr[r], lse_all[r], losses[r], phase=3)
     # ---- forward exchange: column sums of primed block k -> rank (r + k) % W
     inbox = [torch.zeros((6, b), dtype=torch.float32, device=dev) for _ in plans]
     for r, pl in enumerate(plans):
@@ -59,8 +61,9 @@ def cuda_ranks_symw(pkg, img, txt, dino, student, scale, W):
         d_student = torch.empty((b, Dp), dtype=torch.float32, device=dev) if Dp else None
         d_scale = torch.empty(1, dtype=torch.float32, device=dev)
         outs.append((d_image, d_text, d_student, d_scale))
-        be.backward(pl, gathered, states[r], scr[r], lse_all, gout, LAMBDAS, d_image, d_text, d_student, d_scale,
-                    phase=1)
+        for phase in (1, 3):
+            be.backward(pl, gathered, states[r], scr[r], lse_all, gout, LAMBDAS, d_image, d_text, d_student, d_scale,
+                        phase=phase)
     # the receive lists must mirror the send lists
     for r, pl in enumerate(plans):
         expect = sorted((s, k, rows) for s, q in enumerate(plans) for peer, k, rows in q.symw.sends if peer == r)
