@@ -82,7 +82,8 @@ def lib() -> C.CDLL:
     global _lib
     with _lock:
         if _lib is None:
-            path = _build.LIB_PATH
+            # DSOFT_LIB: another build of the same sources (kernel A/B runs, scripts/build_variant.py)
+            path = os.environ.get("DSOFT_LIB") or _build.LIB_PATH
             if not os.path.exists(path):
                 raise DsoftError(
                     f"{path} is missing: the CUDA extension has not been built. Run "

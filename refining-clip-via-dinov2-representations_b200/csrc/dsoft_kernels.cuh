@@ -209,21 +209,62 @@ __device__ __forceinline__ void st_cs_v8(void* dst, const uint32_t (&w)[8]) {
                : "memory");
 }
 
+// Packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: one issue slot and one pass through the FMA pipe for two lanes'
+// worth of work).  The epilogues are issue-bound (two epilogue warps per scheduler next to the MMA stream), so their
+// element loops are written over column PAIRS.  -DDSOFT_PACKED_F32=0 compiles the same loops with scalar operations
+// (A/B arm; results agree up to the summation order, which is the same in both builds).
+#ifndef DSOFT_PACKED_F32
+#define DSOFT_PACKED_F32 1
+#endif
+__device__ __forceinline__ float2 pk(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 pk1(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 pk_mul(float2 a, float2 b) {
+#if DSOFT_PACKED_F32
+  return __fmul2_rn(a, b);
+#else
+  return make_float2(a.x * b.x, a.y * b.y);
+#endif
+}
+__device__ __forceinline__ float2 pk_add(float2 a, float2 b) {
+#if DSOFT_PACKED_F32
+  return __fadd2_rn(a, b);
+#else
+  return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+__device__ __forceinline__ float2 pk_fma(float2 a, float2 b, float2 c) {
+#if DSOFT_PACKED_F32
+  return __ffma2_rn(a, b, c);
+#else
+  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+__device__ __forceinline__ float2 pk_exp2(float2 a) { return make_float2(fast_exp2(a.x), fast_exp2(a.y)); }
+
 // Column sums over the 32 rows of a warp: every lane holds x[k] = the value of ITS row in column k; lane l returns
 // sum over the lanes of x[l].  Butterfly: a stage keeps the half of the columns that matches the lane's bit and
 // swaps the other half with the partner lane (31 shuffles; fixed order, so the result is deterministic).
 __device__ __forceinline__ float warp_colsum32(float (&x)[32], int lane) {
-#define DSOFT_CS_STAGE(O)                                               \
-  {                                                                     \
-    const bool up = (lane & O) != 0;                                    \
-    _Pragma("unroll") for (int i = 0; i < O; ++i) {                     \
-      const float send = up ? x[i] : x[i + O];                          \
-      const float keep = up ? x[i + O] : x[i];                          \
-      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);              \
-    }                                                                   \
+#define DSOFT_CS_STAGE(O)                                                                   \
+  {                                                                                         \
+    const bool up = (lane & O) != 0;                                                        \
+    _Pragma("unroll") for (int i = 0; i < O; i += 2) {                                      \
+      const float send0 = up ? x[i] : x[i + O], send1 = up ? x[i + 1] : x[i + 1 + O];       \
+      const float keep0 = up ? x[i + O] : x[i], keep1 = up ? x[i + 1 + O] : x[i + 1];       \
+      const float2 r = pk_add(pk(keep0, keep1), pk(__shfl_xor_sync(0xffffffffu, send0, O),  \
+                                                   __shfl_xor_sync(0xffffffffu, send1, O))); \
+      x[i] = r.x;                                                                           \
+      x[i + 1] = r.y;                                                                       \
+    }                                                                                       \
   }
-  DSOFT_CS_STAGE(16) DSOFT_CS_STAGE(8) DSOFT_CS_STAGE(4) DSOFT_CS_STAGE(2) DSOFT_CS_STAGE(1)
+  DSOFT_CS_STAGE(16) DSOFT_CS_STAGE(8) DSOFT_CS_STAGE(4) DSOFT_CS_STAGE(2)
 #undef DSOFT_CS_STAGE
+  {
+    const bool up = (lane & 1) != 0;
+    const float send = up ? x[0] : x[1];
+    const float keep = up ? x[1] : x[0];
+    x[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
   return x[0];
 }
 
@@ -567,6 +608,7 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       }
     } else if constexpr (MODE == MODE_CLIP) {
       const float s2 = P.scal[SC_SCALE_L2];
+      const float2 s22 = pk1(s2);
       float m = M_FLOOR, sum = 0.f, dg = 0.f;
       bool have_dg = false;
       int it = 0;
@@ -588,7 +630,11 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
           }
           float x[32];
 #pragma unroll
-          for (int e = 0; e < 32; ++e) x[e] = v[e] * s2;
+          for (int e = 0; e < 32; e += 2) {
+            const float2 xx = pk_mul(pk(v[e], v[e + 1]), s22);
+            x[e] = xx.x;
+            x[e + 1] = xx.y;
+          }
           if (jrel0 + 32 > P.ncols) {
 #pragma unroll
             for (int e = 0; e < 32; ++e)
@@ -598,10 +644,12 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
 #pragma unroll
           for (int e = 4; e < 32; ++e) cm[e & 3] = fmaxf(cm[e & 3], x[e]);
           const float mnew = fmaxf(m, fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])));
-          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          const float2 nm2 = pk1(-mnew);
+          float2 acc[2] = {pk1(0.f), pk1(0.f)};
 #pragma unroll
-          for (int e = 0; e < 32; ++e) acc[e & 3] += fast_exp2(x[e] - mnew);
-          sum = sum * fast_exp2(m - mnew) + ((acc[0] + acc[1]) + (acc[2] + acc[3]));
+          for (int e = 0; e < 32; e += 2)
+            acc[(e >> 1) & 1] = pk_add(acc[(e >> 1) & 1], pk_exp2(pk_add(pk(x[e], x[e + 1]), nm2)));
+          sum = sum * fast_exp2(m - mnew) + ((acc[0].x + acc[0].y) + (acc[1].x + acc[1].y));
           m = mnew;
         }
         tc_fence_before();
@@ -835,13 +883,16 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
           const float mw = warp_max_f32(mo);
           float ref = mw, csum, cmax = mw;
           if (mw - 80.f <= lo) {
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            float2 acc[2] = {pk1(0.f), pk1(0.f)};
+            const float2 as22 = pk1(as2), nmw2 = pk1(-mw);
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              v[e] = fast_exp2(fmaf(v[e], as2, -mw));
-              acc[e & 3] += v[e];
+            for (int e = 0; e < 32; e += 2) {
+              const float2 ex = pk_exp2(pk_fma(pk(v[e], v[e + 1]), as22, nmw2));
+              v[e] = ex.x;
+              v[e + 1] = ex.y;
+              acc[(e >> 1) & 1] = pk_add(acc[(e >> 1) & 1], ex);
             }
-            csum = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+            csum = (acc[0].x + acc[0].y) + (acc[1].x + acc[1].y);
           } else {
             ref = mo;
             float x[32], acc = 0.f;
@@ -889,6 +940,8 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       const bool live_row = li < P.b;         // rows past b are K entries of the transposed GEMM: keep them zero
       const bool ds_both = P.ds_both != 0;
       float dsacc = 0.f;
+      float2 dsacc2 = pk1(0.f);  // fast form: even / odd columns
+      const float2 s22 = pk1(s2), ncref2 = pk1(-cref), fr2 = pk1(fr);
       // per-column values: lane l fetches columns 4l .. 4l+3 of this warp's 128-column strip ONE TILE AHEAD (a
       // single coalesced 16-byte load per lane and tile) and the warp broadcasts them with shuffles.  Eight
       // broadcast loads per 32-column chunk, one chunk ahead, left the epilogue waiting on L2 (long-scoreboard
@@ -938,12 +991,14 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
             for (int e4 = 0; e4 < 8; ++e4) {
               const float fc[4] = {cur[e4].x, cur[e4].y, cur[e4].z, cur[e4].w};
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
+              for (int k = 0; k < 4; k += 2) {
                 const int e = 4 * e4 + k;
-                const float ex = fast_exp2(fmaf(v[e], s2, -cref));
-                const float gg = ex * (fr + fc[k]);
-                dsacc = fmaf(ds_both ? gg : ex * fr, v[e], dsacc);  // ragged columns carry dot = 0
-                g[e] = gg;
+                const float2 vv = pk(v[e], v[e + 1]);
+                const float2 ex = pk_exp2(pk_fma(vv, s22, ncref2));
+                const float2 gg = pk_mul(ex, pk_add(fr2, pk(fc[k], fc[k + 1])));
+                dsacc2 = pk_fma(ds_both ? gg : pk_mul(ex, fr2), vv, dsacc2);  // ragged columns carry dot = 0
+                g[e] = gg.x;
+                g[e + 1] = gg.y;
               }
             }
           } else {
@@ -978,7 +1033,7 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
         }
       }
       if (lane == 0) bulk_wait_group<0>();  // the stores have landed before the CTA may exit
-      if (li < P.b) P.ds_part[sp * P.b + li] = dsacc;
+      if (li < P.b) P.ds_part[sp * P.b + li] = dsacc + (dsacc2.x + dsacc2.y);
     } else if constexpr (MODE == MODE_SOFT_G) {
       // G_aj = [(2^(p-ls_a) + 2^(p-ls_j)) - (2^(q-lt_a) + 2^(q-lt_j))] * mant(1/||y_j||), j != a, for the
       // student (-> gout[0]) and the text term (-> gout[1]) from ONE teacher tile.
@@ -998,6 +1053,7 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       const float lt = P.lse_row[0][lic];
       const bool fast_t = P.fast_t != 0;
       const float frt = fast_t ? exp2f(mt - lt) : 0.f;
+      const float2 cq2 = pk1(cq), nmt2 = pk1(-mt), nfrt2 = pk1(-frt);
       const bool real_block = rb * BM < P.b;
       const bool live_row = li < P.b;  // rows past b are K entries of the transposed gradient GEMM: keep them zero
       float E[128];  // -(teacher terms) of this thread's 128 columns, kept across the student / text products
@@ -1036,13 +1092,19 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
               const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
               const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
+              for (int k = 0; k < 4; k += 2) {
                 const int e = 4 * e4 + k;
-                const float q2 = v[e] * cq * rr[k];
-                if (fast_t) {
-                  E[c * 32 + e] = -fast_exp2(q2 - mt) * (frt + ll[k]);
+                if (fast_t) {  // -2^(q - M_t) (2^(M_t - lt_a) + 2^(M_t - lt_j))
+                  const float2 ex = pk_exp2(pk_fma(pk(v[e], v[e + 1]), pk_mul(cq2, pk(rr[k], rr[k + 1])), nmt2));
+                  const float2 r = pk_mul(ex, pk_add(nfrt2, pk(-ll[k], -ll[k + 1])));
+                  E[c * 32 + e] = r.x;
+                  E[c * 32 + e + 1] = r.y;
                 } else {
-                  E[c * 32 + e] = -(fast_exp2(q2 - lt) + fast_exp2(q2 - ll[k]));
+#pragma unroll
+                  for (int u = 0; u < 2; ++u) {
+                    const float q2 = v[e + u] * cq * rr[k + u];
+                    E[c * 32 + e + u] = -(fast_exp2(q2 - lt) + fast_exp2(q2 - ll[k + u]));
+                  }
                 }
               }
             }
@@ -1057,6 +1119,7 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
           const float cy = ry * my;
           const float fry = exp2f(my - P.lse_row[p][lic]);
           const float rowf = P.tri ? mant12(ry) : 1.f;
+          const float2 cy2 = pk1(cy), nmy2 = pk1(-my), fry2 = pk1(fry), rowf2 = pk1(rowf);
           uint32_t rA[32], rB[32];
           tmem_ld32_nowait(lane_addr + slot * CT + half * 128, rA);
 #pragma unroll
@@ -1087,12 +1150,19 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
               const float ll[4] = {l4.x, l4.y, l4.z, l4.w};
               float g4[4];
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
+              for (int k = 0; k < 4; k += 2) {
                 const int e = 4 * e4 + k;
-                const float ex = fast_exp2(fmaf(v[e] * cy, rr[k], -my));
-                float g = fmaf(ex, fry + ll[k], E[c * 32 + e]);  // symmetric in (a, j) when world == 1
-                if (need_mask && ((gj0 + e == gi) || (jrel0 + e >= P.ncols) || !live_row)) g = 0.f;
-                g4[k] = g * (rowf * mant12(rr[k]));
+                const float2 rk = pk(rr[k], rr[k + 1]);
+                const float2 ex = pk_exp2(pk_fma(pk(v[e], v[e + 1]), pk_mul(cy2, rk), nmy2));
+                // symmetric in (a, j) when world == 1
+                float2 g = pk_fma(ex, pk_add(fry2, pk(ll[k], ll[k + 1])), pk(E[c * 32 + e], E[c * 32 + e + 1]));
+                if (need_mask) {
+                  if ((gj0 + e == gi) || (jrel0 + e >= P.ncols) || !live_row) g.x = 0.f;
+                  if ((gj0 + e + 1 == gi) || (jrel0 + e + 1 >= P.ncols) || !live_row) g.y = 0.f;
+                }
+                g = pk_mul(g, pk_mul(rowf2, pk(mant12(rk.x), mant12(rk.y))));
+                g4[k] = g.x;
+                g4[k + 1] = g.y;
               }
               w16[2 * e4 + 0] = pack_f16x2(g4[0], g4[1]);
               w16[2 * e4 + 1] = pack_f16x2(g4[2], g4[3]);
@@ -1356,7 +1426,9 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       // dead row (2^arg = 0 without a select).  The weighted sums are kept relative to the fixed maxima,
       // sum w (q - M_t) etc.; finalize_fwd adds M * Zt back.
       const float bias_t = live_row ? -mt2 : NEG_BIG;
-      float zt = 0.f, aq = 0.f, ap = 0.f, ar = 0.f, zs = 0.f, zx = 0.f;
+      const float2 cq2 = pk1(cq), bias_t2 = pk1(bias_t);
+      float2 zt2 = pk1(0.f), aq2 = pk1(0.f);  // even / odd columns
+      float ap = 0.f, ar = 0.f, zs = 0.f, zx = 0.f;
       float w[128];  // teacher weights 2^(q - M_t) of this thread's 128 columns, kept across the three products
       const size_t cp_stride = static_cast<size_t>(P.cp_rows) * P.cp_pitch;  // one quantity of the column partials
       float* cp_row = P.colpart + static_cast<size_t>(rb * 4 + q) * P.cp_pitch;
@@ -1396,15 +1468,22 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
               const float4 r = rc[e4];
               const float rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
+              for (int k = 0; k < 4; k += 2) {
                 const int e = 4 * e4 + k;
-                const float arg = fmaf(__uint_as_float(rcur[e]), cq * rr[k], bias_t);
-                float we = fast_exp2(arg);
-                if (need_mask && (jrel0 + e >= P.ncols || jrel0 + e == li)) we = 0.f;  // ragged; teacher diag masked
-                w[c * 32 + e] = we;
-                wq[e] = we * arg;
-                zt += we;
-                aq += wq[e];
+                const float2 arg = pk_fma(pk(__uint_as_float(rcur[e]), __uint_as_float(rcur[e + 1])),
+                                          pk_mul(cq2, pk(rr[k], rr[k + 1])), bias_t2);
+                float2 we = pk_exp2(arg);
+                if (need_mask) {  // ragged; teacher diag masked
+                  if (jrel0 + e >= P.ncols || jrel0 + e == li) we.x = 0.f;
+                  if (jrel0 + e + 1 >= P.ncols || jrel0 + e + 1 == li) we.y = 0.f;
+                }
+                const float2 wa = pk_mul(we, arg);
+                w[c * 32 + e] = we.x;
+                w[c * 32 + e + 1] = we.y;
+                wq[e] = wa.x;
+                wq[e + 1] = wa.y;
+                zt2 = pk_add(zt2, we);
+                aq2 = pk_add(aq2, wa);
               }
             }
             if (offdiag) {  // warp-uniform
@@ -1424,7 +1503,8 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
           tc_fence_after();
           const float cs = (p == 1) ? cp : cr;
           const float bias_y = live_row ? -((p == 1) ? ms2 : mx2) : NEG_BIG;
-          float b0 = 0.f, b1 = 0.f;
+          const float2 cs2 = pk1(cs), bias_y2 = pk1(bias_y);
+          float2 b0 = pk1(0.f), b1 = pk1(0.f);
           uint32_t rA[32], rB[32];
           tmem_ld32_nowait(lane_addr + slot * CT + half * 128, rA);
 #pragma unroll
@@ -1447,15 +1527,23 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
               const float4 r = rc[e4];
               const float rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
+              for (int k = 0; k < 4; k += 2) {
                 const int e = 4 * e4 + k;
-                const float arg = fmaf(__uint_as_float(rcur[e]), cs * rr[k], bias_y);
-                float ex = fast_exp2(arg);
-                if (rag && jrel0 + e >= P.ncols) ex = 0.f;
-                es[e] = ex;
-                wp[e] = w[c * 32 + e] * arg;  // w is zero on masked entries and in dead rows
-                b0 += ex;
-                b1 += wp[e];
+                const float2 arg = pk_fma(pk(__uint_as_float(rcur[e]), __uint_as_float(rcur[e + 1])),
+                                          pk_mul(cs2, pk(rr[k], rr[k + 1])), bias_y2);
+                float2 ex = pk_exp2(arg);
+                if (rag) {
+                  if (jrel0 + e >= P.ncols) ex.x = 0.f;
+                  if (jrel0 + e + 1 >= P.ncols) ex.y = 0.f;
+                }
+                // w is zero on masked entries and in dead rows
+                const float2 wa = pk_mul(pk(w[c * 32 + e], w[c * 32 + e + 1]), arg);
+                es[e] = ex.x;
+                es[e + 1] = ex.y;
+                wp[e] = wa.x;
+                wp[e + 1] = wa.y;
+                b0 = pk_add(b0, ex);
+                b1 = pk_add(b1, wa);
               }
             }
             if (offdiag) {
@@ -1465,10 +1553,11 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
               cp_row[(p == 1 ? 2 : 3) * cp_stride + jrel0 + lane] = s1;
             }
           }
-          if (p == 1) { zs += b0; ap += b1; } else { zx += b0; ar += b1; }
+          if (p == 1) { zs += b0.x + b0.y; ap += b1.x + b1.y; } else { zx += b0.x + b0.y; ar += b1.x + b1.y; }
         }
         mbar_arrive(smem_u32(&col_empty[cb]));
       }
+      const float zt = zt2.x + zt2.y, aq = aq2.x + aq2.y;
       if (li < P.b) {  // same partial layout as MODE_SOFT; the maximum is the fixed one
         const int o = sp * P.b + li;
         const int st = P.npart * P.b;

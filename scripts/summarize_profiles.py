@@ -117,11 +117,40 @@ def full_summary(tag, rep=None, out_name=None):
     return out
 
 
+def traffic_table(tag, summary=None):
+    """profiles/ncu_traffic.csv (read by bench.py for `roofline.traffic`): DRAM bytes read + written per launch of
+    the default workload's tile kernels, keyed by bench.py's kernel names.  One step at world 1 launches, in order:
+    soft forward <9>, CLIP forward <10>, soft G <4>, student GEMM, text GEMM, CLIP G <3>, image GEMM, text^T GEMM."""
+    summary = summary or os.path.join(PROF, f"{tag}_ncu_full_tile_kernels.csv")
+    if not os.path.exists(summary):
+        return
+    with open(summary) as f:
+        rows = list(csv.DictReader(l for l in f if not l.startswith('"#')))
+    names = {"dsoft_fwd_kernel<9, 2>": ["fwd_soft"], "dsoft_fwd_kernel<10, 2>": ["fwd_clip_i2t"],
+             "dsoft_fwd_kernel<4, 2>": ["bwd_build_g_soft"], "dsoft_fwd_kernel<3, 2>": ["bwd_build_g_clip"],
+             "dsoft_gy_kernel<0>": ["bwd_student", "bwd_text", "bwd_clip_image"], "dsoft_gy_kernel<1>": ["bwd_clip_text"]}
+    sha = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+    seen = collections.Counter()
+    with open(os.path.join(PROF, "ncu_traffic.csv"), "w") as f:
+        f.write("# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch, ncu --set full --clock-control none,\n"
+                "# default bench workload (B=32768, one B200); written by scripts/summarize_profiles.py\n")
+        f.write("kernel,dram_bytes,source,git_sha\n")
+        for r in rows:
+            k = r["kernel"].replace("void ", "")
+            if k not in names or seen[k] >= len(names[k]):
+                continue
+            name = names[k][seen[k]]
+            seen[k] += 1
+            tot = (float(r["dram__bytes_read.sum"]) + float(r["dram__bytes_write.sum"])) * 1e9
+            f.write(f"{name},{tot:.6g},{os.path.basename(summary)},{sha}\n")
+
+
 def main():
     tag = sys.argv[1]
     os.makedirs(PROF, exist_ok=True)
     launch_summary(tag)
     full_summary(tag)
+    traffic_table(tag)
     for fn in sorted(os.listdir(OUT)):
         if fn.startswith(f"{tag}_bench") and fn.endswith(".json"):
             shutil.copy(os.path.join(OUT, fn), os.path.join(PROF, fn))
