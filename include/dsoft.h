@@ -126,23 +126,25 @@ int dsoft_head_forward(const dsoft_plan_t* plan, void* gathered_dev, const void*
                        const void* w2_dev, const float* b2_dev, int32_t hidden_dim, void* hidden_dev, void* stream);
 
 /* Symmetric soft tiles across ranks (world > 1, global soft scope, gather_with_grad, DSOFT_F_GMAT, local batch a
- * multiple of 512; environment DSOFT_SYM_W=0 switches it off).  The teacher / student / text Gram matrices are
+ * multiple of 512 and a per-rank block of more than 2^28 similarity entries; environment DSOFT_SYM_W=0 switches it
+ * off, DSOFT_SYM_W=1 drops the size condition).  The teacher / student / text Gram matrices are
  * symmetric, so each pair of row blocks is computed by ONE of its two ranks, and what belongs to the other rank's
  * rows is exchanged by the caller - the reduce-scatter of the gathered-feature gradients that `gather_features`
  * implies (loss.py:59-64, `_AllGather.backward`), restricted to the soft terms:
- *   dsoft_forward_phase(.., 1)   operand statistics, soft tile kernel + column reductions
+ *   dsoft_forward_phase(.., 4)   operand statistics (scalars, norms)
+ *   dsoft_forward_phase(.., 1)   soft tile kernel + column reductions
  *   caller: the column sums [6][b] of every primed block k >= 1 go to rank (rank + k) % world, the received ones are
  *           added to the first b columns (dsoft_plan_symw_info gives offsets and sizes)
- *   dsoft_forward_phase(.., 3)   CLIP tile kernels; touches nothing the exchange touches, so the caller runs the
- *                                exchange on a second stream next to it
- *   dsoft_forward_phase(.., 2)   finalize (losses, log-sum-exps): after phase 3 and the exchange
- *   dsoft_backward_phase(.., 1)  statistics relayout, fp16 operands, soft logit-gradient kernel + its gradient GEMMs,
- *                                incl. the transposed products
+ *   dsoft_forward_phase(.., 3)   CLIP tile kernels; needs phase 4 only and touches nothing phase 1 or the exchange
+ *                                touch, so the caller may run it on another stream next to them
+ *   dsoft_forward_phase(.., 2)   finalize (losses, log-sum-exps): after phases 1 and 3 and the exchange
+ *   dsoft_backward_phase(.., 4)  statistics relayout, fp16 gradient operands
+ *   dsoft_backward_phase(.., 1)  soft logit-gradient kernel + its gradient GEMMs, incl. the transposed products
  *   caller: rows [(k-1) b, k b) of the transposed products go to rank (rank + k) % world, the received ones are added
  *           to this rank's own partial sums (split 0)
- *   dsoft_backward_phase(.., 3)  CLIP logit-gradient kernels + gradient GEMMs (next to the exchange, as above)
- *   dsoft_backward_phase(.., 2)  finalize (chain rule, outputs): after phase 3 and the exchange
- * Every call of one pass takes the same arguments; phases 1 and 3 go to the same stream in that order.
+ *   dsoft_backward_phase(.., 3)  CLIP logit-gradient kernels + gradient GEMMs (as above: after phase 4, beside 1)
+ *   dsoft_backward_phase(.., 2)  finalize (chain rule, outputs): after phases 1 and 3 and the exchange
+ * Every call of one pass takes the same arguments.
  * dsoft_forward / dsoft_backward refuse such a plan.  Arguments as for dsoft_forward / dsoft_backward. */
 int dsoft_plan_symw_info(const dsoft_plan_t* plan, long long* out12, int n);
 int dsoft_forward_phase(const dsoft_plan_t* plan, const void* gathered_dev, const float* logit_scale_dev,
@@ -223,6 +225,9 @@ int dsoft_profile_read(double* ms_sum, int* counts, int n);
  * active so that per-kernel durations are isolated), on = 1 always forks, on < 0 (default, or the
  * DSOFT_CONCURRENCY=0/1 variable unset) forks only for small per-rank blocks, where it pays. */
 int dsoft_set_concurrency(int on);
+/* What the launches of `plan` will do right now: 0 = serial on `stream`, 1 = forked lanes, 2 = serial because the
+ * recorder is on (a caller that overlaps the phases of a DSOFT_SYM_W plan on its own streams must not do so then). */
+int dsoft_plan_concurrency(const dsoft_plan_t* plan);
 
 /* Test / bring-up helper: C[M][N] (fp32) = A[M][K] . B[N][K]^T with bf16 operands through the same
  * TMA + tcgen05 tile path the loss kernels use (128 x 128 tiles). */

@@ -44,6 +44,7 @@ PROTOTYPES = {
     "dsoft_plan_kernel_flops": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]),
     "dsoft_profile_enable": (C.c_int, [C.c_int]),
     "dsoft_set_concurrency": (C.c_int, [C.c_int]),
+    "dsoft_plan_concurrency": (C.c_int, [C.c_void_p]),
     "dsoft_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]),
     "dsoft_plan_launches_forward": (C.c_int, [C.c_void_p]),
     "dsoft_plan_launches_backward": (C.c_int, [C.c_void_p]),

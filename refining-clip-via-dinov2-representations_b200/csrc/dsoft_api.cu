@@ -220,9 +220,15 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   p->s_col0 = p->soft_local ? sh->rank * sh->b : 0;
   p->s_ncols = p->soft_local ? sh->b : p->B;
   {
+    // DSOFT_SYM_W: 0 = never, 1 = whenever the plan allows it, unset = only for per-rank blocks above 2^28 similarity
+    // entries.  Below that the step is bound by the host (Python + ctypes + NCCL enqueue, ~2.5 ms per step), and the
+    // two extra exchanges cost more host time than the halved soft tiles save on the GPU: global batch 32768 on
+    // 8 GPUs 2.56 ms with the shared tiles against 2.47 ms without, on 2 GPUs 7.4 ms against 8.85 ms.
     const char* e = getenv("DSOFT_SYM_W");
+    const bool big = static_cast<double>(sh->b) * p->B > 268435456.0;
     p->sym_w = soft && sh->world > 1 && !p->soft_local && !p->row_only && (sh->flags & DSOFT_F_GMAT) &&
-               1.4426950408889634 / sh->teacher_temp <= 60.0 && sh->b % 512 == 0 && !(e && e[0] == '0');
+               1.4426950408889634 / sh->teacher_temp <= 60.0 && sh->b % 512 == 0 &&
+               (e ? e[0] != '0' : big);
     p->sw_ncols_a = 0;
     p->sw_rb_half = 0;
     if (p->sym_w) {
@@ -1440,6 +1446,12 @@ static bool concurrency_on(const dsoft_plan* p) {
   return static_cast<double>(p->sh.b) * p->B <= 268435456.0;
 }
 
+extern "C" int dsoft_plan_concurrency(const dsoft_plan_t* p) {
+  if (!p) return 0;
+  if (g_prof.on) return 2;
+  return concurrency_on(p) ? 1 : 0;
+}
+
 struct SideStreams {
   bool ready = false;
   cudaStream_t s[NSIDE];
@@ -2106,8 +2118,8 @@ extern "C" int dsoft_pair_stats(const void* clip_a, const void* clip_b, int32_t 
   return launch_fwd_pair(dsoft_fwd_kernel<MODE_PAIRS, 2>, ceil_div(n, BM), nsplit, st, tm, P);
 }
 
-// phase 0: the whole forward; of a DSOFT_SYM_W plan: 1 = the soft part up to the column-sum exchange, 3 = the CLIP
-// part (independent of the exchange), 2 = finalize
+// phase 0: the whole forward; of a DSOFT_SYM_W plan: 4 = operand statistics, 1 = the soft part up to the column-sum
+// exchange, 3 = the CLIP part (independent of 1 and of the exchange), 2 = finalize
 static int forward_impl(const dsoft_plan_t* p, const void* gathered, const float* logit_scale,
                         const float* lambdas, void* state, void* scratch, float* lse_local,
                         float* losses, float* dbg, void* stream, int phase);
@@ -2117,14 +2129,14 @@ extern "C" int dsoft_forward(const dsoft_plan_t* p, const void* gathered, const 
                              float* losses, float* dbg, void* stream) {
   if (p && p->sym_w)
     return fail(DSOFT_EINVAL, "this plan shares the symmetric soft tiles across ranks (DSOFT_SYM_W): call "
-                              "dsoft_forward_phase 1, 3 (next to the column-sum exchange), 2");
+                              "dsoft_forward_phase 4, 1, 3 (next to the column-sum exchange), 2");
   return forward_impl(p, gathered, logit_scale, lambdas, state, scratch, lse_local, losses, dbg, stream, 0);
 }
 
 extern "C" int dsoft_forward_phase(const dsoft_plan_t* p, const void* gathered, const float* logit_scale,
                                    const float* lambdas, void* state, void* scratch, float* lse_local,
                                    float* losses, float* dbg, void* stream, int phase) {
-  if (phase < 1 || phase > 3) return fail(DSOFT_EINVAL, "phase must be 1, 3 or 2");
+  if (phase < 1 || phase > 4) return fail(DSOFT_EINVAL, "phase must be 4, 1, 3 or 2");
   return forward_impl(p, gathered, logit_scale, lambdas, state, scratch, lse_local, losses, dbg, stream, phase);
 }
 
@@ -2143,11 +2155,11 @@ static int forward_impl(const dsoft_plan_t* p, const void* gathered, const float
   int rc = make_maps(p, gathered, &tm, 64);  // 64-row boxes: each CTA of a pair stages half a column tile
   if (rc) return rc;
 
-  // phases of a DSOFT_SYM_W plan: 1 = operand statistics + soft tile kernel + column reduction, 3 = CLIP kernels
+  // phases of a DSOFT_SYM_W plan: 4 = operand statistics, 1 = soft tile kernel + column reduction, 3 = CLIP kernels
   // (the caller's column-sum exchange runs next to them), 2 = finalize; 0 = everything
-  const bool do_soft = phase == 0 || phase == 1, do_clip = phase == 0 || phase == 3;
+  const bool do_pro = phase == 0 || phase == 4, do_soft = phase == 0 || phase == 1, do_clip = phase == 0 || phase == 3;
   if (phase != 2) {
-  if (do_soft) {
+  if (do_pro) {
   prep_scalars_kernel<<<1, 32, 0, st>>>(logit_scale, p->have_soft ? p->sh.teacher_temp : 0.f,
                                         p->have_text ? p->sh.text_temp : 0.f, S + p->st_scal);
   CUDA_TRY(cudaGetLastError());
@@ -2169,7 +2181,7 @@ static int forward_impl(const dsoft_plan_t* p, const void* gathered, const float
                   st>>>(ra);
     CUDA_TRY(cudaGetLastError());
   }
-  }  // do_soft: scalars + norms
+  }  // do_pro: scalars + norms
 
   if ((rc = set_smem(dsoft_fwd_kernel<MODE_CLIP, 2>, FWD_SMEM_BYTES))) return rc;
   if ((rc = set_smem(dsoft_fwd_kernel<MODE_SOFT, 2>, FWD_SMEM_BYTES))) return rc;
@@ -2267,7 +2279,7 @@ static int forward_impl(const dsoft_plan_t* p, const void* gathered, const float
   }  // do_clip
   if ((rc = fk.join())) return rc;
   }  // phase != 2
-  if (phase == 1 || phase == 3) return 0;
+  if (phase != 0 && phase != 2) return 0;
 
   FinFwdArgs fa;
   fa.b = b;
@@ -2548,8 +2560,9 @@ static int backward_two_phase(const dsoft_plan* p, const void* gathered, float* 
   return fk.join();
 }
 
-// phase 0: the whole backward; of a DSOFT_SYM_W plan: 1 = the soft part up to the exchange of the transposed products
-// (logit-gradient kernel + gradient GEMMs), 3 = the CLIP part (independent of the exchange), 2 = the finalize kernel
+// phase 0: the whole backward; of a DSOFT_SYM_W plan: 4 = statistics relayout + fp16 operands, 1 = the soft part up to
+// the exchange of the transposed products (logit-gradient kernel + gradient GEMMs), 3 = the CLIP part (independent of
+// 1 and of the exchange), 2 = the finalize kernel
 static int backward_impl(const dsoft_plan_t* p, const void* gathered, const void* state, void* scratch,
                          const float* lse_all, const float* gout, const float* lambdas, float* d_image,
                          float* d_text, float* d_student, float* d_scale, void* stream, int phase);
@@ -2559,7 +2572,7 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
                               float* d_text, float* d_student, float* d_scale, void* stream) {
   if (p && p->sym_w)
     return fail(DSOFT_EINVAL, "this plan shares the symmetric soft tiles across ranks (DSOFT_SYM_W): call "
-                              "dsoft_backward_phase 1, 3 (next to the exchange of the transposed products), 2");
+                              "dsoft_backward_phase 4, 1, 3 (next to the exchange of the transposed products), 2");
   return backward_impl(p, gathered, state, scratch, lse_all, gout, lambdas, d_image, d_text, d_student, d_scale,
                        stream, 0);
 }
@@ -2567,7 +2580,7 @@ extern "C" int dsoft_backward(const dsoft_plan_t* p, const void* gathered, const
 extern "C" int dsoft_backward_phase(const dsoft_plan_t* p, const void* gathered, const void* state, void* scratch,
                                     const float* lse_all, const float* gout, const float* lambdas, float* d_image,
                                     float* d_text, float* d_student, float* d_scale, void* stream, int phase) {
-  if (phase < 1 || phase > 3) return fail(DSOFT_EINVAL, "phase must be 1, 3 or 2");
+  if (phase < 1 || phase > 4) return fail(DSOFT_EINVAL, "phase must be 4, 1, 3 or 2");
   return backward_impl(p, gathered, state, scratch, lse_all, gout, lambdas, d_image, d_text, d_student, d_scale,
                        stream, phase);
 }
@@ -2623,7 +2636,7 @@ static int backward_impl(const dsoft_plan_t* p, const void* gathered, const void
   // 2 = finalize; 0 = everything
   if (phase != 2) {
   __half* v16 = reinterpret_cast<__half*>(X + p->sc_v16);
-  if (phase != 3) {
+  if (phase == 0 || phase == 4) {
   lse_stats_kernel<<<LSE_NB, 256, 0, st>>>(lse_all, p->sh.world, b, S + p->st_lsestat);
   CUDA_TRY(cudaGetLastError());
   lse_relayout_kernel<<<ceil_div(5 * p->Bcol, 1024), 256, 0, st>>>(
@@ -2635,14 +2648,15 @@ static int backward_impl(const dsoft_plan_t* p, const void* gathered, const void
       p->offZ, p->have_soft, p->have_text, S + p->st_rinv_z, S + p->st_rinv_t, v16, p->v_row, p->v_offT, p->v_offI,
       p->v_offZn, p->v_offTn);
   CUDA_TRY(cudaGetLastError());
-  }  // phase != 3
+  }  // prologue
   CUtensorMap vmap;
   auto vmap_for = [&](int voff, int cols) {
     return make_map(&vmap, v16 + voff, p->B, cols, p->v_row, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 64);
   };
 
   if (p->gmat) {
-    if ((rc = backward_two_phase(p, gathered, S, X, lse_loc, lsec, v16, gout, lambdas, st, phase != 3, phase != 1)))
+    if ((rc = backward_two_phase(p, gathered, S, X, lse_loc, lsec, v16, gout, lambdas, st, phase == 0 || phase == 1,
+                                 phase == 0 || phase == 3)))
       return rc;
   } else {
   if ((rc = set_smem(dsoft_bwd_kernel<MODE_CLIP>, BWD_SMEM_BYTES))) return rc;
@@ -2755,7 +2769,7 @@ static int backward_impl(const dsoft_plan_t* p, const void* gathered, const void
   if ((rc = fk.join())) return rc;
   }  // !p->gmat
   }  // phase != 2
-  if (phase == 1 || phase == 3) return 0;
+  if (phase != 0 && phase != 2) return 0;
 
   FinBwdArgs fa;
   memset(&fa, 0, sizeof(fa));

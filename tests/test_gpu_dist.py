@@ -24,6 +24,7 @@ def _worker(rank, world, port, B, D, Dd, scale, argd, ctor, ret, gmat):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["DSOFT_GMAT"] = gmat  # backward implementation (read when the package is imported)
+    os.environ["DSOFT_SYM_W"] = "1"  # share the symmetric soft tiles across ranks wherever the plan allows it
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)

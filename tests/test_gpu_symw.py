@@ -1,7 +1,7 @@
 """Symmetric soft tiles across ranks (DSOFT_SYM_W, include/dsoft.h): every pair of row blocks of the teacher /
 student / text Gram matrices is computed by ONE of its two ranks; column sums (forward) and transposed gradient
-products (backward) for the other rank's rows are exchanged between the phases of the C calls (1 soft part, 3 CLIP
-part - independent of the exchange -, 2 finalize).
+products (backward) for the other rank's rows are exchanged between the phases of the C calls (4 operand statistics, 1 soft
+part, 3 CLIP part - independent of 1 and of the exchange -, 2 finalize).
 
 All ranks of a W-rank job are played on ONE GPU through the C ABI, the two exchanges being done by hand exactly as
 `_SymW.exchange_forward / exchange_backward` do over NCCL (same layout object).  Every rank is compared with the
@@ -40,8 +40,8 @@ def cuda_ranks_symw(pkg, img, txt, dino, student, scale, W):
     fscr = [torch.empty(pl.fwd_scratch_numel, dtype=torch.float32, device=dev) for pl in plans]
     losses = [torch.empty(6, dtype=torch.float32, device=dev) for _ in plans]
     for r, pl in enumerate(plans):
-        be.forward(pl, gathered, ls, LAMBDAS, states[r], fscr[r], lse_all[r], losses[r], phase=1)
-        be.forward(pl, gathered, ls, LAMBDAS, states[r], fscr[r], lse_all[r], losses[r], phase=3)
+        for phase in (4, 3, 1):  # the CLIP part needs the operand statistics only
+            be.forward(pl, gathered, ls, LAMBDAS, states[r], fscr[r], lse_all[r], losses[r], phase=phase)
     # ---- forward exchange: column sums of primed block k -> rank (r + k) % W
     inbox = [torch.zeros((6, b), dtype=torch.float32, device=dev) for _ in plans]
     for r, pl in enumerate(plans):
@@ -61,7 +61,7 @@ def cuda_ranks_symw(pkg, img, txt, dino, student, scale, W):
         d_student = torch.empty((b, Dp), dtype=torch.float32, device=dev) if Dp else None
         d_scale = torch.empty(1, dtype=torch.float32, device=dev)
         outs.append((d_image, d_text, d_student, d_scale))
-        for phase in (1, 3):
+        for phase in (4, 3, 1):
             be.backward(pl, gathered, states[r], scr[r], lse_all, gout, LAMBDAS, d_image, d_text, d_student, d_scale,
                         phase=phase)
     # the receive lists must mirror the send lists
@@ -87,7 +87,8 @@ def cuda_ranks_symw(pkg, img, txt, dino, student, scale, W):
 
 
 @pytest.mark.parametrize("W,b,proj", [(2, 512, True), (4, 512, False), (8, 512, True), (3, 512, False), (2, 1024, False)])
-def test_every_rank_against_oracle(pkg, oracle, W, b, proj):
+def test_every_rank_against_oracle(pkg, oracle, W, b, proj, monkeypatch):
+    monkeypatch.setenv("DSOFT_SYM_W", "1")  # small blocks: the plan would not share the tiles on its own
     D, Dd = 128, 192
     B, scale = W * b, 30.0
     img, txt, dino = synth(57 + W, B, D, Dd)

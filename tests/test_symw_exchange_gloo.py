@@ -68,9 +68,9 @@ def _worker(rank, W, port, b, Dz, Dx, ret):
     j = torch.arange(sw.Bcol, dtype=torch.float32)
     for q in range(6):
         cs[q] = colsum_value(rank, j) + 1000.0 * q
-    with sw.beside(dev):
-        sw.exchange_forward(fscr, None)
-    sw.rejoin(dev)
+    order = []
+    sw.run(dev, 1, order.append, lambda: (order.append("x"), sw.exchange_forward(fscr, None)))
+    assert order == [4, 1, "x", 3, 2]
     # ---- backward: transposed products
     scr = torch.full((numel,), -3.0)
     for which, d in ((0, Dz), (1, Dx)):
