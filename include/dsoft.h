@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DSOFT_VERSION 210 /* 0.2.1 */
+#define DSOFT_VERSION 220 /* 0.2.2: phase 4 of the phased calls, dsoft_plan_concurrency */
 
 /* error codes */
 #define DSOFT_EINVAL (-1)  /* bad argument / unsupported shape            */
