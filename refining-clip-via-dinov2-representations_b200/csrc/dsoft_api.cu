@@ -221,9 +221,10 @@ extern "C" int dsoft_plan_create(const dsoft_shape_t* sh, dsoft_plan_t** out) {
   p->s_ncols = p->soft_local ? sh->b : p->B;
   {
     // DSOFT_SYM_W: 0 = never, 1 = whenever the plan allows it, unset = only for per-rank blocks above 2^28 similarity
-    // entries.  Below that the step is bound by the host (Python + ctypes + NCCL enqueue, ~2.5 ms per step), and the
-    // two extra exchanges cost more host time than the halved soft tiles save on the GPU: global batch 32768 on
-    // 8 GPUs 2.56 ms with the shared tiles against 2.47 ms without, on 2 GPUs 7.4 ms against 8.85 ms.
+    // entries.  Below that the step is a few milliseconds of short kernels and the two extra exchanges (about 25
+    // small torch / NCCL calls per step) cost the eager step more than the halved soft tiles save: global batch 32768
+    // on 8 GPUs 2.56 ms with the shared tiles against 2.47 ms without (4 GPUs: 5.29 against 4.41 ms; replayed as a
+    // CUDA graph 4.20 ms), on 2 GPUs 7.4 ms against 8.85 ms.  DESIGN.md section 6.
     const char* e = getenv("DSOFT_SYM_W");
     const bool big = static_cast<double>(sh->b) * p->B > 268435456.0;
     p->sym_w = soft && sh->world > 1 && !p->soft_local && !p->row_only && (sh->flags & DSOFT_F_GMAT) &&
