@@ -188,10 +188,12 @@ class _SymW:
         for which in ((0, 1) if self.Dx else (0,)):
             rem, own = self.remote(scratch, which), self.own(scratch, which)
             for peer, k, rows in self.sends:
-                ops.append(dist.P2POp(dist.isend, rem[(k - 1) * self.b:(k - 1) * self.b + rows], peer, group))
+                # peers are ranks WITHIN the loss's process group (the module's `rank` / `world_size`)
+                ops.append(dist.P2POp(dist.isend, rem[(k - 1) * self.b:(k - 1) * self.b + rows], group=group,
+                                      group_peer=peer))
             for peer, k, rows in self.recvs:
                 buf = torch.empty((rows, rem.shape[1]), dtype=torch.float32, device=rem.device)
-                ops.append(dist.P2POp(dist.irecv, buf, peer, group))
+                ops.append(dist.P2POp(dist.irecv, buf, group=group, group_peer=peer))
                 landed.append((own, rows, buf))
         for req in dist.batch_isend_irecv(ops):
             req.wait()

@@ -51,13 +51,22 @@ def remote_value(s, which, row, col):  # rank s's transposed product, row of the
     return (1 + which) * (100.0 * s + 0.01 * row) + 1e-4 * col
 
 
-def _worker(rank, W, port, b, Dz, Dx, ret):
+def _worker(rank, W, port, b, Dz, Dx, ret, members=None):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=W)
+    dist.init_process_group("gloo", rank=rank, world_size=W if members is None else max(members) + 1)
     torch.set_num_threads(1)
     from dinosoft_b200.loss import _SymW
+
+    group = None
+    if members is not None:  # the loss lives in a sub-group: ranks and peers are group-relative
+        group = dist.new_group(members)
+        if rank not in members:
+            dist.barrier()
+            dist.destroy_process_group()
+            return
+        rank = members.index(rank)
 
     info, fwd_numel, numel = layout(W, rank, b, Dz, Dx)
     sw = _SymW(info, W, rank)
@@ -69,7 +78,7 @@ def _worker(rank, W, port, b, Dz, Dx, ret):
     for q in range(6):
         cs[q] = colsum_value(rank, j) + 1000.0 * q
     order = []
-    sw.run(dev, 1, order.append, lambda: (order.append("x"), sw.exchange_forward(fscr, None)))
+    sw.run(dev, 1, order.append, lambda: (order.append("x"), sw.exchange_forward(fscr, group)))
     assert order == [4, 1, "x", 3, 2]
     # ---- backward: transposed products
     scr = torch.full((numel,), -3.0)
@@ -81,19 +90,21 @@ def _worker(rank, W, port, b, Dz, Dx, ret):
         cols = torch.arange(d, dtype=torch.float32)[None, :]
         rem.copy_(remote_value(rank, which, rows, cols))
         sw.own(scr, which).fill_(0.5)
-    sw.exchange_backward(scr, None)
+    sw.exchange_backward(scr, group)
     ret[rank] = dict(colsum=sw.colsum(fscr).clone(), own=[sw.own(scr, w).clone() for w in ((0, 1) if Dx else (0,))],
                      guard=(float(fscr[0]), float(scr[0])), sends=list(sw.sends), recvs=list(sw.recvs))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("W,b,Dx", [(2, 8, 4), (3, 8, 4), (4, 8, 0), (8, 4, 4)])
-def test_exchanges(W, b, Dx):
+@pytest.mark.parametrize("W,b,Dx,members", [(2, 8, 4, None), (3, 8, 4, None), (4, 8, 0, None), (8, 4, 4, None),
+                                            (2, 8, 4, [0, 2])])
+def test_exchanges(W, b, Dx, members):
     Dz = 6
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(W, _free_port(), b, Dz, Dx, ret), nprocs=W, join=True)
+    nprocs = W if members is None else max(members) + 1
+    mp.spawn(_worker, args=(W, _free_port(), b, Dz, Dx, ret, members), nprocs=nprocs, join=True)
     # every unordered pair of row blocks is computed exactly once: rank r owns (r, r + k) for its primed blocks k
     owned = {}
     for r in range(W):
