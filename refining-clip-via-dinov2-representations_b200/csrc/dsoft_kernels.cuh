@@ -18,6 +18,8 @@
 // (w-4)/4).
 #pragma once
 
+#include <type_traits>
+
 #include "dsoft_ptx.cuh"
 
 namespace dsoft {
@@ -50,6 +52,7 @@ constexpr int MODE_WCE_LSE = 6;
 constexpr int MODE_WCE_DBG = 7;
 constexpr int MODE_WCE_G = 8;
 constexpr int MODE_SOFT_SYM = 9;  // forward soft statistics, world == 1: upper block triangle + column reductions
+constexpr int MODE_SOFT_SYM16 = 13;  // the same with a 16x256b TMEM load shape (4 rows per thread: short butterflies)
 constexpr int MODE_LINEAR = 11;   // projection head layer: out = act(A . W^T + bias) as bf16 (loss.py:214-238, 322-347)
 constexpr int MODE_PAIRS = 12;    // CLIP-blind pair statistics (open_clip_train/helpers.py:221-285): threshold counts
                                   // and candidate pairs over the upper triangle of two Gram matrices
@@ -268,6 +271,39 @@ __device__ __forceinline__ float warp_colsum32(float (&x)[32], int lane) {
   return x[0];
 }
 
+// Column sums for the 16x256b fragment layout: lane (g = lane / 4, c2 = lane % 4) holds x[2 j + e] = the sum over ITS
+// four rows of column 8 j + 2 c2 + e of a 32-column chunk; the sum over the eight row groups g comes out of three
+// butterfly stages (7 shuffles).  Lane (g, c2) returns the total of column 8 (g / 2) + 2 c2 + (g % 2).
+__device__ __forceinline__ float warp_colsum8(float2 (&x)[4], int lane) {
+  float v[8] = {x[0].x, x[0].y, x[1].x, x[1].y, x[2].x, x[2].y, x[3].x, x[3].y};
+  {
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int k = 0; k < 4; k += 2) {
+      const float s0 = up ? v[k] : v[k + 4], s1 = up ? v[k + 1] : v[k + 5];
+      const float k0 = up ? v[k + 4] : v[k], k1 = up ? v[k + 5] : v[k + 1];
+      const float2 r = pk_add(pk(k0, k1), pk(__shfl_xor_sync(0xffffffffu, s0, 16), __shfl_xor_sync(0xffffffffu, s1, 16)));
+      v[k] = r.x;
+      v[k + 1] = r.y;
+    }
+  }
+  {
+    const bool up = (lane & 8) != 0;
+    const float s0 = up ? v[0] : v[2], s1 = up ? v[1] : v[3];
+    const float k0 = up ? v[2] : v[0], k1 = up ? v[3] : v[1];
+    const float2 r = pk_add(pk(k0, k1), pk(__shfl_xor_sync(0xffffffffu, s0, 8), __shfl_xor_sync(0xffffffffu, s1, 8)));
+    v[0] = r.x;
+    v[1] = r.y;
+  }
+  {
+    const bool up = (lane & 4) != 0;
+    const float s0 = up ? v[0] : v[1];
+    const float k0 = up ? v[1] : v[0];
+    v[0] = k0 + __shfl_xor_sync(0xffffffffu, s0, 4);
+  }
+  return v[0];
+}
+
 // Column maxima over the 32 rows of a warp, same butterfly as warp_colsum32
 __device__ __forceinline__ float warp_colmax32(float (&x)[32], int lane) {
 #define DSOFT_CM_STAGE(O)                                               \
@@ -340,7 +376,8 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   constexpr bool kWce = (MODE >= MODE_WCE_STAT && MODE <= MODE_WCE_G);
   // "soft-like": 256-column tiles with several products per tile, staged per-column vectors, setmaxnreg
   constexpr bool kPairs = (MODE == MODE_PAIRS);  // two products per tile like the weighted-CE passes, no column vectors
-  constexpr bool kSoftMode = (MODE == MODE_SOFT || MODE == MODE_SOFT_G || MODE == MODE_SOFT_SYM || kWce || kPairs);
+  constexpr bool kSoftMode = (MODE == MODE_SOFT || MODE == MODE_SOFT_G || MODE == MODE_SOFT_SYM ||
+                              MODE == MODE_SOFT_SYM16 || kWce || kPairs);
   static_assert(!kSoftMode || CG == 2, "the soft modes are written for CTA pairs");
   // streaming mode: stages of (A box | B boxes); resident mode: 8 A boxes, then B-only stages
   const bool resident = P.resident != 0;
@@ -1406,6 +1443,157 @@ dsoft_fwd_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < 11; ++k) P.part[k * st + o] = acc[k];
         }
+      }
+    } else if constexpr (MODE == MODE_SOFT_SYM16) {
+      // ---------------------------------------------------------------- symmetric forward, 16x256b TMEM loads
+      // Same statistics as MODE_SOFT_SYM below (read its comment first), other register layout: tcgen05.ld
+      // 16x256b gives every thread FOUR rows (g, g + 8, g + 16, g + 24 of the warp's 32; g = lane / 4) and, per
+      // 32-column chunk, the columns 8 j + 2 c2 + {0, 1} (j = 0..3, c2 = lane % 4).  The column sums over the warp's
+      // rows then start with three in-register adds per column and need a three-stage butterfly over the eight row
+      // groups (warp_colsum8: 7 shuffles + 14 selects per quantity and chunk) instead of the five-stage one over 32
+      // lanes (31 + 62), which was about half of the MODE_SOFT_SYM epilogue.  Row sums: every thread accumulates its
+      // four rows per product and tile, the four lanes of a row group combine them (two xor stages) and lane c2 keeps
+      // row g + 8 c2, so the persistent accumulators stay one row per thread.
+      const float mt2 = P.scal[SC_ITT_L2], ms2 = P.scal[SC_ITS_L2], mx2 = P.scal[SC_ITX_L2];
+      const int g = lane >> 2, c2 = lane & 3;
+      const int wrow0 = rb * BM + q * 32;  // first local row of this warp
+      int lrow[4];
+      float rq[4], rz[4], rx[4];  // inverse norms of the thread's rows: DINO, student, text
+      const bool has_text = P.nprod == 3;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        lrow[i] = wrow0 + g + 8 * i;
+        const int gr = P.row0 + lrow[i];
+        rq[i] = P.rinv[0][gr];
+        rz[i] = P.rinv[1][gr];
+        rx[i] = has_text ? P.rinv[2][gr] : 0.f;
+      }
+      float zt = 0.f, aq = 0.f, ap = 0.f, ar = 0.f, zs = 0.f, zx = 0.f;  // row g + 8 c2
+      float w[128];  // teacher weights of the thread's 4 rows x 32 columns: [chunk c][half h][8 j + 4 rs + ... ]
+      const size_t cp_stride = static_cast<size_t>(P.cp_rows) * P.cp_pitch;
+      float* cp_row = P.colpart + static_cast<size_t>(rb * 4 + q) * P.cp_pitch;
+      const int mycol = 8 * (g >> 1) + 2 * c2 + (g & 1);  // the column of a chunk whose sum warp_colsum8 returns here
+      // sum over the two columns of a pair, then over the four lanes of the row group; lane c2 takes row c2
+      auto row_take = [&](const float2 (&a)[4]) {
+        float r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          r[i] = a[i].x + a[i].y;
+          r[i] += __shfl_xor_sync(0xffffffffu, r[i], 1);
+          r[i] += __shfl_xor_sync(0xffffffffu, r[i], 2);
+        }
+        return c2 == 0 ? r[0] : (c2 == 1 ? r[1] : (c2 == 2 ? r[2] : r[3]));
+      };
+      int it = 0;
+      for (int t = t0; t < t1; ++t, it += P.nprod) {
+        const int jt0 = t * CT + half * 128;
+        const bool ragged = jt0 + 128 > P.ncols;
+        const bool offdiag = t > (rb >> 1);  // this tile also serves the rows of its column block
+        const int cb = (t - t0) % COL_BUFS;
+        mbar_wait(smem_u32(&col_full[cb]), static_cast<uint32_t>((t - t0) / COL_BUFS) & 1);
+        const float* cv = colbuf + cb * COL_VECS * CT + half * 128;
+        // one product of the tile; kT: the teacher product (writes w, masks its diagonal), else student / text
+        auto product = [&](auto kT_, const int p) {
+          constexpr bool kT = decltype(kT_)::value;
+          const int slot = (it + p) % 2;
+          mbar_wait(smem_u32(&s_full[slot]), static_cast<uint32_t>((it + p) / 2) & 1);
+          tc_fence_after();
+          const float mfix = kT ? mt2 : ((p == 1) ? ms2 : mx2);
+          float2 fr[4], bias[4];  // per row: (1 / norm) * log2(e) / tau, and -M (dead row: -1e30, so 2^arg = 0)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            fr[i] = pk1((kT ? rq[i] : ((p == 1) ? rz[i] : rx[i])) * mfix);
+            bias[i] = pk1(lrow[i] < P.b ? -mfix : NEG_BIG);
+          }
+          float2 a0[4], a1[4];  // per row: sum of the exponentials, sum of w * arg
+#pragma unroll
+          for (int i = 0; i < 4; ++i) a0[i] = a1[i] = pk1(0.f);
+          const uint32_t tbase = lane_addr + slot * CT + half * 128;
+          uint32_t rA[16], rB[16];
+          tmem_ld16x256_nowait(tbase, rA);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int jrel0 = jt0 + c * 32;
+            const bool rag = ragged && jrel0 + 32 > P.ncols;
+            // the teacher diagonal (column == local row, primed coordinates) can only lie in a chunk that overlaps
+            // the warp's rows; diagonal tiles always take the masked path (cheap: one tile per row pair)
+            const bool need_mask = (kT && ((wrow0 < jrel0 + 32 && jrel0 < wrow0 + 32) || !offdiag)) || rag;
+            float2 cs0[4], cs1[4];  // per column pair j: sums over the thread's four rows
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cs0[j] = cs1[j] = pk1(0.f);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t(&rcur)[16] = (h == 0) ? rA : rB;
+              uint32_t(&rnxt)[16] = (h == 0) ? rB : rA;
+              tmem_ld_wait16(rcur);
+              if (h == 0) {
+                tmem_ld16x256_nowait(tbase + (16u << 16) + c * 32, rnxt);
+              } else if (c < 3) {
+                tmem_ld16x256_nowait(tbase + (c + 1) * 32, rnxt);
+              } else {
+                tc_fence_before();
+                release_slot(slot);
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 rr = *reinterpret_cast<const float2*>(cv + p * CT + c * 32 + 8 * j + 2 * c2);
+                const int col = jrel0 + 8 * j + 2 * c2;
+#pragma unroll
+                for (int rs = 0; rs < 2; ++rs) {
+                  const int i = 2 * h + rs;
+                  const int wi = c * 32 + h * 16 + 4 * j + 2 * rs;
+                  const float2 arg = pk_fma(pk(__uint_as_float(rcur[4 * j + 2 * rs]),
+                                               __uint_as_float(rcur[4 * j + 2 * rs + 1])),
+                                            pk_mul(fr[i], rr), bias[i]);
+                  float2 ex = pk_exp2(arg);
+                  if (need_mask) {  // ragged columns; teacher: the diagonal (loss.py:376-377)
+                    if (col >= P.ncols || (kT && col == lrow[i])) ex.x = 0.f;
+                    if (col + 1 >= P.ncols || (kT && col + 1 == lrow[i])) ex.y = 0.f;
+                  }
+                  float2 wa;
+                  if constexpr (kT) {
+                    w[wi] = ex.x;
+                    w[wi + 1] = ex.y;
+                    wa = pk_mul(ex, arg);
+                  } else {
+                    wa = pk_mul(pk(w[wi], w[wi + 1]), arg);  // w is zero on masked entries and in dead rows
+                  }
+                  a0[i] = pk_add(a0[i], ex);
+                  a1[i] = pk_add(a1[i], wa);
+                  cs0[j] = pk_add(cs0[j], ex);
+                  cs1[j] = pk_add(cs1[j], wa);
+                }
+              }
+            }
+            if (offdiag) {  // warp-uniform
+              const float s0 = warp_colsum8(cs0, lane);
+              const float s1 = warp_colsum8(cs1, lane);
+              // quantities as in MODE_SOFT_SYM: [0] teacher sum, [1] sum w q, [2] sum w p, [3] sum w r,
+              // [4] student sum, [5] text sum
+              const int k0 = kT ? 0 : ((p == 1) ? 4 : 5);
+              const int k1 = kT ? 1 : ((p == 1) ? 2 : 3);
+              cp_row[k0 * cp_stride + jrel0 + mycol] = s0;
+              cp_row[k1 * cp_stride + jrel0 + mycol] = s1;
+            }
+          }
+          const float t0s = row_take(a0), t1s = row_take(a1);
+          if (kT) { zt += t0s; aq += t1s; } else if (p == 1) { zs += t0s; ap += t1s; } else { zx += t0s; ar += t1s; }
+        };
+        product(std::true_type{}, 0);
+        for (int p = 1; p < P.nprod; ++p) product(std::false_type{}, p);
+        mbar_arrive(smem_u32(&col_empty[cb]));
+      }
+      const int myrow = wrow0 + g + 8 * c2;
+      if (myrow < P.b) {  // same partial layout as MODE_SOFT; the maximum is the fixed one
+        const int o = sp * P.b + myrow;
+        const int st = P.npart * P.b;
+        P.part[0 * st + o] = mt2;
+        P.part[1 * st + o] = zt;
+        P.part[2 * st + o] = aq;
+        P.part[3 * st + o] = ap;
+        P.part[4 * st + o] = ar;
+        P.part[5 * st + o] = zs;
+        P.part[6 * st + o] = zx;
       }
     } else if constexpr (MODE == MODE_SOFT_SYM) {
       // ---------------------------------------------------------------- symmetric forward (world == 1)

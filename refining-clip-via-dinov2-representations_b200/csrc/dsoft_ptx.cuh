@@ -376,6 +376,28 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
                : "memory");
 }
 
+// 16 lanes x 256 bits, four repeats = a 16-row x 32-column fp32 block per instruction.  Thread t holds, for the
+// 8-column group j = 0..3:  r[4j], r[4j+1] = row (t / 4), columns 8j + 2 (t % 4) + {0, 1};  r[4j+2], r[4j+3] = row
+// (t / 4) + 8, same columns (the accumulator-fragment layout of mma.m16n8).  The lane field of `taddr` selects the
+// first of the 16 lanes (a warp reaches the 32 lanes of its quadrant: + 16 for the second half).
+__device__ __forceinline__ void tmem_ld16x256_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
+                 "+r"(r[15])
+               :
+               : "memory");
+}
+
 // L2 eviction policies for bulk-tensor traffic.  The logit-gradient kernels write gigabytes of G tiles that are not
 // read again before the gradient GEMM, next to a few hundred megabytes of operands that every CTA re-reads: without
 // hints the stores pushed the operands out of L2 (hit rate 38 - 57 %, MMA issuer starved for operands).
