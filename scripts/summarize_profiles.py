@@ -120,13 +120,14 @@ def full_summary(tag, rep=None, out_name=None):
 def traffic_table(tag, summary=None):
     """profiles/ncu_traffic.csv (read by bench.py for `roofline.traffic`): DRAM bytes read + written per launch of
     the default workload's tile kernels, keyed by bench.py's kernel names.  One step at world 1 launches, in order:
-    soft forward <9>, CLIP forward <10>, soft G <4>, student GEMM, text GEMM, CLIP G <3>, image GEMM, text^T GEMM."""
+    soft forward <13> (32x32b form: <9>), CLIP forward <10>, soft G <4>, student GEMM, text GEMM, CLIP G <3>, image GEMM, text^T GEMM."""
     summary = summary or os.path.join(PROF, f"{tag}_ncu_full_tile_kernels.csv")
     if not os.path.exists(summary):
         return
     with open(summary) as f:
         rows = list(csv.DictReader(l for l in f if not l.startswith('"#')))
-    names = {"dsoft_fwd_kernel<9, 2>": ["fwd_soft"], "dsoft_fwd_kernel<10, 2>": ["fwd_clip_i2t"],
+    names = {"dsoft_fwd_kernel<9, 2>": ["fwd_soft"], "dsoft_fwd_kernel<13, 2>": ["fwd_soft"],
+             "dsoft_fwd_kernel<10, 2>": ["fwd_clip_i2t"],
              "dsoft_fwd_kernel<4, 2>": ["bwd_build_g_soft"], "dsoft_fwd_kernel<3, 2>": ["bwd_build_g_clip"],
              "dsoft_gy_kernel<0>": ["bwd_student", "bwd_text", "bwd_clip_image"], "dsoft_gy_kernel<1>": ["bwd_clip_text"]}
     sha = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
