@@ -610,7 +610,10 @@ def run_ours(args):
                          "executed_tflops": kern[dom]["exec_tflops"],
                          "executed_frac": round(kern[dom]["exec_tflops"] / peak_sust, 4),
                          "note": "achieved = algorithmic FLOPs of this launch (SURVEY 8d: each distinct product "
-                                 "once, tile recompute not counted) / its CUDA-event duration"},
+                                 "once, Gram symmetry not discounted, tile recompute not counted) / its CUDA-event "
+                                 "duration; a launch that exploits the symmetry executes about half of them, so frac "
+                                 "can exceed 1: executed_frac is the utilisation of the launch, step_roofline the "
+                                 "figure for the whole step"},
             "step_roofline": {"algorithmic_tflops_per_gpu": round(step_alg_tflops, 1),
                               "frac_of_sustained_peak": round(step_alg_tflops / peak_sust, 4),
                               "frac_of_burst_peak": round(step_alg_tflops / peak_burst, 4) if peak_burst else None,
