@@ -62,6 +62,8 @@ def _worker(rank, world, port, B, D, Dd, scale, argd, ctor, ret, gmat):
     (dict(local_loss=True, gather_with_grad=True, soft_scope="global"), dict(use_projection=True)),
     (dict(local_loss=True, gather_with_grad=True, soft_scope="local"), dict(use_projection=False)),
     (dict(local_loss=True, gather_with_grad=False, soft_scope="global"), dict(use_projection=False)),
+    # detached gathered copies, local soft block: the column-side soft terms stay live (round-1 ADVICE item)
+    (dict(local_loss=True, gather_with_grad=False, soft_scope="local"), dict(use_projection=False)),
 ])
 @pytest.mark.parametrize("gmat", ["always", "never"], ids=["two_phase", "fused"])
 def test_two_gpu_parity(oracle, ctor, argd, gmat):
